@@ -1,0 +1,236 @@
+"""Generate tests/golden/* by RUNNING THE REFERENCE in the build container.
+
+    python -m oracle.gen_golden            (needs /root/reference; never runs on the GPU box)
+
+What it pins:
+  select_kat.json      -- A8: the reference's inline selection statements are read from
+                          /root/reference/src/models/LSTP_SF_blip2_module.py (eval :431-459, train :282-312),
+                          LSTP_module.py (ratio mapping) and executed unmodified on real 0-dim int64 tensors.
+  gumbel.npz           -- A7: F.gumbel_softmax(...).argmax with a fixed torch seed, plus the explicit noise.
+  transform.npz        -- A0: reference ToTensorVideo/NormalizeVideo on random u8 frames.
+  vit_small.npz ...    -- A10-A16, A1-A6: the reference classes (through reference_shim) loaded with the
+                          seeded synthetic state dicts, fp32, small inputs.  Outputs stored as fp16-safe fp32
+                          slices + full-tensor statistics to keep fixtures small.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import textwrap
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import reference_shim                       # noqa: E402
+from videotgb_b200 import synthetic as syn                # noqa: E402
+
+REF = reference_shim.REFERENCE_ROOT
+
+
+def _ref_lines(rel, lo, hi):
+    with open(os.path.join(REF, rel)) as f:
+        lines = f.readlines()[lo - 1: hi]
+    return textwrap.dedent("".join(lines))
+
+
+def _run_reference_selection(src, cand_start_index, cand_end_index, of_lengths, num_frames, nframe):
+    """Execute the reference's `for j in range(len(video_lengths))` loop body source `src`."""
+    b = len(of_lengths)
+    pixel_values = torch.arange(b * num_frames, dtype=torch.float32).view(b, num_frames, 1, 1, 1)
+    sampled = torch.zeros(b, nframe, 1, 1, 1)
+    env = dict(torch=torch, np=np, batch={"of_lengths": list(of_lengths)}, cand_start_index=cand_start_index,
+               cand_end_index=cand_end_index, num_frames=num_frames, nframe=nframe, pixel_values=pixel_values,
+               sampled_pixel_values=sampled, video_lengths=list(of_lengths))
+    exec(src, env)
+    idx = (env["sampled_pixel_values"].view(b, nframe) - torch.arange(b).view(b, 1) * num_frames).long()
+    return idx.tolist()
+
+
+def gen_select():
+    eval_src = _ref_lines("src/models/LSTP_SF_blip2_module.py", 433, 461)
+    train_src = _ref_lines("src/models/LSTP_SF_blip2_module.py", 284, 314)
+    ratio_src = _ref_lines("src/models/LSTP_module.py", 233, 263)
+    assert "range(start, end)" in eval_src and "range(start, (end+1))" in train_src
+    assert "cand_start/video_length*num_frames" in ratio_src
+    # (the ratio variant hard-codes video_length = num_frames + 2)
+    cases = []
+    rng = np.random.default_rng(20240917)
+
+    def add(name, src, variant, draws, lengths, n, k):
+        cs = [torch.tensor([d[i][0] for d in draws]) for i in range(len(draws[0]))]
+        ce = [torch.tensor([d[i][1] for d in draws]) for i in range(len(draws[0]))]
+        out = _run_reference_selection(src, cs, ce, lengths, n, k)
+        cases.append(dict(name=name, variant=variant, draws=draws, of_lengths=list(map(int, lengths)),
+                          num_frames=n, nframe=k, expect=out))
+
+    # hand-written corner cases, one video each, two draws
+    hand = [
+        ("fallback", [[(0, 0), (0, 0)]], [64], 32, 4),
+        ("two_spans", [[(10, 30), (40, 50)]], [64], 32, 4),
+        ("reversed_degenerate", [[(30, 10), (5, 6)]], [64], 32, 4),
+        ("tiny_doubling", [[(20, 22), (20, 22)]], [64], 32, 4),
+        ("out_of_range", [[(70, 10), (3, 9)]], [64], 32, 4),
+        ("long_video", [[(100, 400), (350, 700)]], [1024], 1024, 32),
+        ("exact_k", [[(0, 9), (0, 9)]], [32], 32, 4),
+        ("len2", [[(0, 1), (1, 1)]], [2], 32, 4),
+    ]
+    for name, draws, lengths, n, k in hand:
+        add(name + "_eval", eval_src, "eval", draws, lengths, n, k)
+        add(name + "_train", train_src, "train", draws, lengths, n, k)
+    # random batches incl. padded positions being drawn (index >= of_length)
+    for t in range(40):
+        b = int(rng.integers(1, 9))
+        lof = int(rng.choice([8, 32, 64, 128, 510, 1024]))
+        n = int(rng.choice([8, 32, 64, lof]))
+        k = int(rng.choice([1, 4, 8, 32]))
+        lengths = [int(x) for x in rng.integers(2, lof + 1, size=b)]
+        draws = [[(int(rng.integers(0, lof)), int(rng.integers(0, lof))) for _ in range(2)] for _ in range(b)]
+        add(f"rand{t}_eval", eval_src, "eval", draws, lengths, n, k)
+        add(f"rand{t}_train", train_src, "train", draws, lengths, n, k)
+    for t in range(20):
+        b = int(rng.integers(1, 5))
+        n = int(rng.choice([8, 32, 64]))
+        k = int(rng.choice([4, 8, 32]))
+        draws = [[(int(rng.integers(0, n + 2)), int(rng.integers(0, n + 2))) for _ in range(2)] for _ in range(b)]
+        add(f"rand{t}_ratio", ratio_src, "ratio", draws, [n + 2] * b, n, k)
+    with open(os.path.join(GOLD, "select_kat.json"), "w") as f:
+        json.dump(cases, f)
+    print("select cases:", len(cases))
+
+
+def gen_gumbel():
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    for tag, (b, l) in {"a": (4, 32), "b": (3, 130), "c": (2, 1024)}.items():
+        start = torch.randn(b, l, 1, generator=g)
+        end = torch.randn(b, l, 1, generator=g)
+        logits = torch.cat([start, end], dim=0)
+        torch.manual_seed(100 + l)
+        state = torch.get_rng_state()
+        prob = F.gumbel_softmax(logits, tau=0.5, dim=1)                 # the reference statement (:425)
+        index = prob.argmax(dim=1)
+        torch.set_rng_state(state)
+        gum = -torch.empty_like(logits, memory_format=torch.legacy_contiguous_format).exponential_().log()
+        out[f"{tag}_start"] = start.numpy(); out[f"{tag}_end"] = end.numpy()
+        out[f"{tag}_gumbel"] = gum.numpy(); out[f"{tag}_index"] = index.numpy()
+    np.savez_compressed(os.path.join(GOLD, "gumbel.npz"), **out)
+
+
+def gen_transform():
+    from src.gadgets import transforms as T
+    u8 = syn.synthetic_frames_u8(3, 32, seed=5)
+    u8[0, 0, 0] = torch.tensor([0, 255, 128], dtype=torch.uint8)
+    ref = T.NormalizeVideo((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))(
+        T.ToTensorVideo()(u8)).permute(1, 0, 2, 3).contiguous()
+    # full chain from a float CTHW clip of another size (resize -> uint8 truncation)
+    g = torch.Generator().manual_seed(9)
+    clip = torch.rand(3, 2, 20, 28, generator=g) * 255.0
+    chain = T.ToTHWC()(T.ToUint8()(T.ResizeVideo(16)(clip)))
+    np.savez_compressed(os.path.join(GOLD, "transform.npz"), u8=u8.numpy(), norm=ref.numpy(), clip=clip.numpy(),
+                        clip_u8=chain.contiguous().numpy())
+
+
+def _summ(t: torch.Tensor, stride: int = 7):
+    t = t.detach().float()
+    return dict(shape=list(t.shape), mean=float(t.mean()), std=float(t.std()), absmax=float(t.abs().max())), \
+        t.flatten()[::stride].clone().numpy()
+
+
+def gen_models():
+    reference_shim.install()
+    from transformers import BertConfig, Blip2QFormerConfig, Blip2VisionConfig, InstructBlipQFormerConfig
+    from src.models.components.xblip2 import Blip2QFormerModel, Blip2VisionModel
+    from src.models.components.xinstructblip import InstructBlipQFormerModel
+    from src.models.components.xropebert import RopeBertModel
+    meta, arrays = {}, {}
+    torch.manual_seed(0)
+
+    def load(model, sd):
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected, unexpected
+        assert not [m for m in missing if "position_ids" not in m], missing
+        return model.eval()
+
+    # ---- ViT: full width, 2 layers (fast) and the full 39 layers on 1 frame
+    for tag, layers, nf in (("vit2", 2, 2), ("vit39", 39, 1)):
+        cfg = syn.VisionCfg(layers=layers)
+        sd = syn.vision_state_dict(cfg)
+        m = load(Blip2VisionModel(Blip2VisionConfig(num_hidden_layers=layers)), sd)
+        assert abs(m.config.layer_norm_eps - cfg.eps) < 1e-12
+        u8 = syn.synthetic_frames_u8(nf, seed=11)
+        from oracle.transform_ref import normalize_u8_thwc
+        px = torch.from_numpy(normalize_u8_thwc(u8.numpy()))
+        with torch.no_grad():
+            out = m(pixel_values=px, return_dict=True)
+        meta[tag + "_last"], arrays[tag + "_last"] = _summ(out.last_hidden_state)
+        meta[tag + "_pool"], arrays[tag + "_pool"] = _summ(out.pooler_output, 1)
+        if tag == "vit2":
+            img = out.last_hidden_state
+    # ---- BLIP-2 Q-Former (12 layers) on the 2 frames above + projection
+    qcfg = syn.QFormerCfg()
+    qsd = syn.qformer_state_dict(qcfg)
+    hsd = syn.head_state_dict()
+    qm = load(Blip2QFormerModel(Blip2QFormerConfig()), qsd)
+    assert abs(qm.config.layer_norm_eps - 1e-12) < 1e-20 and qm.config.cross_attention_frequency == 2
+    qt = hsd["query_tokens"].expand(img.shape[0], -1, -1)
+    with torch.no_grad():
+        qo = qm(query_embeds=qt, encoder_hidden_states=img,
+                encoder_attention_mask=torch.ones(img.shape[:2], dtype=torch.long))[0]
+        proj = torch.nn.functional.linear(qo, hsd["language_projection.weight"], hsd["language_projection.bias"])
+    meta["qf_out"], arrays["qf_out"] = _summ(qo, 3)
+    meta["qf_proj"], arrays["qf_proj"] = _summ(proj.reshape(1, -1, proj.shape[-1]), 5)
+    # ---- InstructBLIP Q-Former with padded instruction text
+    icfg = syn.QFormerCfg(instruct=True)
+    isd = syn.qformer_state_dict(icfg)
+    im = load(InstructBlipQFormerModel(InstructBlipQFormerConfig()), isd)
+    g = torch.Generator().manual_seed(21)
+    ids = torch.randint(1000, 30522, (1, 12), generator=g).repeat_interleave(img.shape[0], 0)
+    tmask = torch.ones(img.shape[0], 12, dtype=torch.long); tmask[:, 9:] = 0
+    amask = torch.cat([torch.ones(img.shape[0], 32, dtype=torch.long), tmask], dim=1)
+    with torch.no_grad():
+        io = im(input_ids=ids, attention_mask=amask, query_embeds=qt, encoder_hidden_states=img,
+                encoder_attention_mask=torch.ones(img.shape[:2], dtype=torch.long), return_dict=True).last_hidden_state
+    arrays["iq_ids"] = ids.numpy(); arrays["iq_mask"] = amask.numpy()
+    meta["iq_out"], arrays["iq_out"] = _summ(io, 3)
+    # ---- sampler, both modes, padded flow + padded question
+    scfg = syn.SamplerCfg()
+    ssd = syn.sampler_state_dict(scfg)
+    sm = load(RopeBertModel(BertConfig(fusion_layer=6, encoder_width=768)), ssd)
+    b, lof, tq = 2, 12, 9
+    of = syn.synthetic_flow(b, lof, seed=31)
+    of_len = [12, 7]
+    of_mask = torch.zeros(b, lof + 2, dtype=torch.long)
+    for j, n in enumerate(of_len):
+        of_mask[j, : n + 2] = 1
+    qids = torch.randint(1000, 30522, (b, tq), generator=g)
+    qmask = torch.ones(b, tq, dtype=torch.long); qmask[1, 6:] = 0
+    arrays["s_qids"] = qids.numpy(); arrays["s_qmask"] = qmask.numpy(); arrays["s_ofmask"] = of_mask.numpy()
+    for mode in ("fusion", "multi_modal"):
+        with torch.no_grad():
+            seq, logits = sm(encoder_embeds=of, attention_mask=of_mask, encoder_hidden_states=qids,
+                             encoder_attention_mask=qmask, mode=mode)
+        meta[f"s_{mode}_seq"], arrays[f"s_{mode}_seq"] = _summ(seq, 3)
+        meta[f"s_{mode}_logits"], arrays[f"s_{mode}_logits"] = _summ(logits, 1)
+    with torch.no_grad():
+        emb = sm.temporal_embeddings(of, of_mask)
+    meta["s_ofembed"], arrays["s_ofembed"] = _summ(emb, 1)
+    np.savez_compressed(os.path.join(GOLD, "models.npz"), **arrays)
+    with open(os.path.join(GOLD, "models_meta.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print(json.dumps({k: v for k, v in meta.items()}, indent=0)[:2000])
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    reference_shim.install()
+    which = sys.argv[1:] or ["select", "gumbel", "transform", "models"]
+    for w in which:
+        globals()["gen_" + w]()
+        print("generated", w)
