@@ -1,0 +1,293 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (videotgb_b200.ops -> ctypes)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import select_ref, transform_ref
+from videotgb_b200 import ops
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+
+def _relerr(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def _cos(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return torch.dot(a, b).item() / (a.norm().item() * b.norm().item() + 1e-30)
+
+
+# ------------------------------------------------------------------------------------------------ A0
+def test_normalize_bit_exact():
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (5, 224, 224, 3), generator=g, dtype=torch.uint8)
+    u8[0, 0, 0] = torch.tensor([0, 255, 128], dtype=torch.uint8)
+    want = transform_ref.normalize_u8_thwc(u8.numpy())
+    got = ops.normalize_frames_u8(u8.to(DEV)).cpu().numpy()
+    assert np.array_equal(got, want)
+    z = np.load(os.path.join(GOLDEN, "transform.npz"))                       # reference-generated fixture
+    got = ops.normalize_frames_u8(torch.from_numpy(z["u8"]).to(DEV)).cpu().numpy()
+    assert np.array_equal(got, z["norm"])
+    # all 256 byte values x 3 channels
+    ramp = torch.arange(256, dtype=torch.uint8).view(1, 16, 16, 1).expand(1, 16, 16, 3).contiguous()
+    assert np.array_equal(ops.normalize_frames_u8(ramp.to(DEV)).cpu().numpy(), transform_ref.normalize_u8_thwc(ramp.numpy()))
+
+
+# ------------------------------------------------------------------------------------------------ A7
+def test_gumbel_argmax_golden_and_ties():
+    z = np.load(os.path.join(GOLDEN, "gumbel.npz"))
+    for tag in "abc":
+        s, e, g = (torch.from_numpy(z[f"{tag}_{k}"]) for k in ("start", "end", "gumbel"))
+        logits = torch.cat([s, e], 0)[..., 0].contiguous()
+        got = ops.gumbel_argmax(logits.to(DEV), g[..., 0].contiguous().to(DEV)).cpu()
+        assert torch.equal(got, torch.from_numpy(z[f"{tag}_index"])[:, 0])
+    # engineered exact ties: first index wins, as softmax(...).argmax does
+    logits = torch.zeros(4, 40)
+    gum = torch.zeros(4, 40)
+    logits[0, [7, 21]] = 3.0
+    logits[1, :] = 1.25
+    logits[2, [39, 38]] = 9.0
+    logits[3, 5] = 2.0; gum[3, 9] = 2.0
+    want = ((logits + gum) / 0.5).softmax(1).argmax(1)
+    got = ops.gumbel_argmax(logits.to(DEV), gum.to(DEV)).cpu()
+    assert torch.equal(got, want) and got.tolist() == [7, 0, 38, 5]
+    # random rows incl. long ones vs the oracle
+    g = torch.Generator().manual_seed(11)
+    for rows, length in ((64, 34), (8, 1026), (4, 4000)):
+        lg = torch.randn(rows, length, generator=g)
+        gm = -torch.empty(rows, length).exponential_(generator=g).log()
+        h = rows // 2
+        si, ei = select_ref.gumbel_argmax(lg[:h, :, None], lg[h:, :, None], gm[:, :, None])
+        assert torch.equal(ops.gumbel_argmax(lg.to(DEV), gm.to(DEV)).cpu(), torch.cat([si, ei]))
+
+
+# ------------------------------------------------------------------------------------------------ A8
+def _run_select(cases, **kw):
+    out = []
+    for c in cases:
+        draws = c["draws"]
+        b = len(draws)
+        top_k = len(draws[0])
+        cs = torch.tensor([[draws[j][i][0] for j in range(b)] for i in range(top_k)], dtype=torch.int64)
+        ce = torch.tensor([[draws[j][i][1] for j in range(b)] for i in range(top_k)], dtype=torch.int64)
+        ol = torch.tensor(c["of_lengths"], dtype=torch.int32)
+        got = ops.spans_to_indices(cs.to(DEV), ce.to(DEV), ol.to(DEV), c["num_frames"], c["nframe"], **kw(c))
+        out.append(got.cpu().tolist())
+    return out
+
+
+def test_spans_to_indices_reference_kat():
+    with open(os.path.join(GOLDEN, "select_kat.json")) as f:
+        kat = json.load(f)
+
+    def kw(c):
+        return dict(eval=dict(mapping=ops.MAP_SCALED, inclusive=False), train=dict(mapping=ops.MAP_SCALED, inclusive=True),
+                    ratio=dict(mapping=ops.MAP_RATIO, inclusive=False))[c["variant"]]
+    got = _run_select(kat, kw=kw)
+    for c, g in zip(kat, got):
+        assert g == c["expect"], (c["name"], g, c["expect"])
+
+
+def test_spans_to_indices_random_vs_oracle():
+    rng = np.random.default_rng(5)
+    for t in range(60):
+        b = int(rng.integers(1, 33))
+        lof = int(rng.choice([4, 32, 64, 510, 1024, 4000]))
+        n = int(rng.choice([8, 32, 64, 1024, 4096]))
+        k = int(rng.choice([1, 4, 32, 128]))
+        mapping = int(rng.integers(0, 2))
+        inclusive = bool(rng.integers(0, 2))
+        host_ints = bool(rng.integers(0, 2))
+        lengths = rng.integers(2, lof + 1, size=b)
+        cs = torch.from_numpy(rng.integers(0, lof, size=(2, b)))
+        ce = torch.from_numpy(rng.integers(0, lof, size=(2, b)))
+        if t % 5 == 0:
+            ce = torch.maximum(cs, ce)
+        want = select_ref.select_batch(list(cs), list(ce), lengths.tolist(), n, k,
+                                       mapping="scaled" if mapping == 0 else "ratio", inclusive=inclusive,
+                                       host_ints=host_ints)
+        got = ops.spans_to_indices(cs.to(DEV), ce.to(DEV), torch.from_numpy(lengths.astype(np.int32)).to(DEV), n, k,
+                                   mapping=mapping, inclusive=inclusive, host_ints=host_ints).cpu()
+        assert torch.equal(got, want), (t, b, lof, n, k, mapping, inclusive, host_ints)
+
+
+# ------------------------------------------------------------------------------------------------ A9
+def test_gather_bit_exact():
+    g = torch.Generator().manual_seed(2)
+    for (b, n, k, shape) in ((3, 16, 4, (3, 224, 224)), (2, 8, 8, (3, 32, 32)), (1, 64, 32, (3, 56, 56))):
+        px = torch.randn((b, n) + shape, generator=g)
+        idx = torch.sort(torch.randint(0, n, (b, k), generator=g), dim=1).values
+        want = select_ref.gather_frames(px, idx)
+        got = ops.gather_frames(px.to(DEV), idx.to(DEV)).cpu()
+        assert got.dtype == torch.float32 and torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        ops.gather_frames(torch.zeros(1, 2, 3, dtype=torch.float32, device=DEV), torch.zeros(1, 1, dtype=torch.int64, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------ A10
+def test_patchify_matches_unfold():
+    g = torch.Generator().manual_seed(4)
+    px = torch.randn(3, 3, 224, 224, generator=g)
+    want = torch.nn.functional.unfold(px, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    got = ops.patchify(px.to(DEV), 14, 592).cpu()
+    assert torch.equal(got[:, :588], want.to(torch.bfloat16)) and got[:, 588:].abs().max() == 0
+    u8 = torch.randint(0, 256, (2, 224, 224, 3), generator=g, dtype=torch.uint8)
+    norm = torch.from_numpy(transform_ref.normalize_u8_thwc(u8.numpy()))
+    want = torch.nn.functional.unfold(norm, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588).to(torch.bfloat16)
+    got = ops.patchify_u8(u8.to(DEV), 14, 592).cpu()
+    assert torch.equal(got[:, :588], want)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("m,n", [(257 * 3, 1408), (64, 768), (5, 2048), (1000, 128)])
+def test_layernorm(m, n):
+    g = torch.Generator().manual_seed(m + n)
+    x = torch.randn(m, n, generator=g) * 3 + 0.5
+    gamma = 1 + 0.1 * torch.randn(n, generator=g)
+    beta = 0.1 * torch.randn(n, generator=g)
+    for eps in (1e-6, 1e-12):
+        want = torch.nn.functional.layer_norm(x, (n,), gamma, beta, eps)
+        ob, of = ops.layernorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), eps, want_bf16=True, want_f32=True)
+        assert (of.cpu() - want).abs().max().item() < 2e-5
+        assert torch.equal(ob.cpu(), of.cpu().to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def _gemm_ref(a, w, bias):
+    y = a.double() @ w.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    return y
+
+
+GEMM_SHAPES = [
+    # (M, N, K, bn)
+    (128, 256, 64, 256), (128, 256, 128, 256), (256, 512, 256, 256), (300, 264, 200, 256),
+    (257 * 4, 1408, 1408, 0), (257 * 4, 1408, 1408, 176), (257 * 4, 1408, 1408, 128), (257 * 4, 4224, 1408, 0),
+    (1000, 6144, 1408, 256), (520, 1408, 6144, 0), (256 * 3, 1408, 592, 0), (96, 768, 768, 64), (4097, 768, 3072, 0),
+    (37, 2048, 768, 0), (128, 8, 64, 64),
+]
+
+
+@pytest.mark.parametrize("m,n,k,bn", GEMM_SHAPES)
+def test_gemm_bias_bf16(m, n, k, bn):
+    g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
+    a = (torch.randn(m, k, generator=g)).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(n, generator=g)
+    want = _gemm_ref(a, w, bias)
+    got = ops.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), ops.EPI_BF16, bn=bn).cpu()
+    assert got.shape == (m, n)
+    err = (got.double() - want).abs().max().item()
+    assert err <= 2 ** -7 * want.abs().max().item(), (err, want.abs().max().item())
+    assert _cos(got, want) > 0.99999
+
+
+def test_gemm_epilogues():
+    g = torch.Generator().manual_seed(99)
+    m, n, k = 777, 1408, 1408
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) * 0.03).to(torch.bfloat16)
+    bias = torch.randn(n, generator=g)
+    base = _gemm_ref(a, w, bias)
+    ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
+    # fp32 out
+    got = ops.gemm(ad, wd, bd, ops.EPI_F32).cpu().double()
+    assert (got - base).abs().max().item() < 2e-4 * base.abs().max().item()
+    # no bias
+    got = ops.gemm(ad, wd, None, ops.EPI_F32).cpu().double()
+    assert (got - (base - bias.double())).abs().max().item() < 2e-4 * base.abs().max().item()
+    # GELU(erf)
+    got = ops.gemm(ad, wd, bd, ops.EPI_BF16_GELU).cpu().double()
+    want = torch.nn.functional.gelu(base)
+    assert (got - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+    # residual, in place
+    resid = torch.randn(m, n, generator=g)
+    rd = resid.to(DEV)
+    out = ops.gemm(ad, wd, bd, ops.EPI_F32_RESID, out=rd, resid=rd).cpu().double()
+    assert (out - (base + resid.double())).abs().max().item() < 2e-4 * base.abs().max().item()
+    # residual, out of place with strides (column slice of a wider buffer)
+    wide = torch.zeros(m, n + 64, device=DEV)
+    ops.gemm(ad, wd, bd, ops.EPI_F32_RESID, out=wide[:, :n], resid=resid.to(DEV))
+    assert (wide[:, :n].cpu().double() - (base + resid.double())).abs().max().item() < 2e-4 * base.abs().max().item()
+    assert wide[:, n:].abs().max().item() == 0
+    # strided A (column slice) and row-bias epilogue with CLS-row skipping
+    m2, period = 256 * 3, 256
+    a2w = torch.randn(m2, 640, generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(n, 592, generator=g) * 0.03).to(torch.bfloat16)
+    rowbias = torch.randn(period, n, generator=g)
+    hidden = torch.full((3, 257, n), 7.0, device=DEV)
+    ops.gemm(a2w.to(DEV)[:, :592], w2.to(DEV), None, ops.EPI_F32_ROWBIAS, out=hidden.view(-1, n), rowbias=rowbias.to(DEV),
+             period=period, skip=1)
+    want = (a2w[:, :592].double() @ w2.double().t()).view(3, 256, n) + rowbias.double()
+    assert (hidden[:, 1:].cpu().double() - want).abs().max().item() < 2e-4 * want.abs().max().item()
+    assert (hidden[:, 0] == 7.0).all()
+
+
+def test_gemm_rejects_bad_arguments():
+    a = torch.zeros(8, 60, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(8, 60, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w)                       # K % 8 != 0
+    with pytest.raises(RuntimeError):
+        ops.gemm(a.float(), w)               # dtype
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, b, h, sq, sk, d, scale, mask=None):
+    qh = q.float().view(b, sq, h, d).permute(0, 2, 1, 3)
+    kh = k.float().view(b, sk, h, d).permute(0, 2, 1, 3)
+    vh = v.float().view(b, sk, h, d).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if mask is not None:
+        s = s + mask[:, None, None, :]
+    return (s.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(b * sq, h * d)
+
+
+@pytest.mark.parametrize("b,h,sq,sk,d,masked", [(3, 16, 257, 257, 88, False), (2, 12, 32, 257, 64, False),
+                                                (2, 12, 32, 32, 64, False), (3, 12, 44, 44, 64, True),
+                                                (2, 12, 160, 160, 64, True), (1, 12, 1, 17, 64, False),
+                                                (1, 16, 100, 64, 88, False)])
+def test_attention(b, h, sq, sk, d, masked):
+    g = torch.Generator().manual_seed(b + sq + sk)
+    if sq == sk:
+        qkv = torch.randn(b * sq, 3 * h * d, generator=g).to(torch.bfloat16)
+        q, k, v = qkv[:, : h * d], qkv[:, h * d: 2 * h * d], qkv[:, 2 * h * d:]
+    else:
+        q = torch.randn(b * sq, h * d, generator=g).to(torch.bfloat16)
+        kv = torch.randn(b * sk, 2 * h * d, generator=g).to(torch.bfloat16)
+        k, v = kv[:, : h * d], kv[:, h * d:]
+    mask = None
+    if masked:
+        mask = torch.zeros(b, sk)
+        for j in range(b):
+            mask[j, sk - 3 - 2 * j:] = -10000.0
+    scale = d ** -0.5
+    want = _attn_ref(q, k, v, b, h, sq, sk, d, scale, mask)
+    if sq == sk:
+        qd = qkv.to(DEV)
+        got = ops.attention(qd[:, : h * d], qd[:, h * d: 2 * h * d], qd[:, 2 * h * d:], b, h, sq, sk, d, scale,
+                            None if mask is None else mask.to(DEV))
+    else:
+        kvd = kv.to(DEV)
+        got = ops.attention(q.to(DEV), kvd[:, : h * d], kvd[:, h * d:], b, h, sq, sk, d, scale,
+                            None if mask is None else mask.to(DEV))
+    err = _relerr(got.cpu(), want)
+    assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
+
+
+def test_cast_and_group_mean():
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(77, 768, generator=g)
+    assert torch.equal(ops.cast_bf16(x.to(DEV)).cpu(), x.to(torch.bfloat16))
+    y = torch.randn(12, 32, 768, generator=g)
+    got = ops.group_mean(y.to(DEV), 3, 4).cpu()
+    want = torch.stack([y[i * 4:(i + 1) * 4].mean(0) for i in range(3)])
+    assert (got - want).abs().max().item() < 1e-6

@@ -1,0 +1,66 @@
+"""ctypes loader for libvideotgb_b200.so (the C ABI of include/videotgb_b200.h).
+
+The product path has no CPU or PyTorch fallback: if the library is missing (run `python -m videotgb_b200.build`
+or `__graft_entry__.build()`), or the device is not sm_100, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvideotgb_b200.so")
+
+TGB_OK, TGB_EINVAL, TGB_EARCH, TGB_ECUDA = 0, -1, -2, -3
+
+c_int, c_i64, c_f32, c_vp, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> argtypes; must list every symbol declared in include/videotgb_b200.h (tests/test_abi.py checks this)
+SIGNATURES = {
+    "tgb_last_error": ([], ctypes.c_char_p),
+    "tgb_version": ([], c_int),
+    "tgb_device_check": ([], c_int),
+    "tgb_sm_count": ([], c_int),
+    "tgb_normalize_frames_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
+    "tgb_gumbel_argmax": ([c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_vp], c_int),
+    "tgb_spans_to_indices": ([c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
+    "tgb_gather_frames": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_sz, c_vp], c_int),
+    "tgb_patchify_f32": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp], c_int),
+    "tgb_patchify_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
+    "tgb_fill_cls_rows": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp], c_int),
+    "tgb_gemm_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_int, c_int,
+                       c_vp, c_i64, c_int, c_vp], c_int),
+    "tgb_layernorm_f32": ([c_vp, c_i64, c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp], c_int),
+    "tgb_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int,
+                            c_int, c_f32, c_vp], c_int),
+    "tgb_cast_f32_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp], c_int),
+    "tgb_group_mean_f32": ([c_vp, c_vp, c_int, c_int, c_i64, c_vp], c_int),
+}
+
+_lib = None
+
+
+class TgbError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TgbError(f"{LIB_PATH} is missing -- build it with `python -m videotgb_b200.build`; there is no fallback path")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (args, res) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != TGB_OK:
+        msg = load().tgb_last_error().decode(errors="replace")
+        kind = {TGB_EINVAL: "invalid argument", TGB_EARCH: "unsupported device", TGB_ECUDA: "CUDA error"}.get(status, "error")
+        raise TgbError(f"videotgb_b200 {kind} ({status}): {msg}")

@@ -1,0 +1,264 @@
+// Fused attention  out = softmax(Q K^T * scale + mask) V  for the short sequences of this path
+// (ViT: S=257, d=88, 16 heads; Q-Former: 32(+Tt) queries x 32..257 keys, d=64, 12 heads).
+//
+// One CTA per (batch, head): K and V of that head are staged ONCE in shared memory with cp.async (16-byte, padded
+// pitches chosen so every ldmatrix phase is bank-conflict free), each warp owns 16-query-row tiles and runs a
+// flash-style online softmax over 64-key blocks: S = Q K^T with mma.sync.m16n8k16 (bf16 in, fp32 accumulate),
+// fp32 softmax statistics, P re-used from the accumulator registers as the A operand of P V.  The score matrix
+// never reaches HBM (the reference materialises [F,16,257,257], xblip2.py:174-189).
+//
+// TODO(round 2): move QK^T / PV to tcgen05 with S in TMEM; at 2.8 % of the path's FLOPs this kernel is sized to
+// be HBM/latency-balanced first.
+#include "common.cuh"
+
+namespace tgb {
+
+struct AttnParams {
+  const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v;
+  __nv_bfloat16* out;
+  const float* mask;          // additive [B, Sk] or null
+  long long ldq, ldk, ldv, ldo;
+  int B, H, Sq, Sk;
+  float scale_log2;           // scale * log2(e)
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int D>
+struct AttnCfg {
+  static constexpr int DK = (D + 15) / 16 * 16;        // head dim padded to the MMA K step (88 -> 96)
+  static constexpr int KP = DK + 8;                    // K pitch (elements): 208 B / 144 B rows -> conflict-free ldmatrix
+  static constexpr int VP = (D * 2) % 128 == 0 ? D + 8 : D;   // V pitch: 176 B (d=88) / 144 B (d=64)
+  static constexpr int ND = D / 8;                     // PV n-tiles
+  static constexpr int KS = DK / 16;                   // QK^T k-steps
+  static_assert(D % 8 == 0, "head dim must be a multiple of 8");
+};
+
+// NT = number of 8-key n-tiles in this key block (8 for a full 64-key block, 2/4/6 for the tail).
+template <int D, int NT>
+__device__ __forceinline__ void attn_block(const uint32_t (&qf)[AttnCfg<D>::KS][4], float (&o)[AttnCfg<D>::ND][4],
+                                           float (&mrow)[2], float (&lrow)[2], uint32_t sK, uint32_t sV, int key0,
+                                           int Sk, const float* smask, float scale_log2, int lane) {
+  using C = AttnCfg<D>;
+  float s[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
+  // ---- S = Q K^T
+  const int lrow8 = lane & 7, lmat = lane >> 3;
+#pragma unroll
+  for (int ks = 0; ks < C::KS; ++ks) {
+#pragma unroll
+    for (int nt = 0; nt < NT; nt += 2) {
+      // matrices: 0 = (keys nt, d lo) 1 = (keys nt, d hi) 2 = (keys nt+1, d lo) 3 = (keys nt+1, d hi)
+      const int key = key0 + (nt + (lmat >> 1)) * 8 + lrow8;
+      const int dcol = ks * 16 + (lmat & 1) * 8;
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(sK + (uint32_t)(key * C::KP + dcol) * 2, b0, b1, b2, b3);
+      mma_bf16_16816(s[nt], qf[ks], b0, b1);
+      mma_bf16_16816(s[nt + 1], qf[ks], b2, b3);
+    }
+  }
+  // ---- scale, mask, block max
+  const int kq = (lane & 3) * 2;
+  float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = key0 + nt * 8 + kq + e;
+      float add = 0.f;
+      if (key >= Sk) add = -INFINITY;
+      else if (smask) add = smask[key];
+      s[nt][e] = fmaf(s[nt][e], scale_log2, add);
+      s[nt][2 + e] = fmaf(s[nt][2 + e], scale_log2, add);
+      bm0 = fmaxf(bm0, s[nt][e]);
+      bm1 = fmaxf(bm1, s[nt][2 + e]);
+    }
+  }
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+  const float mn0 = fmaxf(mrow[0], bm0), mn1 = fmaxf(mrow[1], bm1);
+  const float base0 = (mn0 == -INFINITY) ? 0.f : mn0, base1 = (mn1 == -INFINITY) ? 0.f : mn1;
+  const float al0 = ex2_approx(mrow[0] - base0), al1 = ex2_approx(mrow[1] - base1);
+  mrow[0] = mn0; mrow[1] = mn1;
+  float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = ex2_approx(s[nt][0] - base0); s[nt][1] = ex2_approx(s[nt][1] - base0);
+    s[nt][2] = ex2_approx(s[nt][2] - base1); s[nt][3] = ex2_approx(s[nt][3] - base1);
+    ps0 += s[nt][0] + s[nt][1];
+    ps1 += s[nt][2] + s[nt][3];
+  }
+  lrow[0] = lrow[0] * al0 + ps0;
+  lrow[1] = lrow[1] * al1 + ps1;
+#pragma unroll
+  for (int nd = 0; nd < C::ND; ++nd) { o[nd][0] *= al0; o[nd][1] *= al0; o[nd][2] *= al1; o[nd][3] *= al1; }
+  // ---- O += P V   (P from the S accumulators, V through ldmatrix.trans)
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    const int key = key0 + kk * 16 + (lmat & 1) * 8 + lrow8;
+#pragma unroll
+    for (int nd = 0; nd + 1 < C::ND; nd += 2) {
+      uint32_t b0, b1, b2, b3;   // (keys lo, d nd) (keys hi, d nd) (keys lo, d nd+1) (keys hi, d nd+1)
+      ldsm_x4_t(sV + (uint32_t)(key * C::VP + (nd + (lmat >> 1)) * 8) * 2, b0, b1, b2, b3);
+      mma_bf16_16816(o[nd], pa, b0, b1);
+      mma_bf16_16816(o[nd + 1], pa, b2, b3);
+    }
+    if (C::ND & 1) {
+      uint32_t b0, b1;
+      const int key2 = key0 + kk * 16 + ((lane >> 3) & 1) * 8 + lrow8;
+      ldsm_x2_t(sV + (uint32_t)(key2 * C::VP + (C::ND - 1) * 8) * 2, b0, b1);
+      mma_bf16_16816(o[C::ND - 1], pa, b0, b1);
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
+  using C = AttnCfg<D>;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int SkPad = (p.Sk + 15) & ~15;
+  __nv_bfloat16* sKp = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sVp = sKp + (size_t)SkPad * C::KP;
+  float* smask = reinterpret_cast<float*>(sVp + (size_t)SkPad * C::VP);
+  const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+  // ---- stage K, V (and the mask row, pre-multiplied by log2 e) in shared memory
+  constexpr int CH = D / 8;                    // 16-byte chunks per row
+  constexpr int KCH = C::KP / 8;               // chunks per padded K row (zero beyond D)
+  for (int i = tid; i < SkPad * KCH; i += blockDim.x) {
+    const int r = i / KCH, c = i - r * KCH;
+    __nv_bfloat16* dst = sKp + (size_t)r * C::KP + c * 8;
+    if (r < p.Sk && c < CH) cp_async16(dst, p.k + ((long long)b * p.Sk + r) * p.ldk + h * D + c * 8);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  }
+  constexpr int VCH = C::VP / 8;
+  for (int i = tid; i < SkPad * VCH; i += blockDim.x) {
+    const int r = i / VCH, c = i - r * VCH;
+    __nv_bfloat16* dst = sVp + (size_t)r * C::VP + c * 8;
+    if (r < p.Sk && c < CH) cp_async16(dst, p.v + ((long long)b * p.Sk + r) * p.ldv + h * D + c * 8);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  }
+  if (p.mask)
+    for (int i = tid; i < SkPad; i += blockDim.x)
+      smask[i] = i < p.Sk ? p.mask[(long long)b * p.Sk + i] * 1.4426950408889634f : 0.f;
+  cp_async_wait_all();
+  __syncthreads();
+
+  const uint32_t sK = smem_u32(sKp), sV = smem_u32(sVp);
+  const float* sm = p.mask ? smask : nullptr;
+  const int mtiles = (p.Sq + 15) >> 4;
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+  for (int mt = warp; mt < mtiles; mt += nwarps) {
+    // ---- Q fragments straight from global (row-major A layout of m16n8k16)
+    uint32_t qf[C::KS][4];
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const __nv_bfloat16* q0 = p.q + ((long long)b * p.Sq + r0) * p.ldq + h * D;
+    const __nv_bfloat16* q1 = p.q + ((long long)b * p.Sq + r1) * p.ldq + h * D;
+#pragma unroll
+    for (int ks = 0; ks < C::KS; ++ks) {
+      const int c0 = ks * 16 + t2, c1 = c0 + 8;
+      qf[ks][0] = (r0 < p.Sq && c0 < D) ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c0)) : 0u;
+      qf[ks][1] = (r1 < p.Sq && c0 < D) ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c0)) : 0u;
+      qf[ks][2] = (r0 < p.Sq && c1 < D) ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c1)) : 0u;
+      qf[ks][3] = (r1 < p.Sq && c1 < D) ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c1)) : 0u;
+    }
+    float o[C::ND][4];
+#pragma unroll
+    for (int nd = 0; nd < C::ND; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f; }
+    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+    int key0 = 0;
+    for (; key0 + 64 <= SkPad; key0 += 64)
+      attn_block<D, 8>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
+    const int rem = SkPad - key0;               // 0, 16, 32 or 48 keys left
+    if (rem == 16) attn_block<D, 2>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
+    else if (rem == 32) attn_block<D, 4>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
+    else if (rem == 48) attn_block<D, 6>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
+    // ---- normalise and store
+    float l0 = lrow[0], l1 = lrow[1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    __nv_bfloat16* o0 = p.out + ((long long)b * p.Sq + r0) * p.ldo + h * D;
+    __nv_bfloat16* o1 = p.out + ((long long)b * p.Sq + r1) * p.ldo + h * D;
+#pragma unroll
+    for (int nd = 0; nd < C::ND; ++nd) {
+      if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(o0 + nd * 8 + t2) = pack_bf16(o[nd][0] * inv0, o[nd][1] * inv0);
+      if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(o1 + nd * 8 + t2) = pack_bf16(o[nd][2] * inv1, o[nd][3] * inv1);
+    }
+  }
+}
+
+template <int D>
+static int launch_attention(const AttnParams& p, cudaStream_t stream) {
+  using C = AttnCfg<D>;
+  const int SkPad = (p.Sk + 15) & ~15;
+  const size_t smem = (size_t)SkPad * (C::KP + C::VP) * 2 + (size_t)SkPad * 4;
+  TGB_CHECK_ARG(smem <= 227 * 1024, "attention: Sk=%d needs %zu B of shared memory (> 227 KB)", p.Sk, smem);
+  auto kern = attention_kernel<D>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    configured = 227 * 1024;
+  }
+  const int mtiles = (p.Sq + 15) / 16;
+  int warps = mtiles < 9 ? mtiles : 9;            // 9 warps x 2 rounds cover the ViT's 17 row tiles
+  kern<<<p.B * p.H, warps * 32, smem, stream>>>(p);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
+}  // namespace tgb
+
+using namespace tgb;
+
+extern "C" int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  void* out, int64_t ldo, const float* mask, int B, int H, int Sq, int Sk, int D,
+                                  float scale, tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(q && k && v && out, "attention: null pointer");
+  TGB_CHECK_ARG(B >= 0 && H > 0 && Sq > 0 && Sk > 0 && Sk <= 1024, "attention: bad shape B=%d H=%d Sq=%d Sk=%d", B, H, Sq, Sk);
+  TGB_CHECK_ARG(D == 64 || D == 88, "attention: head dim %d not supported (64, 88)", D);
+  TGB_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention: leading dims must be multiples of 8");
+  TGB_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 4) == 0,
+                "attention: q/k/v must be 16-byte aligned");
+  if (B == 0) return TGB_OK;
+  AttnParams p;
+  p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
+  p.out = (__nv_bfloat16*)out; p.mask = mask;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  if (D == 88) return launch_attention<88>(p, (cudaStream_t)stream);
+  return launch_attention<64>(p, (cudaStream_t)stream);
+}

@@ -1,0 +1,216 @@
+"""Thin torch-tensor -> C-ABI call layer.  Each function validates dtype/device/contiguity, hands raw device
+pointers plus the CURRENT torch CUDA stream to libvideotgb_b200.so, and returns torch tensors it allocated.
+torch here is plumbing (device memory + streams); all arithmetic happens in the library's kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_F32_ROWBIAS = range(5)
+MAP_SCALED, MAP_RATIO = 0, 1
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str, contiguous: bool = True) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.TgbError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.TgbError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise _lib.TgbError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _f3(vals):
+    return (ctypes.c_float * 3)(*[float(v) for v in vals])
+
+
+def _rows(t: torch.Tensor, name: str):
+    """2-D row-major view parameters (rows, cols, leading dim) of a tensor whose last dim is contiguous."""
+    if t.dim() < 2 or t.stride(-1) != 1:
+        raise _lib.TgbError(f"{name}: last dimension must be contiguous")
+    if t.dim() == 2:
+        return t.shape[0], t.shape[1], t.stride(0)
+    if not t.is_contiguous():
+        raise _lib.TgbError(f"{name}: >2-D tensors must be contiguous")
+    return t.numel() // t.shape[-1], t.shape[-1], t.shape[-1]
+
+
+# ------------------------------------------------------------------------------------------------ A0
+def normalize_frames_u8(frames_thwc: torch.Tensor, mean=CLIP_MEAN, std=CLIP_STD) -> torch.Tensor:
+    f = _need(frames_thwc, torch.uint8, "frames")
+    t, h, w, c = f.shape
+    if c != 3:
+        raise _lib.TgbError("frames must be [T,H,W,3]")
+    out = torch.empty((t, 3, h, w), dtype=torch.float32, device=f.device)
+    check(_lib.load().tgb_normalize_frames_u8(_p(f), _p(out), t, h, w, _f3(mean), _f3(std), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ A7-A9
+def gumbel_argmax(logits: torch.Tensor, gumbel: torch.Tensor, tau: float = 0.5) -> torch.Tensor:
+    lg = _need(logits, torch.float32, "logits")
+    gm = _need(gumbel, torch.float32, "gumbel")
+    if lg.shape != gm.shape or lg.dim() != 2:
+        raise _lib.TgbError("logits and gumbel must both be [R, L]")
+    idx = torch.empty((lg.shape[0],), dtype=torch.int64, device=lg.device)
+    check(_lib.load().tgb_gumbel_argmax(_p(lg), _p(gm), float(tau), lg.shape[0], lg.shape[1], _p(idx), _stream()))
+    return idx
+
+
+def spans_to_indices(cand_start: torch.Tensor, cand_end: torch.Tensor, of_lengths: torch.Tensor, num_frames: int,
+                     nframe: int, mapping: int = MAP_SCALED, inclusive: bool = False,
+                     host_ints: bool = False) -> torch.Tensor:
+    cs = _need(cand_start, torch.int64, "cand_start")
+    ce = _need(cand_end, torch.int64, "cand_end")
+    ol = _need(of_lengths, torch.int32, "of_lengths")
+    if cs.dim() != 2 or cs.shape != ce.shape or ol.shape != (cs.shape[1],):
+        raise _lib.TgbError("cand_start/cand_end must be [top_k, B] and of_lengths [B]")
+    out = torch.empty((cs.shape[1], nframe), dtype=torch.int64, device=cs.device)
+    check(_lib.load().tgb_spans_to_indices(_p(cs), _p(ce), cs.shape[0], _p(ol), cs.shape[1], int(num_frames),
+                                           int(nframe), int(mapping), int(bool(inclusive)), int(bool(host_ints)),
+                                           _p(out), _stream()))
+    return out
+
+
+def gather_frames(pixel_values: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+    """[B,N,...] , i64 [B,k] -> [B*k, ...] (same dtype as the source; the reference buffer is fp32)."""
+    if not pixel_values.is_cuda or not pixel_values.is_contiguous():
+        raise _lib.TgbError("pixel_values must be a contiguous CUDA tensor")
+    idx = _need(indices, torch.int64, "indices")
+    b, n = pixel_values.shape[:2]
+    k = idx.shape[1]
+    frame_bytes = pixel_values[0, 0].numel() * pixel_values.element_size()
+    out = torch.empty((b * k,) + tuple(pixel_values.shape[2:]), dtype=pixel_values.dtype, device=pixel_values.device)
+    check(_lib.load().tgb_gather_frames(_p(pixel_values), _p(idx), _p(out), b, n, k, frame_bytes, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ A10
+def patchify(pixel_values: torch.Tensor, patch: int, ld: int) -> torch.Tensor:
+    px = _need(pixel_values, torch.float32, "pixel_values")
+    f, c, s, s2 = px.shape
+    if c != 3 or s != s2:
+        raise _lib.TgbError("pixel_values must be [F,3,S,S]")
+    out = torch.empty((f * (s // patch) ** 2, ld), dtype=torch.bfloat16, device=px.device)
+    check(_lib.load().tgb_patchify_f32(_p(px), _p(out), f, s, patch, ld, _stream()))
+    return out
+
+
+def patchify_u8(frames_thwc: torch.Tensor, patch: int, ld: int, mean=CLIP_MEAN, std=CLIP_STD) -> torch.Tensor:
+    fr = _need(frames_thwc, torch.uint8, "frames")
+    f, s, s2, c = fr.shape
+    if c != 3 or s != s2:
+        raise _lib.TgbError("frames must be [F,S,S,3]")
+    out = torch.empty((f * (s // patch) ** 2, ld), dtype=torch.bfloat16, device=fr.device)
+    check(_lib.load().tgb_patchify_u8(_p(fr), _p(out), f, s, patch, ld, _f3(mean), _f3(std), _stream()))
+    return out
+
+
+def fill_cls_rows(hidden: torch.Tensor, cls: torch.Tensor, pos0: torch.Tensor) -> None:
+    h = _need(hidden, torch.float32, "hidden")
+    f, tokens, d = h.shape
+    check(_lib.load().tgb_fill_cls_rows(_p(h), _p(_need(cls, torch.float32, "cls")), _p(_need(pos0, torch.float32, "pos0")),
+                                        f, tokens, d, _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BF16,
+         out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+         rowbias: Optional[torch.Tensor] = None, period: int = 0, skip: int = 0, bn: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T).  a bf16 [M,K] (row stride allowed), w bf16 [N,K]."""
+    _need(a, torch.bfloat16, "a", contiguous=False)
+    _need(w, torch.bfloat16, "w", contiguous=False)
+    m, k, lda = _rows(a, "a")
+    n, kw, ldw = _rows(w, "w")
+    if k != kw:
+        raise _lib.TgbError(f"gemm: K mismatch {k} vs {kw}")
+    out_dtype = torch.bfloat16 if epilogue in (EPI_BF16, EPI_BF16_GELU) else torch.float32
+    if out is None:
+        if epilogue == EPI_F32_ROWBIAS:
+            raise _lib.TgbError("gemm: the row-bias epilogue writes into a caller-provided buffer")
+        out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    _need(out, out_dtype, "out", contiguous=False)
+    _, n_out, ldo = _rows(out, "out")
+    if n_out != n:
+        raise _lib.TgbError("gemm: out has the wrong width")
+    ldr = 0
+    if resid is not None:
+        _need(resid, torch.float32, "resid", contiguous=False)
+        _, _, ldr = _rows(resid, "resid")
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    if rowbias is not None:
+        _need(rowbias, torch.float32, "rowbias")
+    check(_lib.load().tgb_gemm_bf16(_p(a), lda, _p(w), ldw, m, n, k, epilogue, _p(bias), _p(resid), ldr, _p(rowbias),
+                                    period, skip, _p(out), ldo, bn, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, want_bf16: bool = True,
+              want_f32: bool = False):
+    _need(x, torch.float32, "x", contiguous=False)
+    m, n, ldx = _rows(x, "x")
+    ob = torch.empty((m, n), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    of = torch.empty((m, n), dtype=torch.float32, device=x.device) if want_f32 else None
+    check(_lib.load().tgb_layernorm_f32(_p(x), ldx, _p(_need(gamma, torch.float32, "gamma")),
+                                        _p(_need(beta, torch.float32, "beta")), float(eps), m, n, _p(ob), n, _p(of), n,
+                                        _stream()))
+    return ob, of
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, heads: int, sq: int, sk: int,
+              head_dim: int, scale: float, mask: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q/k/v: bf16 2-D views [batch*S, >= heads*head_dim] (column slices of a fused projection are fine)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, torch.bfloat16, nm, contiguous=False)
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise _lib.TgbError(f"attention: {nm} must be a 2-D row-major view")
+    if q.shape[0] != batch * sq or k.shape[0] != batch * sk or v.shape[0] != batch * sk:
+        raise _lib.TgbError("attention: row counts do not match batch*S")
+    if out is None:
+        out = torch.empty((batch * sq, heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    if mask is not None:
+        _need(mask, torch.float32, "mask")
+        if mask.shape != (batch, sk):
+            raise _lib.TgbError("attention: mask must be [batch, Sk]")
+    check(_lib.load().tgb_attention_bf16(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+                                         out.stride(0), _p(mask), batch, heads, sq, sk, head_dim, float(scale), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ misc
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need(x, torch.float32, "x", contiguous=False)
+    m, n, ldx = _rows(x, "x")
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().tgb_cast_f32_bf16(_p(x), ldx, _p(out), n, m, n, _stream()))
+    return out
+
+
+def group_mean(x: torch.Tensor, groups: int, width: int) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    if x.shape[0] != groups * width:
+        raise _lib.TgbError("group_mean: leading dim must be groups*width")
+    inner = x[0].numel()
+    out = torch.empty((groups,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    check(_lib.load().tgb_group_mean_f32(_p(x), _p(out), groups, width, inner, _stream()))
+    return out
