@@ -115,10 +115,36 @@ TGB_API int tgb_layernorm_f32(const float* x, int64_t ldx, const float* gamma, c
 /* ---------------------------------------------------------------- attention ---------------------------
  * softmax(Q K^T * scale + mask) V for one (batch, head) per CTA; fp32 softmax, bf16 tensor-core operands.
  * (xblip2.py:174-189 ViT, :647-686 Q-Former).  q/k/v: bf16, row (b*S + i), head h at columns [h*D, (h+1)*D).
- * mask: f32 additive [B, Sk] or NULL.  out: bf16 [B*Sq, ldo].  D in {64, 88}.  Sk <= 1024.               */
+ * mask: f32 additive [B, Sk] or NULL.  out: bf16 [B*Sq, ldo].  D in {64, 88}; long key sequences stream K/V through shared memory.               */
 TGB_API int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                        void* out, int64_t ldo, const float* mask, int B, int H, int Sq, int Sk, int D, float scale,
                        tgb_stream_t stream);
+
+/* ---------------------------------------------------------------- A1/A2/A4 temporal sampler -----------
+ * TemporalOFEmbedding (src/models/components/xropebert.py:103-129): Conv2d(2,768,k16,s16) -> flatten(2) ->
+ * Linear(196,1) has no non-linearity in between, so it reassociates exactly to
+ *   z[f,(c,ky,kx)] = sum_p fc_w[p] * flow[f,c,py*16+ky,px*16+kx]     (tgb_of_patch_reduce, HBM-bound, 1 pass)
+ *   y = z * W_conv^T + (b_conv * sum(fc_w) + fc_b)                      (tgb_gemm_bf16, [T,512]x[512,768])
+ * flow f32 [frames, C, S, S]; fc_weight f32 [(S/16)^2]; z bf16 [frames, ldz], ldz >= C*256.               */
+TGB_API int tgb_of_patch_reduce(const float* flow, const float* fc_weight, void* z_bf16, int frames, int C, int S, int P,
+                                int ldz, tgb_stream_t stream);
+/* xropebert.py:118-127: cat(bos, y, zero row); row ends[b] := eos; += frame_pos_embed[t]; LayerNorm(eps).
+ * y f32 [B, L, N]; ends i32 [B] (= of_mask.sum(1)-1); out [B, L+2, N] as f32 and/or bf16.                   */
+TGB_API int tgb_sampler_assemble(const float* y, const float* bos, const float* eos, const float* pos, const int32_t* ends,
+                                 const float* gamma, const float* beta, float eps, int B, int L, int N, float* out_f32,
+                                 void* out_bf16, tgb_stream_t stream);
+/* LayerNorm(table[ids[r]] + pos[r % period] + addvec): RopeBertEmbeddings (xropebert.py:190-208: word + token_type[0],
+ * no position) and InstructBlipQFormerEmbeddings (xinstructblip.py:1018-1046: word + position).  pos/addvec may be NULL. */
+TGB_API int tgb_embed_layernorm(const int64_t* ids, const float* table, int64_t vocab, const float* pos, int period,
+                                const float* addvec, const float* gamma, const float* beta, float eps, int64_t rows, int N,
+                                float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, tgb_stream_t stream);
+/* apply_rotary_position_embeddings / apply_rope (xropebert.py:334-377), in place on bf16 [rows, ldx] head vectors
+ * (H heads of HD at columns [h*HD,(h+1)*HD)); position = row % S; table f32 [>=S, HD] = [sin(HD/2) | cos(HD/2)].     */
+TGB_API int tgb_rope_bf16(void* x, int64_t ldx, const float* table, int64_t rows, int S, int H, int HD, tgb_stream_t stream);
+
+/* mrc_head = Linear(768, 2) in fp32 (xropebert.py:953,1164): out f32 [M,N] = x f32 [M,K] * w[N,K]^T + bias, N <= 8.   */
+TGB_API int tgb_linear_small_f32(const float* x, int64_t ldx, const float* w, const float* bias, int64_t M, int N, int K,
+                                 float* out, int64_t ldo, tgb_stream_t stream);
 
 /* ---------------------------------------------------------------- small elementwise ops ---------------*/
 /* out bf16 [M,N] (ldo) = x f32 [M,N] (ldx) */

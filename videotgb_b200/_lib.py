@@ -33,6 +33,12 @@ SIGNATURES = {
     "tgb_layernorm_f32": ([c_vp, c_i64, c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp], c_int),
     "tgb_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int,
                             c_int, c_f32, c_vp], c_int),
+    "tgb_of_patch_reduce": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp], c_int),
+    "tgb_sampler_assemble": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
+    "tgb_embed_layernorm": ([c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_f32, c_i64, c_int, c_vp, c_i64, c_vp,
+                             c_i64, c_vp], c_int),
+    "tgb_rope_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp], c_int),
+    "tgb_linear_small_f32": ([c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp], c_int),
     "tgb_cast_f32_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp], c_int),
     "tgb_group_mean_f32": ([c_vp, c_vp, c_int, c_int, c_i64, c_vp], c_int),
 }

@@ -59,7 +59,7 @@ struct AttnCfg {
 template <int D, int NT>
 __device__ __forceinline__ void attn_block(const uint32_t (&qf)[AttnCfg<D>::KS][4], float (&o)[AttnCfg<D>::ND][4],
                                            float (&mrow)[2], float (&lrow)[2], uint32_t sK, uint32_t sV, int key0,
-                                           int Sk, const float* smask, float scale_log2, int lane) {
+                                           int Sk, const float* smask, float scale_log2, int lane, int kbase = 0) {
   using C = AttnCfg<D>;
   float s[NT][4];
 #pragma unroll
@@ -88,7 +88,7 @@ __device__ __forceinline__ void attn_block(const uint32_t (&qf)[AttnCfg<D>::KS][
     for (int e = 0; e < 2; ++e) {
       const int key = key0 + nt * 8 + kq + e;
       float add = 0.f;
-      if (key >= Sk) add = -INFINITY;
+      if (kbase + key >= Sk) add = -INFINITY;
       else if (smask) add = smask[key];
       s[nt][e] = fmaf(s[nt][e], scale_log2, add);
       s[nt][2 + e] = fmaf(s[nt][2 + e], scale_log2, add);
@@ -218,12 +218,108 @@ __global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
   }
 }
 
+
+// Long-key variant (sampler, up to ~1k candidate frames): one 16-row query tile per warp, K/V streamed through
+// shared memory in chunks of KC keys, online-softmax state carried in registers across chunks.
+template <int D>
+__global__ void __launch_bounds__(256) attention_chunked_kernel(const AttnParams p, int KC) {
+  using C = AttnCfg<D>;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int SkPad = (p.Sk + 15) & ~15;
+  __nv_bfloat16* sKp = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sVp = sKp + (size_t)KC * C::KP;
+  float* smask = reinterpret_cast<float*>(sVp + (size_t)KC * C::VP);
+  const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int mt = blockIdx.y * nwarps + warp;
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+  const int r0 = mt * 16 + g, r1 = r0 + 8;
+  uint32_t qf[C::KS][4];
+  {
+    const __nv_bfloat16* q0 = p.q + ((long long)b * p.Sq + r0) * p.ldq + h * D;
+    const __nv_bfloat16* q1 = p.q + ((long long)b * p.Sq + r1) * p.ldq + h * D;
+#pragma unroll
+    for (int ks = 0; ks < C::KS; ++ks) {
+      const int c0 = ks * 16 + t2, c1 = c0 + 8;
+      qf[ks][0] = (r0 < p.Sq && c0 < D) ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c0)) : 0u;
+      qf[ks][1] = (r1 < p.Sq && c0 < D) ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c0)) : 0u;
+      qf[ks][2] = (r0 < p.Sq && c1 < D) ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c1)) : 0u;
+      qf[ks][3] = (r1 < p.Sq && c1 < D) ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c1)) : 0u;
+    }
+  }
+  float o[C::ND][4];
+#pragma unroll
+  for (int nd = 0; nd < C::ND; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f; }
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const uint32_t sK = smem_u32(sKp), sV = smem_u32(sVp);
+  const float* sm = p.mask ? smask : nullptr;
+  constexpr int CH = D / 8, KCH = C::KP / 8, VCH = C::VP / 8;
+  for (int c0 = 0; c0 < SkPad; c0 += KC) {
+    const int len = (SkPad - c0) < KC ? (SkPad - c0) : KC;
+    __syncthreads();
+    for (int i = tid; i < len * KCH; i += blockDim.x) {
+      const int r = i / KCH, c = i - r * KCH;
+      __nv_bfloat16* dst = sKp + (size_t)r * C::KP + c * 8;
+      if (c0 + r < p.Sk && c < CH) cp_async16(dst, p.k + ((long long)b * p.Sk + c0 + r) * p.ldk + h * D + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < len * VCH; i += blockDim.x) {
+      const int r = i / VCH, c = i - r * VCH;
+      __nv_bfloat16* dst = sVp + (size_t)r * C::VP + c * 8;
+      if (c0 + r < p.Sk && c < CH) cp_async16(dst, p.v + ((long long)b * p.Sk + c0 + r) * p.ldv + h * D + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    if (p.mask)
+      for (int i = tid; i < len; i += blockDim.x)
+        smask[i] = (c0 + i) < p.Sk ? p.mask[(long long)b * p.Sk + c0 + i] * 1.4426950408889634f : 0.f;
+    cp_async_wait_all();
+    __syncthreads();
+    int key0 = 0;
+    for (; key0 + 64 <= len; key0 += 64)
+      attn_block<D, 8>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane, c0);
+    const int rem = len - key0;
+    if (rem == 16) attn_block<D, 2>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane, c0);
+    else if (rem == 32) attn_block<D, 4>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane, c0);
+    else if (rem == 48) attn_block<D, 6>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane, c0);
+  }
+  float l0 = lrow[0], l1 = lrow[1];
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  __nv_bfloat16* o0 = p.out + ((long long)b * p.Sq + r0) * p.ldo + h * D;
+  __nv_bfloat16* o1 = p.out + ((long long)b * p.Sq + r1) * p.ldo + h * D;
+#pragma unroll
+  for (int nd = 0; nd < C::ND; ++nd) {
+    if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(o0 + nd * 8 + t2) = pack_bf16(o[nd][0] * inv0, o[nd][1] * inv0);
+    if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(o1 + nd * 8 + t2) = pack_bf16(o[nd][2] * inv1, o[nd][3] * inv1);
+  }
+}
+
+template <int D>
+static int launch_attention_chunked(const AttnParams& p, cudaStream_t stream) {
+  using C = AttnCfg<D>;
+  const int KC = 256;
+  const size_t smem = (size_t)KC * (C::KP + C::VP) * 2 + (size_t)KC * 4;
+  auto kern = attention_chunked_kernel<D>;
+  static bool configured = false;
+  if (!configured) {
+    TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int mtiles = (p.Sq + 15) / 16;
+  const int warps = mtiles < 8 ? mtiles : 8;
+  dim3 grid(p.B * p.H, (mtiles + warps - 1) / warps);
+  kern<<<grid, warps * 32, smem, stream>>>(p, KC);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
 template <int D>
 static int launch_attention(const AttnParams& p, cudaStream_t stream) {
   using C = AttnCfg<D>;
   const int SkPad = (p.Sk + 15) & ~15;
   const size_t smem = (size_t)SkPad * (C::KP + C::VP) * 2 + (size_t)SkPad * 4;
-  TGB_CHECK_ARG(smem <= 227 * 1024, "attention: Sk=%d needs %zu B of shared memory (> 227 KB)", p.Sk, smem);
+  if (smem > 112 * 1024) return launch_attention_chunked<D>(p, stream);     // long key sequences: stream K/V
   auto kern = attention_kernel<D>;
   static size_t configured = 0;
   if (smem > configured) {
@@ -247,7 +343,7 @@ extern "C" int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int
   int st = check_device();
   if (st != TGB_OK) return st;
   TGB_CHECK_ARG(q && k && v && out, "attention: null pointer");
-  TGB_CHECK_ARG(B >= 0 && H > 0 && Sq > 0 && Sk > 0 && Sk <= 1024, "attention: bad shape B=%d H=%d Sq=%d Sk=%d", B, H, Sq, Sk);
+  TGB_CHECK_ARG(B >= 0 && H > 0 && Sq > 0 && Sk > 0 && (long long)B * H <= 2147483647, "attention: bad shape B=%d H=%d Sq=%d Sk=%d", B, H, Sq, Sk);
   TGB_CHECK_ARG(D == 64 || D == 88, "attention: head dim %d not supported (64, 88)", D);
   TGB_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention: leading dims must be multiples of 8");
   TGB_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 4) == 0,

@@ -1,0 +1,494 @@
+"""Host-side mirror of the reference vision / Q-Former module API, running on the sm_100a kernels.
+
+Drop-in contract: same constructor argument (an HF-style config object), same forward
+keyword arguments and return conventions (`[0]`, `.last_hidden_state`, `.pooler_output`), same parameter names
+and shapes (checkpoints load with `load_state_dict`), same Python exceptions on missing inputs.
+
+  Blip2VisionModel / InstructBlipVisionModel   <- src/models/components/xblip2.py:500-563 / xinstructblip.py:498-561
+  Blip2QFormerModel                            <- xblip2.py:988-1174
+  InstructBlipQFormerModel                     <- xinstructblip.py:1049-1242
+
+The nn.Modules below only *hold* parameters (fp32 masters under the reference names).  All arithmetic happens in
+libvideotgb_b200.so through `ops`: bf16 tensor-core GEMMs with fused bias/GELU/residual epilogues, fp32 residual
+stream / LayerNorm / softmax statistics (the same split as the reference under `trainer.precision: bf16`).
+Forward / inference only (eval-mode semantics: every dropout is the identity); there is no fallback path.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import TgbError
+
+
+# ------------------------------------------------------------------------------------------------ holders
+class _Linear(nn.Module):
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_features, in_features).normal_(0.0, 0.02))
+        self.bias = nn.Parameter(torch.zeros(out_features))
+
+
+class _LayerNorm(nn.Module):
+    def __init__(self, n: int, eps: float):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n))
+        self.bias = nn.Parameter(torch.zeros(n))
+        self.eps = eps
+
+
+class _Conv(nn.Module):
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k).normal_(0.0, 0.02))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class _Embedding(nn.Module):
+    def __init__(self, n, d):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(n, d).normal_(0.0, 0.02))
+
+
+class _Holder(nn.Module):
+    pass
+
+
+def _cfg(config, name, default=None):
+    v = getattr(config, name, None)
+    return default if v is None else v
+
+
+class _KernelModule(nn.Module):
+    """Common plumbing: lazily packed bf16 weights, invalidated whenever parameters may have changed."""
+
+    def __init__(self):
+        super().__init__()
+        self._packed = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self):
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode: bool = True):
+        if mode:
+            # parity is defined in eval mode; the kernels implement no dropout / backward
+            pass
+        return super().train(mode)
+
+    @staticmethod
+    def _bf16(w: torch.Tensor) -> torch.Tensor:
+        return w.detach().to(torch.bfloat16).contiguous()
+
+    @staticmethod
+    def _f32(w: torch.Tensor) -> torch.Tensor:
+        return w.detach().to(torch.float32).contiguous()
+
+    def _device_check(self, t: torch.Tensor):
+        if not t.is_cuda:
+            raise TgbError("videotgb_b200 modules run on a B200 only (inputs must be CUDA tensors); no CPU fallback")
+
+
+def _model_output(cls_name: str, **kw):
+    import transformers.modeling_outputs as mo
+    return getattr(mo, cls_name)(**kw)
+
+
+# ------------------------------------------------------------------------------------------------ ViT
+class Blip2VisionModel(_KernelModule):
+    main_input_name = "pixel_values"
+
+    def __init__(self, config=None, max_frames_per_pass: int = 256):
+        super().__init__()
+        self.config = config if config is not None else SimpleNamespace()
+        d = self.hidden = _cfg(config, "hidden_size", 1408)
+        self.heads = _cfg(config, "num_attention_heads", 16)
+        self.layers_n = _cfg(config, "num_hidden_layers", 39)
+        self.mlp = _cfg(config, "intermediate_size", 6144)
+        self.image = _cfg(config, "image_size", 224)
+        self.patch = _cfg(config, "patch_size", 14)
+        self.eps = _cfg(config, "layer_norm_eps", 1e-6)
+        self.head_dim = d // self.heads
+        if self.head_dim * self.heads != d:
+            raise ValueError(f"embed_dim must be divisible by num_heads (got `embed_dim`: {d} and `num_heads`: {self.heads}).")
+        self.tokens = (self.image // self.patch) ** 2 + 1
+        self.max_frames_per_pass = max_frames_per_pass
+        self.embeddings = _Holder()
+        self.embeddings.class_embedding = nn.Parameter(torch.randn(1, 1, d) * 0.02)
+        self.embeddings.position_embedding = nn.Parameter(torch.randn(1, self.tokens, d) * 0.02)
+        self.embeddings.patch_embedding = _Conv(3, d, self.patch)
+        self.encoder = _Holder()
+        self.encoder.layers = nn.ModuleList()
+        for _ in range(self.layers_n):
+            lyr = _Holder()
+            lyr.self_attn = _Holder()
+            lyr.self_attn.qkv = _Linear(d, 3 * d)            # bias = cat(q_bias, zeros, v_bias) in checkpoints
+            lyr.self_attn.projection = _Linear(d, d)
+            lyr.layer_norm1 = _LayerNorm(d, self.eps)
+            lyr.mlp = _Holder()
+            lyr.mlp.fc1 = _Linear(d, self.mlp)
+            lyr.mlp.fc2 = _Linear(self.mlp, d)
+            lyr.layer_norm2 = _LayerNorm(d, self.eps)
+            self.encoder.layers.append(lyr)
+        self.post_layernorm = _LayerNorm(d, self.eps)
+
+    def get_input_embeddings(self):
+        return self.embeddings
+
+    # -- weights as the kernels want them
+    def _pack(self):
+        if self._packed is not None:
+            return self._packed
+        d, p = self.hidden, self.patch
+        kdim = 3 * p * p
+        kpad = (kdim + 7) // 8 * 8
+        w = self.embeddings.patch_embedding.weight.detach().reshape(d, kdim)
+        pw = torch.zeros(d, kpad, dtype=torch.bfloat16, device=w.device)
+        pw[:, :kdim] = w.to(torch.bfloat16)
+        pos = self.embeddings.position_embedding.detach()[0].float()
+        pk = SimpleNamespace(
+            kpad=kpad, patch_w=pw,
+            patch_rowbias=(pos[1:] + self.embeddings.patch_embedding.bias.detach().float()).contiguous(),
+            cls=self._f32(self.embeddings.class_embedding.reshape(-1)), pos0=pos[0].contiguous(),
+            layers=[], post=(self._f32(self.post_layernorm.weight), self._f32(self.post_layernorm.bias)))
+        for lyr in self.encoder.layers:
+            pk.layers.append(SimpleNamespace(
+                ln1=(self._f32(lyr.layer_norm1.weight), self._f32(lyr.layer_norm1.bias)),
+                ln2=(self._f32(lyr.layer_norm2.weight), self._f32(lyr.layer_norm2.bias)),
+                qkv_w=self._bf16(lyr.self_attn.qkv.weight), qkv_b=self._f32(lyr.self_attn.qkv.bias),
+                proj_w=self._bf16(lyr.self_attn.projection.weight), proj_b=self._f32(lyr.self_attn.projection.bias),
+                fc1_w=self._bf16(lyr.mlp.fc1.weight), fc1_b=self._f32(lyr.mlp.fc1.bias),
+                fc2_w=self._bf16(lyr.mlp.fc2.weight), fc2_b=self._f32(lyr.mlp.fc2.bias)))
+        self._packed = pk
+        return pk
+
+    # -- the frame-batched encoder (A10-A13)
+    def _encode(self, pk, cols: torch.Tensor, nf: int, last: torch.Tensor, last_bf16: Optional[torch.Tensor]):
+        d, s, h = self.hidden, self.tokens, self.heads
+        m = nf * s
+        dev = cols.device
+        x = torch.empty((m, d), dtype=torch.float32, device=dev)             # fp32 residual stream
+        ops.gemm(cols, pk.patch_w, None, ops.EPI_F32_ROWBIAS, out=x, rowbias=pk.patch_rowbias, period=s - 1, skip=1)
+        ops.fill_cls_rows(x.view(nf, s, d), pk.cls, pk.pos0)
+        ln = torch.empty((m, d), dtype=torch.bfloat16, device=dev)
+        qkv = torch.empty((m, 3 * d), dtype=torch.bfloat16, device=dev)
+        ctx = torch.empty((m, d), dtype=torch.bfloat16, device=dev)
+        hid = torch.empty((m, self.mlp), dtype=torch.bfloat16, device=dev)
+        scale = self.head_dim ** -0.5
+        for lw in pk.layers:
+            ops.layernorm(x, lw.ln1[0], lw.ln1[1], self.eps, out_bf16=ln)
+            ops.gemm(ln, lw.qkv_w, lw.qkv_b, ops.EPI_BF16, out=qkv)
+            ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nf, h, s, s, self.head_dim, scale, out=ctx)
+            ops.gemm(ctx, lw.proj_w, lw.proj_b, ops.EPI_F32_RESID, out=x, resid=x)
+            ops.layernorm(x, lw.ln2[0], lw.ln2[1], self.eps, out_bf16=ln)
+            ops.gemm(ln, lw.fc1_w, lw.fc1_b, ops.EPI_BF16_GELU, out=hid)
+            ops.gemm(hid, lw.fc2_w, lw.fc2_b, ops.EPI_F32_RESID, out=x, resid=x)
+        ops.layernorm(x, pk.post[0], pk.post[1], self.eps, out_bf16=last_bf16, out_f32=last)
+
+    def encode_patches(self, cols: torch.Tensor, nf: int):
+        """im2col'ed frames (bf16 [nf*256, kpad]) -> (last_hidden_state f32 [nf,257,D], bf16 copy)."""
+        pk = self._pack()
+        d, s = self.hidden, self.tokens
+        last = torch.empty((nf * s, d), dtype=torch.float32, device=cols.device)
+        last_bf16 = torch.empty((nf * s, d), dtype=torch.bfloat16, device=cols.device)
+        step = self.max_frames_per_pass
+        per = s - 1
+        for f0 in range(0, nf, step):
+            f1 = min(nf, f0 + step)
+            self._encode(pk, cols[f0 * per: f1 * per], f1 - f0, last[f0 * s: f1 * s], last_bf16[f0 * s: f1 * s])
+        return last.view(nf, s, d), last_bf16.view(nf, s, d)
+
+    def forward(self, pixel_values: Optional[torch.Tensor] = None, output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None, return_dict: Optional[bool] = None):
+        return_dict = return_dict if return_dict is not None else _cfg(self.config, "use_return_dict", True)
+        if pixel_values is None:
+            raise ValueError("You have to specify pixel_values")
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("the fused encoder does not materialise attentions / per-layer hidden states")
+        self._device_check(pixel_values)
+        pk = self._pack()
+        nf = pixel_values.shape[0]
+        px = pixel_values
+        if px.dtype != torch.float32 or not px.is_contiguous():
+            px = px.float().contiguous()
+        cols = ops.patchify(px, self.patch, pk.kpad)
+        last, last_bf16 = self.encode_patches(cols, nf)
+        pooled = ops.layernorm(last[:, 0, :], pk.post[0], pk.post[1], self.eps, want_bf16=False, want_f32=True)[1]
+        last._tgb_bf16 = last_bf16                  # lets the Q-Former skip a re-cast of its K/V operand
+        if not return_dict:
+            return (last, pooled)
+        return _model_output("BaseModelOutputWithPooling", last_hidden_state=last, pooler_output=pooled,
+                             hidden_states=None, attentions=None)
+
+    def forward_u8(self, frames_thwc: torch.Tensor):
+        """Fast path: u8 [F,S,S,3] decoded frames -> fused normalise+patchify -> encoder.  Same result as
+        `forward(normalize(frames))` up to the bf16 rounding both share."""
+        self._device_check(frames_thwc)
+        pk = self._pack()
+        cols = ops.patchify_u8(frames_thwc, self.patch, pk.kpad)
+        last, last_bf16 = self.encode_patches(cols, frames_thwc.shape[0])
+        last._tgb_bf16 = last_bf16
+        return last
+
+
+class InstructBlipVisionModel(Blip2VisionModel):
+    """xinstructblip.py:498-561 -- same arithmetic; the twin differs only in not casting pixels to the conv weight
+    dtype (xinstructblip.py:116), which is moot here because the patch GEMM always consumes bf16."""
+
+
+# ------------------------------------------------------------------------------------------------ Q-Former
+class _QFormerBase(_KernelModule):
+    instruct = False
+
+    def __init__(self, config=None):
+        super().__init__()
+        self.config = config if config is not None else SimpleNamespace()
+        d = self.hidden = _cfg(config, "hidden_size", 768)
+        self.heads = _cfg(config, "num_attention_heads", 12)
+        self.layers_n = _cfg(config, "num_hidden_layers", 12)
+        self.mlp = _cfg(config, "intermediate_size", 3072)
+        self.enc_hidden = _cfg(config, "encoder_hidden_size", 1408)
+        self.cross_freq = _cfg(config, "cross_attention_frequency", 2)
+        self.eps = _cfg(config, "layer_norm_eps", 1e-12)
+        self.head_dim = d // self.heads
+        if d % self.heads != 0:
+            raise ValueError("The hidden size (%d) is not a multiple of the number of attention heads (%d)" % (d, self.heads))
+        self.encoder = _Holder()
+        self.encoder.layer = nn.ModuleList()
+        for i in range(self.layers_n):
+            lyr = _Holder()
+            lyr.attention = self._attn_block(d, d)
+            if i % self.cross_freq == 0:
+                lyr.crossattention = self._attn_block(d, self.enc_hidden)
+            lyr.intermediate_query = _Holder()
+            lyr.intermediate_query.dense = _Linear(d, self.mlp)
+            lyr.output_query = _Holder()
+            lyr.output_query.dense = _Linear(self.mlp, d)
+            lyr.output_query.LayerNorm = _LayerNorm(d, self.eps)
+            if self.instruct:
+                lyr.intermediate = _Holder()
+                lyr.intermediate.dense = _Linear(d, self.mlp)
+                lyr.output = _Holder()
+                lyr.output.dense = _Linear(self.mlp, d)
+                lyr.output.LayerNorm = _LayerNorm(d, self.eps)
+            self.encoder.layer.append(lyr)
+
+    def _attn_block(self, d, kv_in):
+        blk = _Holder()
+        blk.attention = _Holder()
+        blk.attention.query = _Linear(d, d)
+        blk.attention.key = _Linear(kv_in, d)
+        blk.attention.value = _Linear(kv_in, d)
+        blk.output = _Holder()
+        blk.output.dense = _Linear(d, d)
+        blk.output.LayerNorm = _LayerNorm(d, self.eps)
+        return blk
+
+    def _pack_layers(self):
+        out = []
+        for lyr in self.encoder.layer:
+            a = lyr.attention
+            lp = SimpleNamespace(
+                qkv_w=self._bf16(torch.cat([a.attention.query.weight, a.attention.key.weight, a.attention.value.weight], 0)),
+                qkv_b=self._f32(torch.cat([a.attention.query.bias, a.attention.key.bias, a.attention.value.bias], 0)),
+                ao_w=self._bf16(a.output.dense.weight), ao_b=self._f32(a.output.dense.bias),
+                ao_ln=(self._f32(a.output.LayerNorm.weight), self._f32(a.output.LayerNorm.bias)),
+                cross=None,
+                iq_w=self._bf16(lyr.intermediate_query.dense.weight), iq_b=self._f32(lyr.intermediate_query.dense.bias),
+                oq_w=self._bf16(lyr.output_query.dense.weight), oq_b=self._f32(lyr.output_query.dense.bias),
+                oq_ln=(self._f32(lyr.output_query.LayerNorm.weight), self._f32(lyr.output_query.LayerNorm.bias)))
+            if hasattr(lyr, "crossattention"):
+                c = lyr.crossattention
+                lp.cross = SimpleNamespace(
+                    q_w=self._bf16(c.attention.query.weight), q_b=self._f32(c.attention.query.bias),
+                    kv_w=self._bf16(torch.cat([c.attention.key.weight, c.attention.value.weight], 0)),   # fused K|V, N=1536
+                    kv_b=self._f32(torch.cat([c.attention.key.bias, c.attention.value.bias], 0)),
+                    o_w=self._bf16(c.output.dense.weight), o_b=self._f32(c.output.dense.bias),
+                    o_ln=(self._f32(c.output.LayerNorm.weight), self._f32(c.output.LayerNorm.bias)))
+            if self.instruct:
+                lp.it_w = self._bf16(lyr.intermediate.dense.weight)
+                lp.it_b = self._f32(lyr.intermediate.dense.bias)
+                lp.ot_w = self._bf16(lyr.output.dense.weight)
+                lp.ot_b = self._f32(lyr.output.dense.bias)
+                lp.ot_ln = (self._f32(lyr.output.LayerNorm.weight), self._f32(lyr.output.LayerNorm.bias))
+            out.append(lp)
+        return out
+
+    # -- helpers
+    def _post_ln(self, acc_f32, ln, eps):
+        """LayerNorm of an fp32 [M,N] sum -> (fp32, bf16)."""
+        ob, of = ops.layernorm(acc_f32, ln[0], ln[1], eps, want_bf16=True, want_f32=True)
+        return of, ob
+
+    def _image_operand(self, encoder_hidden_states: torch.Tensor) -> torch.Tensor:
+        cached = getattr(encoder_hidden_states, "_tgb_bf16", None)
+        if cached is not None and cached.shape == encoder_hidden_states.shape:
+            return cached.reshape(-1, cached.shape[-1])
+        e = encoder_hidden_states
+        if e.dtype == torch.bfloat16:
+            return e.contiguous().view(-1, e.shape[-1])
+        return ops.cast_bf16(e.float().contiguous().view(-1, e.shape[-1]))
+
+    @staticmethod
+    def _additive(mask: Optional[torch.Tensor], value: float) -> Optional[torch.Tensor]:
+        if mask is None:
+            return None
+        return ((1.0 - mask.to(torch.float32)) * value).contiguous()
+
+    def _run_layers(self, layers, x_f32, x_bf16, nf, seq, nq, img, s_img, self_mask, cross_mask):
+        d, h, hd = self.hidden, self.heads, self.head_dim
+        scale = 1.0 / math.sqrt(hd)
+        for lp in layers:
+            # self-attention over all `seq` rows (queries + instruction tokens)
+            qkv = ops.gemm(x_bf16, lp.qkv_w, lp.qkv_b, ops.EPI_BF16)
+            ctx = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nf, h, seq, seq, hd, scale, self_mask)
+            acc = ops.gemm(ctx, lp.ao_w, lp.ao_b, ops.EPI_F32_RESID, resid=x_f32)
+            a_f32, a_bf16 = self._post_ln(acc, lp.ao_ln, self.eps)
+            if seq > nq:       # InstructBLIP: split query rows / text rows (plain strided copies)
+                a3f, a3b = a_f32.view(nf, seq, d), a_bf16.view(nf, seq, d)
+                q_f32, q_bf16 = a3f[:, :nq].reshape(-1, d), a3b[:, :nq].reshape(-1, d)
+                t_f32, t_bf16 = a3f[:, nq:].reshape(-1, d), a3b[:, nq:].reshape(-1, d)
+            else:
+                q_f32, q_bf16 = a_f32, a_bf16
+            if lp.cross is not None:
+                c = lp.cross
+                if img is None:
+                    raise ValueError("encoder_hidden_states must be given for cross-attention layers")
+                qc = ops.gemm(q_bf16, c.q_w, c.q_b, ops.EPI_BF16)
+                kv = ops.gemm(img, c.kv_w, c.kv_b, ops.EPI_BF16)                      # [F*257, 1536]
+                cctx = ops.attention(qc, kv[:, :d], kv[:, d:], nf, h, nq, s_img, hd, scale, cross_mask)
+                acc = ops.gemm(cctx, c.o_w, c.o_b, ops.EPI_F32_RESID, resid=q_f32)
+                q_f32, q_bf16 = self._post_ln(acc, c.o_ln, self.eps)
+            inter = ops.gemm(q_bf16, lp.iq_w, lp.iq_b, ops.EPI_BF16_GELU)
+            acc = ops.gemm(inter, lp.oq_w, lp.oq_b, ops.EPI_F32_RESID, resid=q_f32)
+            q_f32, q_bf16 = self._post_ln(acc, lp.oq_ln, self.eps)
+            if seq > nq:
+                inter = ops.gemm(t_bf16, lp.it_w, lp.it_b, ops.EPI_BF16_GELU)
+                acc = ops.gemm(inter, lp.ot_w, lp.ot_b, ops.EPI_F32_RESID, resid=t_f32)
+                t_f32, t_bf16 = self._post_ln(acc, lp.ot_ln, self.eps)
+                x_f32 = torch.cat([q_f32.view(nf, nq, d), t_f32.view(nf, seq - nq, d)], 1).view(-1, d)
+                x_bf16 = torch.cat([q_bf16.view(nf, nq, d), t_bf16.view(nf, seq - nq, d)], 1).view(-1, d)
+            else:
+                x_f32, x_bf16 = q_f32, q_bf16
+        return x_f32
+
+    def _finish(self, x_f32, nf, seq, return_dict):
+        seq_out = x_f32.view(nf, seq, self.hidden)
+        pooled = seq_out[:, 0, :]
+        if not return_dict:
+            return (seq_out, pooled)
+        return _model_output("BaseModelOutputWithPoolingAndCrossAttentions", last_hidden_state=seq_out,
+                             pooler_output=pooled, past_key_values=None, hidden_states=None, attentions=None,
+                             cross_attentions=None)
+
+
+class Blip2QFormerModel(_QFormerBase):
+    """`qformer(query_embeds=, encoder_hidden_states=, encoder_attention_mask=)[0]`  (LSTP_SF_blip2_module.py:472-477)."""
+
+    def __init__(self, config=None):
+        super().__init__(config)
+        self.layernorm = _LayerNorm(self.hidden, self.eps)
+
+    def _pack(self):
+        if self._packed is None:
+            self._packed = SimpleNamespace(ln=(self._f32(self.layernorm.weight), self._f32(self.layernorm.bias)),
+                                           layers=self._pack_layers())
+        return self._packed
+
+    def forward(self, query_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, head_mask=None,
+                encoder_hidden_states: Optional[torch.Tensor] = None,
+                encoder_attention_mask: Optional[torch.Tensor] = None, past_key_values=None, use_cache=None,
+                output_attentions=None, output_hidden_states=None, return_dict: Optional[bool] = None):
+        return_dict = return_dict if return_dict is not None else _cfg(self.config, "use_return_dict", True)
+        if past_key_values is not None or output_attentions or output_hidden_states or head_mask is not None:
+            raise NotImplementedError("KV cache / attention outputs / head masks are not on the VideoTGB hot path")
+        self._device_check(query_embeds)
+        pk = self._pack()
+        nf, nq, d = query_embeds.shape
+        q = query_embeds.to(torch.float32).contiguous().view(-1, d)       # materialises the expand()
+        x_bf16, x_f32 = ops.layernorm(q, pk.ln[0], pk.ln[1], self.eps, want_bf16=True, want_f32=True)
+        img, s_img = None, 0
+        if encoder_hidden_states is not None:
+            img = self._image_operand(encoder_hidden_states)
+            s_img = encoder_hidden_states.shape[1]
+        self_mask = self._additive(attention_mask, -10000.0)
+        # image masks are all-ones on this path (LSTP_SF_blip2_module.py:469); the additive form is exact either way
+        cross_mask = self._additive(encoder_attention_mask, torch.finfo(torch.float32).min)
+        x = self._run_layers(pk.layers, x_f32, x_bf16, nf, nq, nq, img, s_img, self_mask, cross_mask)
+        return self._finish(x, nf, nq, return_dict)
+
+
+class InstructBlipQFormerModel(_QFormerBase):
+    """`qformer(input_ids=, attention_mask=, query_embeds=, encoder_hidden_states=, encoder_attention_mask=,
+    return_dict=True).last_hidden_state[:, :32]`  (LSTP_SF_module.py:546-559)."""
+    instruct = True
+
+    def __init__(self, config=None):
+        super().__init__(config)
+        vocab = _cfg(config, "vocab_size", 30522)
+        max_pos = _cfg(config, "max_position_embeddings", 512)
+        self.embeddings = _Holder()
+        self.embeddings.word_embeddings = _Embedding(vocab, self.hidden)
+        self.embeddings.position_embeddings = _Embedding(max_pos, self.hidden)
+        self.embeddings.layernorm = _LayerNorm(self.hidden, self.eps)
+        self.embeddings.register_buffer("position_ids", torch.arange(max_pos).expand((1, -1)), persistent=False)
+
+    def _pack(self):
+        if self._packed is None:
+            e = self.embeddings
+            self._packed = SimpleNamespace(word=self._f32(e.word_embeddings.weight), pos=self._f32(e.position_embeddings.weight),
+                                           ln=(self._f32(e.layernorm.weight), self._f32(e.layernorm.bias)),
+                                           layers=self._pack_layers())
+        return self._packed
+
+    def forward(self, input_ids: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                position_ids=None, query_embeds: Optional[torch.Tensor] = None, head_mask=None,
+                encoder_hidden_states: Optional[torch.Tensor] = None,
+                encoder_attention_mask: Optional[torch.Tensor] = None, past_key_values=None, use_cache=None,
+                output_attentions=None, output_hidden_states=None, return_dict: Optional[bool] = None):
+        return_dict = return_dict if return_dict is not None else _cfg(self.config, "use_return_dict", True)
+        if input_ids is None and query_embeds is None:
+            raise ValueError("You have to specify query_embeds when input_ids is None")
+        if query_embeds is None:
+            raise NotImplementedError("text-only Q-Former passes are not on the VideoTGB hot path")
+        if past_key_values is not None or output_attentions or output_hidden_states or head_mask is not None or \
+                position_ids is not None:
+            raise NotImplementedError("KV cache / attention outputs / head masks / custom position ids are not on the hot path")
+        self._device_check(query_embeds)
+        pk = self._pack()
+        nf, nq, d = query_embeds.shape
+        tt = 0 if input_ids is None else input_ids.shape[1]
+        seq = nq + tt
+        x_f32 = torch.empty((nf, seq, d), dtype=torch.float32, device=query_embeds.device)
+        x_bf16 = torch.empty((nf, seq, d), dtype=torch.bfloat16, device=query_embeds.device)
+        # query rows: LayerNorm(query_embeds); identical for every frame when query_embeds is an expand() of query_tokens
+        qn_b, qn_f = ops.layernorm(query_embeds.to(torch.float32).contiguous().view(-1, d), pk.ln[0], pk.ln[1], self.eps,
+                                   want_bf16=True, want_f32=True)
+        x_f32[:, :nq] = qn_f.view(nf, nq, d)
+        x_bf16[:, :nq] = qn_b.view(nf, nq, d)
+        if tt:
+            if tt > pk.pos.shape[0]:
+                raise ValueError(f"instruction length {tt} exceeds max_position_embeddings {pk.pos.shape[0]}")
+            t_f = torch.empty((nf * tt, d), dtype=torch.float32, device=x_f32.device)
+            t_b = torch.empty((nf * tt, d), dtype=torch.bfloat16, device=x_f32.device)
+            ops.embed_layernorm(input_ids.to(torch.int64).contiguous().view(-1), pk.word, pk.ln[0], pk.ln[1], self.eps,
+                                pos=pk.pos, period=tt, out_f32=t_f, out_bf16=t_b)
+            x_f32[:, nq:] = t_f.view(nf, tt, d)
+            x_bf16[:, nq:] = t_b.view(nf, tt, d)
+        img, s_img = None, 0
+        if encoder_hidden_states is not None:
+            img = self._image_operand(encoder_hidden_states)
+            s_img = encoder_hidden_states.shape[1]
+        self_mask = self._additive(attention_mask, -10000.0)
+        cross_mask = self._additive(encoder_attention_mask, torch.finfo(torch.float32).min)
+        x = self._run_layers(pk.layers, x_f32.view(-1, d), x_bf16.view(-1, d), nf, seq, nq, img, s_img, self_mask, cross_mask)
+        return self._finish(x, nf, seq, return_dict)

@@ -164,11 +164,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, want_bf16: bool = True,
-              want_f32: bool = False):
+              want_f32: bool = False, out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
     _need(x, torch.float32, "x", contiguous=False)
     m, n, ldx = _rows(x, "x")
-    ob = torch.empty((m, n), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    of = torch.empty((m, n), dtype=torch.float32, device=x.device) if want_f32 else None
+    ob = out_bf16 if out_bf16 is not None else (
+        torch.empty((m, n), dtype=torch.bfloat16, device=x.device) if want_bf16 else None)
+    of = out_f32 if out_f32 is not None else (
+        torch.empty((m, n), dtype=torch.float32, device=x.device) if want_f32 else None)
+    if ob is not None and (ob.dtype != torch.bfloat16 or ob.shape != (m, n) or not ob.is_contiguous()):
+        raise _lib.TgbError("layernorm: out_bf16 must be a contiguous bf16 [M,N] tensor")
+    if of is not None and (of.dtype != torch.float32 or of.shape != (m, n) or not of.is_contiguous()):
+        raise _lib.TgbError("layernorm: out_f32 must be a contiguous f32 [M,N] tensor")
     check(_lib.load().tgb_layernorm_f32(_p(x), ldx, _p(_need(gamma, torch.float32, "gamma")),
                                         _p(_need(beta, torch.float32, "beta")), float(eps), m, n, _p(ob), n, _p(of), n,
                                         _stream()))
@@ -213,4 +219,71 @@ def group_mean(x: torch.Tensor, groups: int, width: int) -> torch.Tensor:
     inner = x[0].numel()
     out = torch.empty((groups,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
     check(_lib.load().tgb_group_mean_f32(_p(x), _p(out), groups, width, inner, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+def of_patch_reduce(flow: torch.Tensor, fc_weight: torch.Tensor, patch: int = 16) -> torch.Tensor:
+    """flow f32 [T, C, S, S] -> bf16 [T, C*patch*patch] weighted patch reduction (see csrc/sampler.cu)."""
+    fl = _need(flow, torch.float32, "flow")
+    t, c, s, s2 = fl.shape
+    fw = _need(fc_weight, torch.float32, "fc_weight")
+    if s != s2 or fw.numel() != (s // patch) ** 2:
+        raise _lib.TgbError("of_patch_reduce: fc_weight must have (S/patch)^2 elements")
+    z = torch.empty((t, c * patch * patch), dtype=torch.bfloat16, device=fl.device)
+    check(_lib.load().tgb_of_patch_reduce(_p(fl), _p(fw), _p(z), t, c, s, patch, z.shape[1], _stream()))
+    return z
+
+
+def sampler_assemble(y: torch.Tensor, bos, eos, pos, ends: torch.Tensor, gamma, beta, eps: float):
+    """y f32 [B, L, N] -> (f32, bf16) [B, L+2, N]."""
+    _need(y, torch.float32, "y")
+    b, l, n = y.shape
+    _need(ends, torch.int32, "ends")
+    of = torch.empty((b, l + 2, n), dtype=torch.float32, device=y.device)
+    ob = torch.empty((b, l + 2, n), dtype=torch.bfloat16, device=y.device)
+    if pos.shape[0] < l + 2:
+        raise _lib.TgbError(f"sampler: {l + 2} positions exceed max_position_embeddings={pos.shape[0]}")
+    check(_lib.load().tgb_sampler_assemble(_p(y), _p(_need(bos, torch.float32, "bos")), _p(_need(eos, torch.float32, "eos")),
+                                           _p(_need(pos, torch.float32, "pos")), _p(ends), _p(_need(gamma, torch.float32, "gamma")),
+                                           _p(_need(beta, torch.float32, "beta")), float(eps), b, l, n, _p(of), _p(ob), _stream()))
+    return of, ob
+
+
+def embed_layernorm(ids: torch.Tensor, table: torch.Tensor, gamma, beta, eps: float, pos: Optional[torch.Tensor] = None,
+                    period: int = 0, addvec: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+                    out_bf16: Optional[torch.Tensor] = None):
+    """ids i64 [R] -> LayerNorm(table[ids] + pos[r % period] + addvec) written to 2-D (possibly strided) outputs."""
+    _need(ids, torch.int64, "ids")
+    _need(table, torch.float32, "table")
+    r, n = ids.numel(), table.shape[1]
+    if out_f32 is None and out_bf16 is None:
+        out_f32 = torch.empty((r, n), dtype=torch.float32, device=ids.device)
+        out_bf16 = torch.empty((r, n), dtype=torch.bfloat16, device=ids.device)
+    ldf = out_f32.stride(0) if out_f32 is not None else 0
+    ldb = out_bf16.stride(0) if out_bf16 is not None else 0
+    check(_lib.load().tgb_embed_layernorm(_p(ids), _p(table), table.shape[0], _p(pos), int(period), _p(addvec),
+                                          _p(_need(gamma, torch.float32, "gamma")), _p(_need(beta, torch.float32, "beta")),
+                                          float(eps), r, n, _p(out_f32), ldf, _p(out_bf16), ldb, _stream()))
+    return out_f32, out_bf16
+
+
+def rope_(x: torch.Tensor, table: torch.Tensor, seq: int, heads: int, head_dim: int) -> torch.Tensor:
+    """In-place rotary embedding on a bf16 2-D view [rows, >= heads*head_dim]; position = row % seq."""
+    _need(x, torch.bfloat16, "x", contiguous=False)
+    _need(table, torch.float32, "table")
+    if x.dim() != 2 or x.stride(1) != 1 or table.shape[0] < seq or table.shape[1] != head_dim:
+        raise _lib.TgbError("rope: bad shapes")
+    check(_lib.load().tgb_rope_bf16(_p(x), x.stride(0), _p(table), x.shape[0], seq, heads, head_dim, _stream()))
+    return x
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """fp32 out[M,N] = x[M,K] @ w[N,K].T + bias for tiny N (<= 8)."""
+    _need(x, torch.float32, "x", contiguous=False)
+    m, k, ldx = _rows(x, "x")
+    _need(w, torch.float32, "w")
+    n = w.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    check(_lib.load().tgb_linear_small_f32(_p(x), ldx, _p(w), _p(bias), m, n, k, _p(out), n, _stream()))
     return out

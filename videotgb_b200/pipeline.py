@@ -1,0 +1,138 @@
+"""The hot path end to end: sampler scoring -> span draw / selection / gather -> ViT-g -> Q-Former ->
+language_projection -> LLM query tokens.
+
+`VideoTGBEncoder` has the attribute layout the reference task modules use
+(`self.temporal_encoder`, `self.model.vision_model`, `self.model.qformer`, `self.model.query_tokens`,
+`self.model.language_projection`, `self.model.temporal_projection`; src/models/LSTP_SF_blip2_module.py:84-89,
+eval/utils/model.py:33-37), so `load_state_dict(ckpt["state_dict"], strict=False)` of a reference checkpoint fills it,
+and `encode(batch)` is the body of `eval_forward` (LSTP_SF_blip2_module.py:383-484) up to the tokens handed to the
+unchanged HF language model.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops, selection
+from .modeling import (Blip2QFormerModel, Blip2VisionModel, InstructBlipQFormerModel, InstructBlipVisionModel,
+                       _KernelModule, _Linear)
+from .sampler import RopeBertModel
+
+
+class _Blip2Like(nn.Module):
+    """`self.model` of the reference: vision_model, qformer, query_tokens, language_projection, temporal_projection
+    (xblip2.py:1540-1556 / xinstructblip.py:1255-1273).  The language model itself is out of scope (unchanged HF)."""
+
+    def __init__(self, vision_config=None, qformer_config=None, llm_hidden: int = 2048, instruct: bool = False,
+                 num_query_tokens: int = 32):
+        super().__init__()
+        self.vision_model = (InstructBlipVisionModel if instruct else Blip2VisionModel)(vision_config)
+        self.qformer = (InstructBlipQFormerModel if instruct else Blip2QFormerModel)(qformer_config)
+        self.query_tokens = nn.Parameter(torch.zeros(1, num_query_tokens, self.qformer.hidden))
+        self.language_projection = LanguageProjection(self.qformer.hidden, llm_hidden)
+        self.temporal_projection = _Linear(self.qformer.hidden, llm_hidden)     # kept for checkpoint compatibility only
+
+
+class LanguageProjection(_KernelModule):
+    """nn.Linear(768, H_llm) (xblip2.py:1552) on the tcgen05 GEMM; accepts [..., 768] fp32/bf16, returns fp32."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features).normal_(0.0, 0.02))
+        self.bias = nn.Parameter(torch.zeros(out_features))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self._device_check(x)
+        if self._packed is None:
+            self._packed = (self._bf16(self.weight), self._f32(self.bias))
+        w, b = self._packed
+        x2 = x.reshape(-1, self.in_features)
+        a = x2.contiguous() if x2.dtype == torch.bfloat16 else ops.cast_bf16(x2.to(torch.float32).contiguous())
+        y = ops.gemm(a, w, b, ops.EPI_F32)
+        return y.view(*x.shape[:-1], self.out_features)
+
+
+class VideoTGBEncoder(nn.Module):
+    def __init__(self, vision_config=None, qformer_config=None, sampler_config=None, llm_hidden: int = 2048,
+                 instruct: bool = False):
+        super().__init__()
+        self.instruct = instruct
+        self.model = _Blip2Like(vision_config, qformer_config, llm_hidden, instruct)
+        self.temporal_encoder = RopeBertModel(sampler_config)
+
+    # ---- stages -------------------------------------------------------------------------------------------
+    def score(self, batch, mode: str = "fusion"):
+        """A1-A6: -> (of_feat, start_logits [B,L,1], end_logits [B,L,1])."""
+        of_feat, of_logits = self.temporal_encoder(
+            encoder_embeds=batch["of"], attention_mask=batch["of_mask"],
+            encoder_hidden_states=batch["sampler_question"],
+            encoder_attention_mask=batch.get("sampler_question_attention_mask"), mode=mode)
+        start_logits, end_logits = of_logits.split(1, dim=-1)
+        return of_feat, start_logits, end_logits
+
+    def select(self, start_logits, end_logits, batch, pixel_values, nframe, variant="eval", gumbel=None, generator=None):
+        """A7-A9: -> (sampled_pixel_values [B*nframe,3,H,W], indices [B,nframe])."""
+        return selection.select_and_gather(start_logits, end_logits, batch["of_lengths"], pixel_values, nframe,
+                                           variant=variant, gumbel=gumbel, generator=generator)
+
+    def tokens(self, sampled_pixel_values: torch.Tensor, batch_size: int, batch=None, assemble: str = "concat",
+               widths=None) -> torch.Tensor:
+        """A10-A16: frames -> `language_model_inputs` ([B, nframe*32, H_llm] concat, or [B, 32, H_llm] mean-pooled)."""
+        m = self.model
+        image_embeddings = m.vision_model(pixel_values=sampled_pixel_values, return_dict=True).last_hidden_state
+        nf = image_embeddings.shape[0]
+        query_tokens = m.query_tokens.expand(nf, -1, -1)
+        if self.instruct:
+            nframe = nf // batch_size
+            ids = torch.repeat_interleave(batch["qformer_text"], nframe, 0)
+            tmask = torch.repeat_interleave(batch["qformer_text_attention_mask"], nframe, 0)
+            qmask = torch.ones(query_tokens.shape[:-1], dtype=torch.long, device=ids.device)
+            out = m.qformer(input_ids=ids, attention_mask=torch.cat([qmask, tmask], dim=1), query_embeds=query_tokens,
+                            encoder_hidden_states=image_embeddings, encoder_attention_mask=None, return_dict=True)
+            query_output = out.last_hidden_state[:, : query_tokens.size(1), :]
+        else:
+            query_output = m.qformer(query_embeds=query_tokens, encoder_hidden_states=image_embeddings,
+                                     encoder_attention_mask=None)[0]
+        return self.assemble(query_output, batch_size, assemble, widths)
+
+    def assemble(self, query_output: torch.Tensor, batch_size: int, mode: str = "concat", widths=None) -> torch.Tensor:
+        m = self.model
+        if mode == "concat":                       # LSTP_SF_blip2_module.py:480-481
+            y = m.language_projection(query_output)
+            return y.reshape(batch_size, -1, y.shape[-1])
+        if mode != "mean":
+            raise ValueError(mode)
+        nf = query_output.shape[0]                 # eval/utils/model.py:186-195, LSTP_Vicuna_IV_module.py:233-242
+        q = query_output.to(torch.float32).contiguous()
+        if widths is None or len(set(widths)) == 1:
+            pooled = ops.group_mean(q, batch_size, nf // batch_size)
+        else:
+            parts, idx = [], 0
+            for w in widths:
+                parts.append(ops.group_mean(q[idx: idx + w].contiguous(), 1, w))
+                idx += w
+            pooled = torch.cat(parts, 0)
+        return m.language_projection(pooled)
+
+    # ---- the whole path -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, batch, mode: str = "fusion", variant: str = "eval", assemble: str = "concat", gumbel=None,
+               generator=None, return_aux: bool = False):
+        """batch keys as the reference collate produces them (videoinstruct_dataset.py:147-192): frames [B*N,3,H,W]
+        (or [B,N,3,H,W]), of, of_mask, of_lengths, sampler_question(+_attention_mask), nframe, and for InstructBLIP
+        qformer_text(+_attention_mask)."""
+        nframe = batch["nframe"]
+        b = batch["of"].shape[0]
+        px = batch["frames"]
+        if px.dim() == 4:
+            px = px.view(b, -1, *px.shape[1:])
+        _, start_logits, end_logits = self.score(batch, mode)
+        sampled, idx = self.select(start_logits, end_logits, batch, px, nframe, variant, gumbel, generator)
+        out = self.tokens(sampled, b, batch, assemble)
+        if return_aux:
+            return out, SimpleNamespace(indices=idx, start_logits=start_logits, end_logits=end_logits)
+        return out

@@ -1,0 +1,74 @@
+"""Span draw -> frame indices -> gather, on the device with no host round trip.
+
+Replaces the inline block every reference task module carries (canonical: src/models/LSTP_SF_blip2_module.py:415-464):
+two rounds of `F.gumbel_softmax(cat(start,end), tau=0.5, dim=1).argmax(dim=1)`, the per-video Python loop (span ->
+frame range, set union, fallback, doubling, numpy-linspace midpoints -- each comparison on a CUDA scalar is a device
+sync in the reference) and `index_select` into an fp32 zeros buffer.  Here it is three kernel launches.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import ops
+
+VARIANTS = {
+    # name: (mapping, inclusive)         reference site
+    "eval": (ops.MAP_SCALED, False),     # LSTP_SF_blip2_module.py:446-447
+    "train": (ops.MAP_SCALED, True),     # LSTP_SF_blip2_module.py:296-297
+    "ratio": (ops.MAP_RATIO, False),     # LSTP_module.py:245, eval/utils/model.py:135
+}
+
+
+def gumbel_noise_like(logits: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Exactly the draw `F.gumbel_softmax` makes: -log(Exp(1)) with the tensor's device RNG."""
+    e = torch.empty_like(logits, memory_format=torch.legacy_contiguous_format)
+    return -e.exponential_(generator=generator).log()
+
+
+def draw_spans(start_logits: torch.Tensor, end_logits: torch.Tensor, top_k: int = 2, tau: float = 0.5,
+               gumbel: Optional[Sequence[torch.Tensor]] = None, generator: Optional[torch.Generator] = None):
+    """start/end logits [B,L,1] (or [B,L]) -> (cand_start, cand_end) int64 [top_k, B] on the device.
+
+    `gumbel[i]` ([2B,L,1] or [2B,L]) overrides the i-th round's noise (parity tests feed the reference's draw).
+    """
+    b, l = start_logits.shape[:2]
+    logits = torch.cat([start_logits.reshape(b, l), end_logits.reshape(b, l)], dim=0).to(torch.float32).contiguous()
+    starts, ends = [], []
+    for i in range(top_k):
+        g = gumbel[i].reshape(2 * b, l).to(torch.float32).contiguous() if gumbel is not None else \
+            gumbel_noise_like(logits, generator)
+        idx = ops.gumbel_argmax(logits, g, tau)
+        starts.append(idx[:b])
+        ends.append(idx[b:])
+    return torch.stack(starts), torch.stack(ends)
+
+
+def select_indices(cand_start: torch.Tensor, cand_end: torch.Tensor, of_lengths, num_frames: int, nframe: int,
+                   variant: str = "eval", host_ints: bool = False) -> torch.Tensor:
+    """-> int64 [B, nframe] sorted frame indices (device)."""
+    mapping, inclusive = VARIANTS[variant]
+    if not torch.is_tensor(of_lengths):
+        if min(of_lengths) < 2:
+            raise ZeroDivisionError("of_lengths must be >= 2 (the reference divides by video_length-1)")
+        of_lengths = torch.tensor(list(of_lengths), dtype=torch.int32, device=cand_start.device)
+    return ops.spans_to_indices(cand_start.contiguous(), cand_end.contiguous(), of_lengths.to(torch.int32).contiguous(),
+                                num_frames, nframe, mapping, inclusive, host_ints)
+
+
+def uniform_indices(batch: int, num_frames: int, nframe: int, device) -> torch.Tensor:
+    """The uniform-sampling baseline / fallback (`cand_index = list(range(num_frames))`, LSTP_blip2_module.py:254):
+    an empty candidate set falls back to all frames inside the kernel."""
+    z = torch.zeros((1, batch), dtype=torch.int64, device=device)
+    lengths = torch.full((batch,), max(2, num_frames), dtype=torch.int32, device=device)
+    # a reversed span (1, 0) maps to an empty range -> "all frames" -> linspace midpoints
+    return ops.spans_to_indices(z + 1, z, lengths, num_frames, nframe, ops.MAP_SCALED, False, True)
+
+
+def select_and_gather(start_logits, end_logits, of_lengths, pixel_values: torch.Tensor, nframe: int,
+                      variant: str = "eval", top_k: int = 2, tau: float = 0.5, gumbel=None, generator=None):
+    """pixel_values [B,N,3,H,W] -> (sampled [B*nframe,3,H,W] (source dtype; fp32 in the reference), indices [B,nframe])."""
+    cs, ce = draw_spans(start_logits, end_logits, top_k, tau, gumbel, generator)
+    idx = select_indices(cs, ce, of_lengths, pixel_values.shape[1], nframe, variant)
+    return ops.gather_frames(pixel_values.contiguous(), idx), idx
