@@ -18,8 +18,30 @@ CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
+LAUNCHES = 0          # kernels launched through this layer (every C-ABI compute call enqueues exactly one kernel)
+_PROFILE = None       # when a list: (name, shape, start_event, end_event) per launch, see profile_launches()
+
+
 def _stream() -> int:
+    global LAUNCHES
+    LAUNCHES += 1
     return torch.cuda.current_stream().cuda_stream
+
+
+class profile_launches:
+    """Context manager: CUDA-event timing of every GEMM launch issued inside (used by bench.py's roofline leg)."""
+
+    def __enter__(self):
+        global _PROFILE
+        _PROFILE = []
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        torch.cuda.synchronize()
+        self.records = [(n, shp, a.elapsed_time(b)) for (n, shp, a, b) in _PROFILE]
+        _PROFILE = None
+        return False
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -157,8 +179,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _need(bias, torch.float32, "bias")
     if rowbias is not None:
         _need(rowbias, torch.float32, "rowbias")
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(_lib.load().tgb_gemm_bf16(_p(a), lda, _p(w), ldw, m, n, k, epilogue, _p(bias), _p(resid), ldr, _p(rowbias),
                                     period, skip, _p(out), ldo, bn, _stream()))
+    if _PROFILE is not None:
+        e1.record()
+        _PROFILE.append(("gemm", (m, n, k, epilogue), e0, e1))
     return out
 
 
@@ -175,9 +203,15 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         raise _lib.TgbError("layernorm: out_bf16 must be a contiguous bf16 [M,N] tensor")
     if of is not None and (of.dtype != torch.float32 or of.shape != (m, n) or not of.is_contiguous()):
         raise _lib.TgbError("layernorm: out_f32 must be a contiguous f32 [M,N] tensor")
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(_lib.load().tgb_layernorm_f32(_p(x), ldx, _p(_need(gamma, torch.float32, "gamma")),
                                         _p(_need(beta, torch.float32, "beta")), float(eps), m, n, _p(ob), n, _p(of), n,
                                         _stream()))
+    if _PROFILE is not None:
+        e1.record()
+        _PROFILE.append(("layernorm", (m, n, ob is not None, of is not None), e0, e1))
     return ob, of
 
 
@@ -198,8 +232,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
         _need(mask, torch.float32, "mask")
         if mask.shape != (batch, sk):
             raise _lib.TgbError("attention: mask must be [batch, Sk]")
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(_lib.load().tgb_attention_bf16(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
                                          out.stride(0), _p(mask), batch, heads, sq, sk, head_dim, float(scale), _stream()))
+    if _PROFILE is not None:
+        e1.record()
+        _PROFILE.append(("attention", (batch, heads, sq, sk, head_dim), e0, e1))
     return out
 
 

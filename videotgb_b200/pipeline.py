@@ -63,6 +63,7 @@ class VideoTGBEncoder(nn.Module):
         self.instruct = instruct
         self.model = _Blip2Like(vision_config, qformer_config, llm_hidden, instruct)
         self.temporal_encoder = RopeBertModel(sampler_config)
+        self.token_exchange = None      # optional distributed.TokenAllGather: all-gather of the Q-Former tokens
 
     # ---- stages -------------------------------------------------------------------------------------------
     def score(self, batch, mode: str = "fusion"):
@@ -101,6 +102,8 @@ class VideoTGBEncoder(nn.Module):
 
     def assemble(self, query_output: torch.Tensor, batch_size: int, mode: str = "concat", widths=None) -> torch.Tensor:
         m = self.model
+        if self.token_exchange is not None:
+            self.token_exchange.exchange(query_output)      # NCCL all-gather on a side stream, overlaps the projection
         if mode == "concat":                       # LSTP_SF_blip2_module.py:480-481
             y = m.language_projection(query_output)
             return y.reshape(batch_size, -1, y.shape[-1])
@@ -118,6 +121,24 @@ class VideoTGBEncoder(nn.Module):
             pooled = torch.cat(parts, 0)
         return m.language_projection(pooled)
 
+    def tokens_from_u8(self, sampled_u8: torch.Tensor, batch_size: int, batch=None, assemble: str = "concat"):
+        """Same as `tokens` for u8 THWC frames: normalise (A0) is fused into the patchify kernel."""
+        m = self.model
+        image_embeddings = m.vision_model.forward_u8(sampled_u8)
+        nf = image_embeddings.shape[0]
+        query_tokens = m.query_tokens.expand(nf, -1, -1)
+        if self.instruct:
+            nframe = nf // batch_size
+            ids = torch.repeat_interleave(batch["qformer_text"], nframe, 0)
+            tmask = torch.repeat_interleave(batch["qformer_text_attention_mask"], nframe, 0)
+            qmask = torch.ones(query_tokens.shape[:-1], dtype=torch.long, device=ids.device)
+            out = m.qformer(input_ids=ids, attention_mask=torch.cat([qmask, tmask], dim=1), query_embeds=query_tokens,
+                            encoder_hidden_states=image_embeddings, return_dict=True)
+            query_output = out.last_hidden_state[:, : query_tokens.size(1), :]
+        else:
+            query_output = m.qformer(query_embeds=query_tokens, encoder_hidden_states=image_embeddings)[0]
+        return self.assemble(query_output, batch_size, assemble)
+
     # ---- the whole path -----------------------------------------------------------------------------------
     @torch.no_grad()
     def encode(self, batch, mode: str = "fusion", variant: str = "eval", assemble: str = "concat", gumbel=None,
@@ -133,6 +154,26 @@ class VideoTGBEncoder(nn.Module):
         _, start_logits, end_logits = self.score(batch, mode)
         sampled, idx = self.select(start_logits, end_logits, batch, px, nframe, variant, gumbel, generator)
         out = self.tokens(sampled, b, batch, assemble)
+        if return_aux:
+            return out, SimpleNamespace(indices=idx, start_logits=start_logits, end_logits=end_logits)
+        return out
+
+    @torch.no_grad()
+    def encode_u8(self, batch, mode: str = "fusion", variant: str = "eval", assemble: str = "concat", gumbel=None,
+                  generator=None, return_aux: bool = False):
+        """Same path starting from DECODED u8 frames `frames_u8` [B,N,H,W,3] (what the dataloader holds before the
+        reference's CPU-side ToTensorVideo/NormalizeVideo).  Normalisation is a per-pixel map, so it commutes with the
+        gather: only the `nframe` selected frames per video are normalised, fused into the patchify kernel -- the fp32
+        [B,N,3,H,W] candidate tensor of the reference is never materialised.  Results equal `encode` on
+        `VideoNormalizer()(frames_u8)`."""
+        nframe = batch["nframe"]
+        px = batch["frames_u8"]
+        b = px.shape[0]
+        _, start_logits, end_logits = self.score(batch, mode)
+        cs, ce = selection.draw_spans(start_logits, end_logits, 2, 0.5, gumbel, generator)
+        idx = selection.select_indices(cs, ce, batch["of_lengths"], px.shape[1], nframe, variant)
+        sampled = ops.gather_frames(px.contiguous(), idx)
+        out = self.tokens_from_u8(sampled, b, batch, assemble)
         if return_aux:
             return out, SimpleNamespace(indices=idx, start_logits=start_logits, end_logits=end_logits)
         return out
