@@ -106,6 +106,9 @@ TGB_API int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw
                   const float* bias, const float* resid, int64_t ldr, const float* rowbias, int period, int skip,
                   void* out, int64_t ldo, int bn, tgb_stream_t stream);
 
+/* Debug / test knob: 0 = choose per problem (default), 1 = single-CTA 128xBN tiles, 2 = CTA-pair 256xBN tiles.      */
+TGB_API int tgb_gemm_set_cta_group(int cta_group);
+
 /* ---------------------------------------------------------------- LayerNorm ---------------------------
  * nn.LayerNorm over the last dim (xblip2.py:222-224,511; :703,:782; xropebert.py:91).  x: f32 [M,N] (ldx).
  * Writes bf16 and/or f32 outputs (either may be NULL).  N % 4 == 0, N <= 8192.                            */

@@ -176,8 +176,15 @@ GEMM_SHAPES = [
 ]
 
 
+@pytest.fixture(params=[1, 2], ids=["cta1", "cta2"])
+def cta_group(request):
+    ops.gemm_set_cta_group(request.param)
+    yield request.param
+    ops.gemm_set_cta_group(0)
+
+
 @pytest.mark.parametrize("m,n,k,bn", GEMM_SHAPES)
-def test_gemm_bias_bf16(m, n, k, bn):
+def test_gemm_bias_bf16(m, n, k, bn, cta_group):
     g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
     a = (torch.randn(m, k, generator=g)).to(torch.bfloat16)
     w = (torch.randn(n, k, generator=g) * 0.05).to(torch.bfloat16)
@@ -190,7 +197,7 @@ def test_gemm_bias_bf16(m, n, k, bn):
     assert _cos(got, want) > 0.9999
 
 
-def test_gemm_epilogues():
+def test_gemm_epilogues(cta_group):
     g = torch.Generator().manual_seed(99)
     m, n, k = 777, 1408, 1408
     a = torch.randn(m, k, generator=g).to(torch.bfloat16)

@@ -82,17 +82,27 @@ def bench(m, n, k, epi, bn=0, iters=20):
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     ok = True
+    for cg in (2, 1):
+        ops.gemm_set_cta_group(cg)
+        print("cta_group", cg)
+        for shape in [(256, 256, 64, 256), (256, 512, 256, 256), (300, 264, 200, 256), (1028, 1408, 1408, 176), (520, 4224, 1408, 128)]:
+            ok = probe(*shape) and ok
+    ops.gemm_set_cta_group(0)
     for shape in [(128, 64, 64, 64), (128, 256, 64, 256), (128, 256, 256, 256), (256, 512, 512, 256), (300, 264, 200, 256),
                   (1028, 1408, 1408, 176), (1028, 1408, 1408, 128)]:
         ok = probe(*shape) and ok
     if "--bench" in sys.argv and ok:
         M = 257 * 256
-        for bn in (0, 256, 176, 128):
-            bench(M, 1408, 1408, ops.EPI_F32_RESID, bn)
-        bench(M, 4224, 1408, ops.EPI_BF16)
-        bench(M, 4224, 1408, ops.EPI_BF16, 256)
-        bench(M, 6144, 1408, ops.EPI_BF16_GELU)
-        bench(M, 6144, 1408, ops.EPI_BF16)
-        bench(M, 1408, 6144, ops.EPI_F32_RESID)
-        bench(M, 1408, 6144, ops.EPI_F32_RESID, 256)
-        bench(8192, 8192, 8192, ops.EPI_BF16)
+        for cg in (2, 1):
+            ops.gemm_set_cta_group(cg)
+            print("cta_group", cg)
+            for bn in (256, 176, 128):
+                bench(M, 1408, 1408, ops.EPI_F32_RESID, bn)
+            bench(M, 4224, 1408, ops.EPI_BF16, 256)
+            bench(M, 4224, 1408, ops.EPI_BF16, 176)
+            bench(M, 6144, 1408, ops.EPI_BF16_GELU, 256)
+            bench(M, 6144, 1408, ops.EPI_BF16, 256)
+            bench(M, 1408, 6144, ops.EPI_F32_RESID, 256)
+            bench(M, 1408, 6144, ops.EPI_F32_RESID, 176)
+            bench(8192, 8192, 8192, ops.EPI_BF16, 256)
+        ops.gemm_set_cta_group(0)

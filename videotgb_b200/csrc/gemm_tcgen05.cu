@@ -1,16 +1,20 @@
 // bf16 GEMM with fused epilogues on the 5th-gen tensor cores:  out = epi(A[M,K] * W[N,K]^T)
 //
-// Persistent, warp-specialised kernel, one CTA per SM:
-//   warp 0     TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) of A [128 x 64] and W [BN x 64] bf16 tiles into a
-//                             STAGES-deep shared-memory ring, completion on `full` mbarriers
-//   warp 1     MMA issuer     one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per
-//                             stage, accumulating in TMEM; tcgen05.commit frees the stage / publishes the tile
-//   warp 2     TMEM allocator 512 columns = two BN-column fp32 accumulators (double buffered)
-//   warps 4-7  epilogue       tcgen05.ld the finished accumulator (lane == output row), fuse bias / GELU /
-//                             residual / row-bias, store bf16 or fp32; overlaps the next tile's main loop
+// Persistent, warp-specialised kernel; one CTA per SM, CTAs paired into 2-CTA clusters (cta_group::2) so that one
+// tcgen05.mma computes a 256 x BN tile across two SMs and each SM stages only half of the W tile:
+//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B): A [128 x 64] + W [BN/CG x 64] bf16 per stage into a
+//                              STAGES-deep shared-memory ring; both CTAs' bytes complete on the LEADER's `full` mbarrier
+//   warp 1      MMA issuer     (leader CTA only) one thread issues tcgen05.mma.cta_group::CG.kind::f16
+//                              (M=128*CG, N=BN, K=16) x4 per stage into TMEM; tcgen05.commit (multicast to both CTAs)
+//                              frees the stage / publishes the accumulator
+//   warp 2      TMEM allocator 512 columns = two BN-column fp32 accumulators (double buffered)
+//   warps 4-11  epilogue       tcgen05.ld the finished accumulator (lane == output row; two warps per lane quarter
+//                              split the 16-column chunks), fuse bias / GELU / residual / row-bias, store bf16 or fp32;
+//                              overlaps the next tile's main loop.  Residual rows are prefetched two chunks ahead.
 //
 // Both operands are K-major (row-major activations [M,K] and nn.Linear weights [N,K]), so the same descriptor
 // recipe serves A and B.  Tails: TMA zero-fills out-of-bounds rows/columns, the epilogue masks stores.
+// CG=1 (single-CTA, M=128 tiles) is kept for small problems and as a cross-check of the paired path.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -18,16 +22,17 @@
 
 namespace tgb {
 
-constexpr int BM = 128;
+constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
 
 struct GemmParams {
   int M, N, K;
   int epi;
-  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int num_m_blocks, num_n_blocks, num_k_blocks;     // m blocks of 128*CG rows
   int period, skip;
   const float* bias;
   const float* resid;
@@ -36,23 +41,25 @@ struct GemmParams {
   long long ldo, ldr;
 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
+  static constexpr int B_ROWS = BN / CG;                 // W rows staged per CTA
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (196 * 1024) / STAGE_BYTES < 8 ? (196 * 1024) / STAGE_BYTES : 8;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint");
+  static_assert(B_ROWS % 8 == 0, "W half tile must be whole swizzle atoms");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-B aligned for SWIZZLE_128B");
   static_assert(2 * BN <= (int)TMEM_COLS, "two accumulators must fit TMEM");
 };
 
+// One 16-column chunk of one output row: v = acc (+bias | +rowbias) (GELU) (+resid) -> store.
 template <int EPI>
-__device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], long long out_row,
-                                                 int row, int rb_row, int col, int ncols) {
-  // ncols in {8,16}: number of valid columns in this 16-wide chunk (N % 8 == 0).
+__device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], const float4 (&res)[4],
+                                                 long long out_row, int rb_row, int col, int ncols) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
@@ -80,13 +87,9 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
     for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
   }
   if (EPI == TGB_EPI_F32_RESID) {
-    const float4* rp = reinterpret_cast<const float4*>(p.resid + (long long)row * p.ldr + col);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (j * 4 < ncols) {
-        const float4 r = rp[j];
-        v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-      }
+      v[4 * j + 0] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
     }
   }
   if (EPI == TGB_EPI_BF16 || EPI == TGB_EPI_BF16_GELU) {
@@ -111,11 +114,23 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
   }
 }
 
-template <int BN, int EPI>
+__device__ __forceinline__ void load_resid16(const GemmParams& p, float4 (&r)[4], bool ok, int row, int col) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok && col < p.N) {
+    const float4* rp = reinterpret_cast<const float4*>(p.resid + (long long)row * p.ldr + col);
+    const int nv = (p.N - col) >= 16 ? 4 : 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) r[j] = rp[j];
+  }
+}
+
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -127,6 +142,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
   if (warp == 0 && lane == 0) {
@@ -135,49 +154,58 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);                 // leader's producer arrival (+ the transaction bytes of both CTAs)
+      mbar_init(&empty_bar[s], 1);                // one tcgen05.commit arrival (multicast to both CTAs)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], CG * EPI_WARPS);  // lane 0 of every epilogue warp of every CTA of the pair
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) tmem_alloc_cg<CG>(tmem_slot, TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------- TMA producer
+    // ------------------------------------------------------------- TMA producer (every CTA loads its halves)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / p.num_n_blocks;
         const int n_blk = tile - m_blk * p.num_n_blocks;
+        const int a_row = (m_blk * CG + (int)rank) * BM;
+        const int b_row = n_blk * BN + (int)rank * Cfg::B_ROWS;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + Cfg::A_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d(sa + Cfg::A_BYTES, &tma_b, &full_bar[stage], kb * BK, b_row);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
+            const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_cg2(sa, &tma_a, bar0, kb * BK, a_row);
+            tma_load_2d_cg2(sa + Cfg::A_BYTES, &tma_b, bar0, kb * BK, b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    // ------------------------------------------------------------- MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -190,28 +218,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss_cg<CG>(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);          // stage reusable once these MMAs have read it
+          umma_commit_cg<CG>(&empty_bar[stage]);     // stage reusable (in both CTAs) once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);              // accumulator complete
+        umma_commit_cg<CG>(&tmem_full[acc]);         // accumulator complete (both CTAs' epilogues)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ------------------------------------------------------------- epilogue (4 warps, TMEM lane == row)
-    const int ew = warp & 3;
+    // ------------------------------------------------------------- epilogue (8 warps; TMEM lane == row)
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;              // which 16-column chunks (even / odd)
+    constexpr int NCHUNK = BN / 16;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t empty0 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+    const uint32_t empty1 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * BM + ew * 32 + lane;
+      const int row = (m_blk * CG + (int)rank) * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      const int col0 = n_blk * BN;
       long long out_row = row;
       int rb_row = 0;
       if (EPI == TGB_EPI_F32_ROWBIAS) {
@@ -219,28 +250,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         rb_row = row - grp * p.period;
         out_row = (long long)grp * (p.period + p.skip) + p.skip + rb_row;
       }
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
-#pragma unroll 2
-      for (int c = 0; c < BN; c += 16) {
-        const int col = n_blk * BN + c;
-        if (col >= p.N) break;                      // warp-uniform
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_row + c, v);
-        tmem_ld_wait();
-        const int ncols = (p.N - col) >= 16 ? 16 : 8;
-        if (row_ok) epilogue_store16<EPI>(p, v, out_row, row, rb_row, col, ncols);
+      // residual prefetch ring, two chunks ahead (independent of the MMA, so it starts before the accumulator is ready)
+      float4 r0[4], r1[4];
+      if (EPI == TGB_EPI_F32_RESID) {
+        load_resid16(p, r0, row_ok, row, col0 + half * 16);
+        load_resid16(p, r1, row_ok, row, col0 + (half + 2) * 16);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int j = half; j < NCHUNK; j += 4) {       // two chunks (j, j+2) per iteration
+        const int cA = col0 + j * 16, cB = col0 + (j + 2) * 16;
+        if (cA >= p.N) break;                        // warp-uniform
+        uint32_t vA[16], vB[16];
+        tmem_ld_32x32b_x16_nomem(t_row + j * 16, vA);
+        const bool hasB = (j + 2 < NCHUNK) && (cB < p.N);
+        if (hasB) tmem_ld_32x32b_x16_nomem(t_row + (j + 2) * 16, vB);
+        float4 ra[4], rbv[4];
+        if (EPI == TGB_EPI_F32_RESID) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { ra[q] = r0[q]; rbv[q] = r1[q]; }
+          load_resid16(p, r0, row_ok && (j + 4 < NCHUNK), row, col0 + (j + 4) * 16);
+          load_resid16(p, r1, row_ok && (j + 6 < NCHUNK), row, col0 + (j + 6) * 16);
+        }
+        tmem_ld_wait_dep(vA);
+        if (row_ok) epilogue_store16<EPI>(p, vA, ra, out_row, rb_row, cA, (p.N - cA) >= 16 ? 16 : 8);
+        if (hasB) {
+          tmem_ld_wait_dep(vB);
+          if (row_ok) epilogue_store16<EPI>(p, vB, rbv, out_row, rb_row, cB, (p.N - cB) >= 16 ? 16 : 8);
+        }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(acc == 0 ? empty0 : empty1);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_cg<CG>(tmem_base, TMEM_COLS);
   }
 }
 
@@ -279,55 +334,108 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
   return TGB_OK;
 }
 
-template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
+static int g_force_cg = 0;     // 0 = choose, 1 / 2 = force (tests exercise both paths)
+
+template <int BN, int EPI, int CG>
+static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG>;
+  p.num_m_blocks = (p.M + BM * CG - 1) / (BM * CG);
+  p.num_n_blocks = (p.N + BN - 1) / BN;
+  p.num_k_blocks = (p.K + BK - 1) / BK;
+  CUtensorMap ta, tb;
+  int st = make_tmap(&ta, A, p.M, p.K, lda, BM);
+  if (st != TGB_OK) return st;
+  st = make_tmap(&tb, W, p.N, p.K, ldw, Cfg::B_ROWS);
+  if (st != TGB_OK) return st;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG>;
   static bool configured = false;
   if (!configured) {
     TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  TGB_CUDA(cudaGetLastError());
+  const int max_clusters = sm_count() / CG;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return TGB_OK;
 }
 
-template <int BN>
-static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+template <int BN, int CG>
+static int dispatch_epi(const void* A, long long lda, const void* W, long long ldw, const GemmParams& p, cudaStream_t s) {
   switch (p.epi) {
-    case TGB_EPI_BF16: return launch_gemm<BN, TGB_EPI_BF16>(ta, tb, p, s);
-    case TGB_EPI_BF16_GELU: return launch_gemm<BN, TGB_EPI_BF16_GELU>(ta, tb, p, s);
-    case TGB_EPI_F32: return launch_gemm<BN, TGB_EPI_F32>(ta, tb, p, s);
-    case TGB_EPI_F32_RESID: return launch_gemm<BN, TGB_EPI_F32_RESID>(ta, tb, p, s);
-    case TGB_EPI_F32_ROWBIAS: return launch_gemm<BN, TGB_EPI_F32_ROWBIAS>(ta, tb, p, s);
+    case TGB_EPI_BF16: return launch_gemm<BN, TGB_EPI_BF16, CG>(A, lda, W, ldw, p, s);
+    case TGB_EPI_BF16_GELU: return launch_gemm<BN, TGB_EPI_BF16_GELU, CG>(A, lda, W, ldw, p, s);
+    case TGB_EPI_F32: return launch_gemm<BN, TGB_EPI_F32, CG>(A, lda, W, ldw, p, s);
+    case TGB_EPI_F32_RESID: return launch_gemm<BN, TGB_EPI_F32_RESID, CG>(A, lda, W, ldw, p, s);
+    case TGB_EPI_F32_ROWBIAS: return launch_gemm<BN, TGB_EPI_F32_ROWBIAS, CG>(A, lda, W, ldw, p, s);
   }
   set_last_error("unknown epilogue %d", p.epi);
   return TGB_EINVAL;
 }
 
-static int choose_bn(int M, int N) {
-  const int cands[4] = {256, 176, 128, 64};
-  const int mblocks = (M + BM - 1) / BM;
-  int best = 256;
-  long long best_cost = -1;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    const long long nblocks = (N + bn - 1) / bn;
-    const long long tiles = nblocks * mblocks;
-    const long long waves = (tiles + sm_count() - 1) / sm_count();
-    // cost ~ MMA cycles of the busiest SM; narrower tiles pay more shared-memory traffic per flop
-    long long cost = waves * bn * (bn >= 176 ? 100 : (bn == 128 ? 108 : 125));
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+template <int CG>
+static int dispatch_bn(int bn, const void* A, long long lda, const void* W, long long ldw, const GemmParams& p,
+                       cudaStream_t s) {
+  switch (bn) {
+    case 256: return dispatch_epi<256, CG>(A, lda, W, ldw, p, s);
+    case 176: return dispatch_epi<176, CG>(A, lda, W, ldw, p, s);
+    case 128: return dispatch_epi<128, CG>(A, lda, W, ldw, p, s);
+    case 64: return dispatch_epi<64, CG>(A, lda, W, ldw, p, s);
   }
-  return best;
+  set_last_error("gemm: unsupported N tile %d (256/176/128/64)", bn);
+  return TGB_EINVAL;
+}
+
+// Tile choice: minimise the MMA time of the busiest SM; narrower tiles pay more operand traffic per flop.
+static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
+  // measured on B200: a tcgen05.mma with N=176 costs as much as N=256 (N is processed in 128-wide passes), so 176
+  // is only reachable by forcing bn; prefer 256, then 128.
+  const int cands[4] = {256, 128, 64, 64};
+  int best_bn = 256, best_cg = 2;
+  double best_cost = -1.0;
+  for (int cg = 2; cg >= 1; --cg) {
+    if (g_force_cg && cg != g_force_cg) continue;
+    const long long mblocks = (M + BM * cg - 1) / (BM * cg);
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cands[i];
+      const long long nblocks = (N + bn - 1) / bn;
+      const long long tiles = nblocks * mblocks;
+      const long long slots = sm_count() / cg;
+      const long long waves = (tiles + slots - 1) / slots;
+      double eff = bn >= 176 ? 1.0 : (bn == 128 ? 0.9 : 0.75);
+      if (cg == 1) eff *= 0.9;
+      const double cost = (double)waves * bn / eff;
+      if (best_cost < 0 || cost < best_cost * 0.999) { best_cost = cost; best_bn = bn; best_cg = cg; }
+    }
+  }
+  *bn_out = best_bn;
+  *cg_out = best_cg;
 }
 
 }  // namespace tgb
 
 using namespace tgb;
+
+extern "C" int tgb_gemm_set_cta_group(int cta_group) {
+  if (cta_group < 0 || cta_group > 2) {
+    set_last_error("cta_group must be 0 (auto), 1 or 2");
+    return TGB_EINVAL;
+  }
+  g_force_cg = cta_group;
+  return TGB_OK;
+}
 
 extern "C" int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
                              const float* bias, const float* resid, int64_t ldr, const float* rowbias, int period,
@@ -346,26 +454,15 @@ extern "C" int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
     TGB_CHECK_ARG(resid && ldr % 4 == 0 && ldr >= N && ((uintptr_t)resid % 16) == 0, "gemm: bad residual");
   if (epilogue == TGB_EPI_F32_ROWBIAS)
     TGB_CHECK_ARG(rowbias && period > 0 && skip >= 0 && ((uintptr_t)rowbias % 16) == 0, "gemm: bad rowbias");
-  if (bn == 0) bn = choose_bn(M, N);
+  int auto_bn, cg;
+  choose_tile(M, N, &auto_bn, &cg);
+  if (bn == 0) bn = auto_bn;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.epi = epilogue;
-  p.num_m_blocks = (M + BM - 1) / BM;
-  p.num_n_blocks = (N + bn - 1) / bn;
-  p.num_k_blocks = (K + BK - 1) / BK;
+  p.num_m_blocks = p.num_n_blocks = p.num_k_blocks = 0;
   p.period = period > 0 ? period : 1; p.skip = skip;
   p.bias = bias; p.resid = resid; p.rowbias = rowbias; p.out = out; p.ldo = ldo; p.ldr = ldr;
-  CUtensorMap ta, tb;
-  st = make_tmap(&ta, A, M, K, lda, BM);
-  if (st != TGB_OK) return st;
-  st = make_tmap(&tb, W, N, K, ldw, bn);
-  if (st != TGB_OK) return st;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  switch (bn) {
-    case 256: return dispatch_epi<256>(ta, tb, p, s);
-    case 176: return dispatch_epi<176>(ta, tb, p, s);
-    case 128: return dispatch_epi<128>(ta, tb, p, s);
-    case 64: return dispatch_epi<64>(ta, tb, p, s);
-  }
-  set_last_error("gemm: unsupported N tile %d (256/176/128/64)", bn);
-  return TGB_EINVAL;
+  if (cg == 2) return dispatch_bn<2>(bn, A, lda, W, ldw, p, s);
+  return dispatch_bn<1>(bn, A, lda, W, ldw, p, s);
 }

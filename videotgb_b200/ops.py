@@ -190,6 +190,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+def gemm_set_cta_group(cta_group: int) -> None:
+    """0 = auto, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles; test / debug knob."""
+    check(_lib.load().tgb_gemm_set_cta_group(int(cta_group)))
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, want_bf16: bool = True,
               want_f32: bool = False, out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
