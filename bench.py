@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--vit-layers", type=int, default=39, help="debug only; the reported config uses 39")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--profile", action="store_true",
+                    help="for runs under ncu: 1 untimed warm-up + 1 step of the resident path, nothing else (not a bench value)")
     return ap.parse_args()
 
 
@@ -260,6 +262,13 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    if args.profile:
+        step_resident()
+        torch.cuda.synchronize()
+        step_resident()
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_only": True, "launches_per_step": ops.LAUNCHES // 2}))
+        return
     for _ in range(max(3, args.warmup)):
         step_resident()
     clocks = ClockSampler(local)

@@ -44,9 +44,9 @@ class TokenAllGather:
             local.record_stream(self.stream)
         else:
             if local.dtype == torch.bfloat16 and not local.is_cuda:
-                # gloo has no bf16 all_gather_into_tensor on every build: move the bits as int16
-                g = self.gathered.view(torch.int16)
-                dist.all_gather_into_tensor(g, local.view(torch.int16), group=self.group)
+                # gloo has no bf16 collectives: move the raw bytes
+                g = self.gathered.view(torch.uint8)
+                dist.all_gather_into_tensor(g, local.view(torch.uint8), group=self.group)
             else:
                 dist.all_gather_into_tensor(self.gathered, local, group=self.group)
 
