@@ -59,19 +59,28 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// Exact-erf GELU (HF ACT2FN["gelu"]) via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7), written so the
-// negative branch has no cancellation.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Exact-erf GELU (HF ACT2FN["gelu"]):  gelu(x) = x * Phi(x),  Phi(x) = 1 - 0.5*erfc(x/sqrt2).
+// erfc via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7) with the 0.5 folded into the coefficients:
+//   h(|x|) = 0.5*erfc(|x|/sqrt2) = t*(a1 + t*(a2 + t*(a3 + t*(a4 + t*a5)))) * exp(-x^2/2) / 2,  t = 1/(1 + p*|x|/sqrt2)
+//   gelu(x) = 0.5*x + |x|*(0.5 - h)        (branch-free; equals x*(1-h) for x >= 0 and x*h for x < 0)
+// 13 FP32 ops + 2 MUFU per element.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
   poly *= t;
-  const float pe = poly * ex2_approx(-z * z * 1.4426950408889634f);   // erfc(|z|)
-  const float cdf2 = (x >= 0.0f) ? (2.0f - pe) : pe;                  // 2*Phi(x)
-  return 0.5f * x * cdf2;
+  const float e = ex2_approx((x * -0.72134752044448170f) * x);     // exp(-x^2/2)
+  const float h = poly * e;
+  return fmaf(ax, 0.5f - h, 0.5f * x);
 }
 
 // ------------------------------------------------------------------ mbarrier

@@ -8,9 +8,10 @@
 //                              (M=128*CG, N=BN, K=16) x4 per stage into TMEM; tcgen05.commit (multicast to both CTAs)
 //                              frees the stage / publishes the accumulator
 //   warp 2      TMEM allocator 512 columns = two BN-column fp32 accumulators (double buffered)
-//   warps 4-11  epilogue       tcgen05.ld the finished accumulator (lane == output row; two warps per lane quarter
-//                              split the 16-column chunks), fuse bias / GELU / residual / row-bias, store bf16 or fp32;
-//                              overlaps the next tile's main loop.  Residual rows are prefetched two chunks ahead.
+//   warps 4-19  epilogue       tcgen05.ld the finished accumulator (lane == output row; four warps per lane quarter
+//                              split the 16-column chunks), transpose each chunk through shared memory so the global
+//                              side is coalesced, fuse bias / GELU / residual / row-bias, store bf16 or fp32;
+//                              overlaps the next tile's main loop.  Residual rows are prefetched one chunk ahead.
 //
 // Both operands are K-major (row-major activations [M,K] and nn.Linear weights [N,K]), so the same descriptor
 // recipe serves A and B.  Tails: TMA zero-fills out-of-bounds rows/columns, the epilogue masks stores.
@@ -25,9 +26,11 @@ namespace tgb {
 constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                       // 4 per TMEM lane quarter / SM sub-partition
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int STG_PITCH = 20;                        // floats per staged row: 16 + 4 pad -> conflict-free 16-B phases
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;
 
 struct GemmParams {
   int M, N, K;
@@ -47,82 +50,35 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES < 8 ? (196 * 1024) / STAGE_BYTES : 8;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - STG_BYTES - BAR_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES < 8 ? BUDGET / STAGE_BYTES : 8;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint");
   static_assert(B_ROWS % 8 == 0, "W half tile must be whole swizzle atoms");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-B aligned for SWIZZLE_128B");
   static_assert(2 * BN <= (int)TMEM_COLS, "two accumulators must fit TMEM");
 };
 
-// One 16-column chunk of one output row: v = acc (+bias | +rowbias) (GELU) (+resid) -> store.
+// Epilogue math on 4 consecutive columns of one output row (transposed mapping: 4 lanes cover a 16-column row chunk,
+// so a warp instruction touches 8 rows x 64 contiguous bytes instead of 32 scattered rows).
 template <int EPI>
-__device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], const float4 (&res)[4],
-                                                 long long out_row, int rb_row, int col, int ncols) {
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-  if (EPI == TGB_EPI_F32_ROWBIAS) {
-    const float4* rb = reinterpret_cast<const float4*>(p.rowbias + (long long)rb_row * p.N + col);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j * 4 < ncols) {
-        const float4 b = __ldg(rb + j);
-        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-  } else if (p.bias != nullptr) {
-    const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j * 4 < ncols) {
-        const float4 b = __ldg(bp + j);
-        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-  }
+__device__ __forceinline__ void epilogue_store4(const GemmParams& p, float4 v, const float4& bias4, const float4& res,
+                                                long long out_row, int col) {
+  v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
   if (EPI == TGB_EPI_BF16_GELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+    v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
   }
   if (EPI == TGB_EPI_F32_RESID) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[4 * j + 0] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
-    }
+    v.x += res.x; v.y += res.y; v.z += res.z; v.w += res.w;
   }
   if (EPI == TGB_EPI_BF16 || EPI == TGB_EPI_BF16_GELU) {
-    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + col);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (j * 8 < ncols) {
-        uint4 o;
-        o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-        op[j] = o;
-      }
-    }
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + col) = o;
   } else {
-    float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + col);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j * 4 < ncols) op[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-  }
-}
-
-__device__ __forceinline__ void load_resid16(const GemmParams& p, float4 (&r)[4], bool ok, int row, int col) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ok && col < p.N) {
-    const float4* rp = reinterpret_cast<const float4*>(p.resid + (long long)row * p.ldr + col);
-    const int nv = (p.N - col) >= 16 ? 4 : 2;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < nv) r[j] = rp[j];
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + col) = v;
   }
 }
 
@@ -134,7 +90,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -229,10 +186,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ------------------------------------------------------------- epilogue (8 warps; TMEM lane == row)
+    // ------------------------------------------------------------- epilogue (16 warps)
+    // TMEM hands every thread one ROW (lane == row) of a 16-column chunk.  The chunk is transposed through a padded
+    // per-warp shared-memory tile so that the global side is coalesced: thread -> (row = i*8 + lane/4, 4 columns at
+    // (lane%4)*4), i.e. 64 contiguous bytes per row and 8 rows per instruction for the residual read and the store.
+    const int ew = warp - 4;
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;              // which 16-column chunks (even / odd)
+    const int sub = ew >> 2;                       // which 16-column chunks: sub, sub+NSUB, ...
+    constexpr int NSUB = EPI_WARPS / 4;
     constexpr int NCHUNK = BN / 16;
+    float* stg = staging + ew * (32 * STG_PITCH);
+    const int trow = lane >> 2;
+    const int tcol = (lane & 3) * 4;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t empty0 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
@@ -240,46 +205,72 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
-      const int row = (m_blk * CG + (int)rank) * BM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = (m_blk * CG + (int)rank) * BM + quarter * 32;
       const int col0 = n_blk * BN;
-      long long out_row = row;
-      int rb_row = 0;
-      if (EPI == TGB_EPI_F32_ROWBIAS) {
-        const int grp = row / p.period;
-        rb_row = row - grp * p.period;
-        out_row = (long long)grp * (p.period + p.skip) + p.skip + rb_row;
+      long long orow[4];
+      int rbrow[4];
+      bool rok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = row_base + i * 8 + trow;
+        rok[i] = row < p.M;
+        orow[i] = row;
+        rbrow[i] = 0;
+        if (EPI == TGB_EPI_F32_ROWBIAS) {
+          const int grp = row / p.period;
+          rbrow[i] = row - grp * p.period;
+          orow[i] = (long long)grp * (p.period + p.skip) + p.skip + rbrow[i];
+        }
       }
-      // residual prefetch ring, two chunks ahead (independent of the MMA, so it starts before the accumulator is ready)
-      float4 r0[4], r1[4];
+      // residual prefetch, one chunk ahead (independent of the MMA: the first one is issued before the tile is ready)
+      float4 rnext[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rnext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (EPI == TGB_EPI_F32_RESID) {
-        load_resid16(p, r0, row_ok, row, col0 + half * 16);
-        load_resid16(p, r1, row_ok, row, col0 + (half + 2) * 16);
+        const int c = col0 + sub * 16 + tcol;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (rok[i] && c < p.N) rnext[i] = *reinterpret_cast<const float4*>(p.resid + (long long)(row_base + i * 8 + trow) * p.ldr + c);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int j = half; j < NCHUNK; j += 4) {       // two chunks (j, j+2) per iteration
-        const int cA = col0 + j * 16, cB = col0 + (j + 2) * 16;
-        if (cA >= p.N) break;                        // warp-uniform
-        uint32_t vA[16], vB[16];
-        tmem_ld_32x32b_x16_nomem(t_row + j * 16, vA);
-        const bool hasB = (j + 2 < NCHUNK) && (cB < p.N);
-        if (hasB) tmem_ld_32x32b_x16_nomem(t_row + (j + 2) * 16, vB);
-        float4 ra[4], rbv[4];
-        if (EPI == TGB_EPI_F32_RESID) {
+      for (int j = sub; j < NCHUNK; j += NSUB) {
+        const int col = col0 + j * 16;
+        if (col >= p.N) break;                       // warp-uniform
+        uint32_t v[16];
+        tmem_ld_32x32b_x16_nomem(t_row + j * 16, v);
+        float4 rcur[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { ra[q] = r0[q]; rbv[q] = r1[q]; }
-          load_resid16(p, r0, row_ok && (j + 4 < NCHUNK), row, col0 + (j + 4) * 16);
-          load_resid16(p, r1, row_ok && (j + 6 < NCHUNK), row, col0 + (j + 6) * 16);
+        for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+        if (EPI == TGB_EPI_F32_RESID) {
+          const int cn = col + NSUB * 16 + tcol;
+          const bool more = (j + NSUB < NCHUNK) && (cn < p.N);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (more && rok[i]) rnext[i] = *reinterpret_cast<const float4*>(p.resid + (long long)(row_base + i * 8 + trow) * p.ldr + cn);
         }
-        tmem_ld_wait_dep(vA);
-        if (row_ok) epilogue_store16<EPI>(p, vA, ra, out_row, rb_row, cA, (p.N - cA) >= 16 ? 16 : 8);
-        if (hasB) {
-          tmem_ld_wait_dep(vB);
-          if (row_ok) epilogue_store16<EPI>(p, vB, rbv, out_row, rb_row, cB, (p.N - cB) >= 16 ? 16 : 8);
+        tmem_ld_wait_dep(v);
+        float4* srow = reinterpret_cast<float4*>(stg + lane * STG_PITCH);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          srow[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                __uint_as_float(v[4 * q + 3]));
+        __syncwarp();
+        const int c = col + tcol;
+        const bool cok = c < p.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI != TGB_EPI_F32_ROWBIAS && p.bias != nullptr && cok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(stg + (i * 8 + trow) * STG_PITCH + tcol);
+          if (rok[i] && cok) {
+            if (EPI == TGB_EPI_F32_ROWBIAS) bias4 = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)rbrow[i] * p.N + c));
+            epilogue_store4<EPI>(p, a, bias4, rcur[i], orow[i], c);
+          }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
