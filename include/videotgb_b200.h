@@ -123,6 +123,12 @@ TGB_API int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int64_
                        void* out, int64_t ldo, const float* mask, int B, int H, int Sq, int Sk, int D, float scale,
                        tgb_stream_t stream);
 
+/* ViT self-attention on tcgen05 (xblip2.py:156-192), specialised for the EVA-ViT-g shape: 257 tokens, 16 heads x 88.
+ * qkv: bf16 [frames*257, ld_qkv] fused projection, q|k|v of head h at columns {0,1408,2816}+88h (the tensor is read
+ * through a 3-D TMA map, ld_qkv >= 4224).  out: bf16 [frames*257, ld_out], head h at columns 88h.                    */
+TGB_API int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int frames, float scale,
+                                   tgb_stream_t stream);
+
 /* ---------------------------------------------------------------- A1/A2/A4 temporal sampler -----------
  * TemporalOFEmbedding (src/models/components/xropebert.py:103-129): Conv2d(2,768,k16,s16) -> flatten(2) ->
  * Linear(196,1) has no non-linearity in between, so it reassociates exactly to

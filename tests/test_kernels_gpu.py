@@ -290,6 +290,20 @@ def test_attention(b, h, sq, sk, d, masked):
     assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
 
 
+@pytest.mark.parametrize("frames,scale_in", [(1, 1.0), (3, 1.0), (19, 2.5)])
+def test_vit_attention_tcgen05(frames, scale_in):
+    """The tensor-memory attention kernel (S in TMEM, P as TMEM A operand, V MN-major) vs torch and vs the mma.sync kernel."""
+    g = torch.Generator().manual_seed(frames)
+    qkv = (torch.randn(frames * 257, 4224, generator=g) * scale_in).to(torch.bfloat16)
+    want = _attn_ref(qkv[:, :1408], qkv[:, 1408:2816], qkv[:, 2816:], frames, 16, 257, 257, 88, 88 ** -0.5)
+    qd = qkv.to(DEV)
+    got = ops.vit_attention(qd, frames, 88 ** -0.5)
+    err = _relerr(got.cpu(), want)
+    assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
+    other = ops.attention(qd[:, :1408], qd[:, 1408:2816], qd[:, 2816:], frames, 16, 257, 257, 88, 88 ** -0.5)
+    assert _relerr(got.cpu(), other.cpu()) < 1.5e-2
+
+
 def test_cast_and_group_mean():
     g = torch.Generator().manual_seed(8)
     x = torch.randn(77, 768, generator=g)

@@ -1,0 +1,528 @@
+// ViT self-attention on the 5th-gen tensor cores (S = 257 tokens, 16 heads x 88, fused QKV layout [F*257, 3*16*88]).
+//
+// One persistent CTA per SM walks (frame, head) items.  Per item the 256 patch-token queries form two 128-row tiles
+// (the CLS query row is done by a SIMT warp, see below); all 257 keys are processed in one shot, so there is no online
+// rescaling:
+//   warp 0      TMA producer: 3-D tensor map over [rows][q|k|v x head][88] -> Q tiles, K and V in shared memory
+//               (SWIZZLE_128B, 64-wide d blocks; columns 88..127 are zero-filled by TMA bounds checking)
+//   warp 1      MMA issuer (one thread):
+//                 S[128 x 272] = Q K^T     tcgen05.mma kind::f16, A/B K-major from shared memory (N=256 + N=16)
+//                 O[128 x  96] = P V       A = P in TENSOR MEMORY (bf16, written by the softmax warps), B = V as an
+//                                          MN-major shared-memory operand (no transpose of V anywhere)
+//   warp 2      TMEM allocator: S fp32 [0,272) | P bf16 [272,408) | O fp32 [416,512)
+//   warp 3      CLS query row (row 0 of every image) in fp32 on CUDA cores, reading the swizzled K/V tiles in smem
+//   warps 4-11  softmax + epilogue: two threads per query row (136 keys each) read S from TMEM ONCE into registers,
+//               exchange the row max through shared memory, exponentiate (fp32, exp2), write P back to TMEM as bf16,
+//               later read O, scale by 1/rowsum and store bf16.
+// The score matrix never leaves the SM (the reference materialises [F,16,257,257], xblip2.py:174-189).
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace tgb {
+
+constexpr int VA_S = 257;
+constexpr int VA_D = 88;
+constexpr int VA_H = 16;
+constexpr int VA_BOX_ROWS = 136;                       // TMA box rows (272 keys = 2 boxes; Q tiles use the first 128)
+constexpr int VA_BOX_BYTES = VA_BOX_ROWS * 128;        // 17408, a multiple of 1024
+constexpr int VA_KBLK_BYTES = 2 * VA_BOX_BYTES;        // one 64-wide d block of K or V: 272 rows x 128 B
+constexpr int VA_THREADS = 384;
+constexpr uint32_t VA_COL_S = 0, VA_COL_P = 272, VA_COL_O = 416;
+
+constexpr int VA_SMEM_Q = 0;                           // [2 tiles][2 dblk][136 x 128 B]
+constexpr int VA_SMEM_K = 4 * VA_BOX_BYTES;            // [2 dblk][272 x 128 B]
+constexpr int VA_SMEM_V = VA_SMEM_K + 2 * VA_KBLK_BYTES;
+constexpr int VA_SMEM_BAR = VA_SMEM_V + 2 * VA_KBLK_BYTES;      // 208896
+constexpr int VA_SMEM_XMAX = VA_SMEM_BAR + 256;        // float [2][2][128]  (double buffered by tile parity)
+constexpr int VA_SMEM_XSUM = VA_SMEM_XMAX + 2048;      // float [2][2][128]
+constexpr int VA_SMEM_CLS = VA_SMEM_XSUM + 2048;       // float q0[96] + p[288]
+constexpr int VA_SMEM_TOTAL = VA_SMEM_CLS + (96 + 288) * 4 + 1024;   // + alignment slack
+
+struct VitAttnParams {
+  const __nv_bfloat16* qkv;
+  __nv_bfloat16* out;
+  long long ld_qkv, ld_out;
+  int frames;
+  int num_items;            // frames * 16
+  float scale_log2;
+};
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// MN-major SWIZZLE_128B operand: 64 MN elements (128 B) per K row, 8-row groups every `sbo` bytes, 64-wide MN blocks
+// every `lbo` bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+#define TGB_R8(a, o) "=r"(a[o]), "=r"(a[o + 1]), "=r"(a[o + 2]), "=r"(a[o + 3]), "=r"(a[o + 4]), "=r"(a[o + 5]), "=r"(a[o + 6]), "=r"(a[o + 7])
+#define TGB_W8(a, o) "r"(a[o]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), "r"(a[o + 6]), "r"(a[o + 7])
+
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[NREG]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : TGB_R8(v, OFF), TGB_R8(v, OFF + 8), TGB_R8(v, OFF + 16), TGB_R8(v, OFF + 24)
+      : "r"(taddr));
+}
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[NREG]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : TGB_R8(v, OFF), TGB_R8(v, OFF + 8)
+      : "r"(taddr));
+}
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[NREG]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : TGB_R8(v, OFF) : "r"(taddr));
+}
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[NREG]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), TGB_W8(v, OFF), TGB_W8(v, OFF + 8), TGB_W8(v, OFF + 16), TGB_W8(v, OFF + 24)
+      : "memory");
+}
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[NREG]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[OFF]), "r"(v[OFF + 1]),
+               "r"(v[OFF + 2]), "r"(v[OFF + 3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(VA_THREADS, 1)
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const VitAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + VA_SMEM_Q;
+  uint8_t* sK = smem + VA_SMEM_K;
+  uint8_t* sV = smem + VA_SMEM_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + VA_SMEM_BAR);
+  uint64_t* q_full = bars + 0;     // [2]
+  uint64_t* q_free = bars + 2;     // [2]
+  uint64_t* k_full = bars + 4;
+  uint64_t* k_free = bars + 5;
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_free = bars + 7;
+  uint64_t* s_full = bars + 8;
+  uint64_t* s_free = bars + 9;
+  uint64_t* p_full = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint64_t* o_free = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* xmax = reinterpret_cast<float*>(smem + VA_SMEM_XMAX);
+  float* xsum = reinterpret_cast<float*>(smem + VA_SMEM_XSUM);
+  float* cls_q = reinterpret_cast<float*>(smem + VA_SMEM_CLS);
+  float* cls_p = cls_q + 96;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == 1 && lane == 0) {
+    mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
+    mbar_init(&q_free[0], 1); mbar_init(&q_free[1], 1);
+    mbar_init(k_full, 1); mbar_init(k_free, 2);      // k_free / v_free: tcgen05.commit + the CLS warp
+    mbar_init(v_full, 1); mbar_init(v_free, 2);
+    mbar_init(s_full, 1); mbar_init(s_free, 256);
+    mbar_init(p_full, 256);
+    mbar_init(o_full, 1); mbar_init(o_free, 256);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int i = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+        const int b = w / VA_H, h = w - b * VA_H;
+        const int row0 = b * VA_S;
+        const uint32_t ph = i & 1;
+        mbar_wait(k_free, ph ^ 1);
+        mbar_arrive_expect_tx(k_full, 2 * VA_KBLK_BYTES);
+#pragma unroll
+        for (int db = 0; db < 2; ++db)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sK + db * VA_KBLK_BYTES + hf * VA_BOX_BYTES, &tmap, k_full, db * 64, VA_H + h, row0 + hf * VA_BOX_ROWS);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_free[t], ph ^ 1);
+          mbar_arrive_expect_tx(&q_full[t], 2 * VA_BOX_BYTES);
+#pragma unroll
+          for (int db = 0; db < 2; ++db)
+            tma_load_3d(sQ + (t * 2 + db) * VA_BOX_BYTES, &tmap, &q_full[t], db * 64, h, row0 + 1 + t * 128);
+        }
+        mbar_wait(v_free, ph ^ 1);
+        mbar_arrive_expect_tx(v_full, 2 * VA_KBLK_BYTES);
+#pragma unroll
+        for (int db = 0; db < 2; ++db)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sV + db * VA_KBLK_BYTES + hf * VA_BOX_BYTES, &tmap, v_full, db * 64, 2 * VA_H + h, row0 + hf * VA_BOX_ROWS);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s256 = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 96) | (1u << 16);     // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      auto issue_pv = [&](int gp) {
+        const int ip = gp >> 1, tp = gp & 1;
+        if (tp == 0) mbar_wait(v_full, ip & 1);
+        mbar_wait(p_full, gp & 1);
+        mbar_wait(o_free, (gp & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 17; ++kk) {
+          const uint64_t db = umma_desc_mn_sw128(v_addr + kk * 2048, VA_KBLK_BYTES, 1024);
+          umma_bf16_ts(tmem_base + VA_COL_O, tmem_base + VA_COL_P + kk * 8, db, idesc_pv, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        if (tp == 1) umma_commit(v_free);
+      };
+      int g = 0, i = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+        const uint32_t ph = i & 1;
+        mbar_wait(k_full, ph);
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_full[t], ph);
+          mbar_wait(s_free, (g & 1) ^ 1);
+          tc_fence_after();
+          uint32_t accum = 0;
+#pragma unroll
+          for (int db = 0; db < 2; ++db) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (db == 1 && ks >= 2) break;                       // d = 96..127 is all zero
+              const uint64_t da = umma_desc_sw128(q_addr + (t * 2 + db) * VA_BOX_BYTES + ks * 32);
+              const uint64_t dk = umma_desc_sw128(k_addr + db * VA_KBLK_BYTES + ks * 32);
+              const uint64_t dk2 = umma_desc_sw128(k_addr + db * VA_KBLK_BYTES + 256 * 128 + ks * 32);
+              umma_bf16_ss(tmem_base + VA_COL_S, da, dk, idesc_s256, accum);
+              umma_bf16_ss(tmem_base + VA_COL_S + 256, da, dk2, idesc_s16, accum);
+              accum = 1;
+            }
+          }
+          umma_commit(s_full);
+          umma_commit(&q_free[t]);
+          if (t == 1) umma_commit(k_free);
+          if (g > 0) issue_pv(g - 1);
+          ++g;
+        }
+      }
+      if (g > 0) issue_pv(g - 1);
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ================================================================ CLS query row (fp32, CUDA cores)
+    // Reads K and V from the SAME swizzled shared-memory tiles the tensor cores use (element (key r, d c) of a
+    // 64-wide d block lives at (r/8)*1024 + (r%8)*128 + (((c/8) ^ (r%8)) * 16) + (c%8)*2), so the CLS row costs no
+    // extra global traffic; it co-signs k_free / v_free.
+    int i = 0;
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+      const int b = w / VA_H, h = w - b * VA_H;
+      const long long row0 = (long long)b * VA_S;
+      const __nv_bfloat16* qrow = p.qkv + row0 * p.ld_qkv + h * VA_D;
+      for (int c = lane; c < VA_D / 2; c += 32) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qrow + 2 * c));
+        cls_q[2 * c] = f.x;
+        cls_q[2 * c + 1] = f.y;
+      }
+      __syncwarp();
+      mbar_wait(k_full, i & 1);
+      float sc[9];
+#pragma unroll
+      for (int it = 0; it < 9; ++it) sc[it] = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < VA_D / 8; ++c) {                      // 11 chunks of 8 d
+        const float4 qa = *reinterpret_cast<const float4*>(cls_q + c * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(cls_q + c * 8 + 4);
+        const uint8_t* kblk = sK + (c >> 3) * VA_KBLK_BYTES;
+#pragma unroll
+        for (int it = 0; it < 9; ++it) {
+          const int r = it * 32 + lane;                          // rows up to 287 < 272? guard below
+          if (r < VA_S) {
+            const uint4 kk = *reinterpret_cast<const uint4*>(kblk + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4));
+            const float2 k0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk.x));
+            const float2 k1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk.y));
+            const float2 k2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk.z));
+            const float2 k3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk.w));
+            float d = sc[it];
+            d = fmaf(k0.x, qa.x, d); d = fmaf(k0.y, qa.y, d); d = fmaf(k1.x, qa.z, d); d = fmaf(k1.y, qa.w, d);
+            d = fmaf(k2.x, qb.x, d); d = fmaf(k2.y, qb.y, d); d = fmaf(k3.x, qb.z, d); d = fmaf(k3.y, qb.w, d);
+            sc[it] = d;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(k_free);                        // done reading K (second arrival: tcgen05.commit)
+      float m = -INFINITY;
+#pragma unroll
+      for (int it = 0; it < 9; ++it) {
+        sc[it] = (it * 32 + lane < VA_S) ? sc[it] * p.scale_log2 : -INFINITY;
+        m = fmaxf(m, sc[it]);
+      }
+      m = warp_max(m);
+      float l = 0.f;
+#pragma unroll
+      for (int it = 0; it < 9; ++it) {
+        const int j = it * 32 + lane;
+        const float pj = (j < VA_S) ? ex2_approx(sc[it] - m) : 0.f;
+        cls_p[j] = pj;
+        l += pj;
+      }
+      l = warp_sum(l);
+      __syncwarp();
+      mbar_wait(v_full, i & 1);
+      // O[d] = sum_j p_j V[j][d]: lane -> (d chunk of 8 = lane % 11, key half = lane / 11), lanes 22..31 idle
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      if (lane < 22) {
+        const int dc = lane % 11, kh = lane / 11;
+        const uint8_t* vblk = sV + (dc >> 3) * VA_KBLK_BYTES;
+        const int j0 = kh * 129, j1 = kh == 0 ? 129 : VA_S;
+#pragma unroll 4
+        for (int j = j0; j < j1; ++j) {
+          const uint4 vv = *reinterpret_cast<const uint4*>(vblk + (j >> 3) * 1024 + (j & 7) * 128 + (((dc & 7) ^ (j & 7)) << 4));
+          const float pj = cls_p[j];
+          const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv.x));
+          const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv.y));
+          const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv.z));
+          const float2 v3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv.w));
+          acc[0] = fmaf(pj, v0.x, acc[0]); acc[1] = fmaf(pj, v0.y, acc[1]);
+          acc[2] = fmaf(pj, v1.x, acc[2]); acc[3] = fmaf(pj, v1.y, acc[3]);
+          acc[4] = fmaf(pj, v2.x, acc[4]); acc[5] = fmaf(pj, v2.y, acc[5]);
+          acc[6] = fmaf(pj, v3.x, acc[6]); acc[7] = fmaf(pj, v3.y, acc[7]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_free);                        // done reading V
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += __shfl_down_sync(0xffffffffu, acc[e], 11);
+      if (lane < 11) {
+        const float inv = 1.f / l;
+        uint4 o;
+        o.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+        o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+        o.z = pack_bf16(acc[4] * inv, acc[5] * inv);
+        o.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+        *reinterpret_cast<uint4*>(p.out + row0 * p.ld_out + h * VA_D + lane * 8) = o;
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ================================================================ softmax + epilogue (2 threads per query row)
+    const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;            // keys [0,136) or [136,272); O columns [0,48) or [48,96)
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int nvalid = half == 0 ? 136 : (VA_S - 136);     // valid keys in this half (121 in the second)
+    int g = 0;
+    int pb = 0, ph_ = 0, pt = 0;                 // (frame, head, tile) of the previous tile, for its deferred epilogue
+
+    auto epilogue = [&](int gp, int eb, int eh, int et) {
+      const float l = xsum[((gp & 1) * 2 + 0) * 128 + row] + xsum[((gp & 1) * 2 + 1) * 128 + row];
+      const float inv = 1.f / l;
+      mbar_wait(o_full, gp & 1);
+      tc_fence_after();
+      // 48 (or 40) fp32 columns -> 24 packed bf16 registers, 16 columns at a time to keep register pressure low
+      uint32_t ob[24];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t o[16];
+        tmem_ld16<0>(lane_base + VA_COL_O + half * 48 + c * 16, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          ob[c * 8 + e] = pack_bf16(__uint_as_float(o[2 * e]) * inv, __uint_as_float(o[2 * e + 1]) * inv);
+      }
+      tc_fence_before();
+      mbar_arrive(o_free);
+      __nv_bfloat16* dst = p.out + ((long long)eb * VA_S + 1 + et * 128 + row) * p.ld_out + eh * VA_D + half * 48;
+      const int nchunks = half == 0 ? 6 : 5;     // 48 or 40 valid d columns (d 88..95 is padding)
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        if (c < nchunks) reinterpret_cast<uint4*>(dst)[c] = make_uint4(ob[4 * c], ob[4 * c + 1], ob[4 * c + 2], ob[4 * c + 3]);
+    };
+
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+      const int b = w / VA_H, h = w - b * VA_H;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        uint32_t sv[136];
+        const uint32_t s_addr = lane_base + VA_COL_S + half * 136;
+        tmem_ld32<0>(s_addr, sv);
+        tmem_ld32<32>(s_addr + 32, sv);
+        tmem_ld32<64>(s_addr + 64, sv);
+        tmem_ld32<96>(s_addr + 96, sv);
+        tmem_ld8<128>(s_addr + 128, sv);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free);                      // S is in registers: the next tile's QK^T may overwrite it
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;      // 4 independent chains
+#pragma unroll
+        for (int j = 0; j < 136; j += 4) {
+          if (j + 0 < nvalid) m0 = fmaxf(m0, __uint_as_float(sv[j + 0]));
+          if (j + 1 < nvalid) m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
+          if (j + 2 < nvalid) m2 = fmaxf(m2, __uint_as_float(sv[j + 2]));
+          if (j + 3 < nvalid) m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
+        }
+        float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        float* xm = xmax + (g & 1) * 256;
+        xm[half * 128 + row] = m;
+        named_bar_sync(1 + quarter, 64);
+        m = fmaxf(xm[row], xm[128 + row]);
+        const float negmc = -m * p.scale_log2;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        const float sl2 = p.scale_log2;
+        // exponentiate in place: sv[j] (j < 68) is overwritten with the packed bf16 pair (P[2j], P[2j+1]) as soon as
+        // its two source values are dead.  The previous tile's epilogue sits between the two halves so that its
+        // temporaries fit next to the (by then half-packed) score registers.
+#pragma unroll
+        for (int j = 0; j < 34; j += 2) {
+          const float p0 = (2 * j + 0 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 0]), sl2, negmc)) : 0.f;
+          const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), sl2, negmc)) : 0.f;
+          const float p2 = (2 * j + 2 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 2]), sl2, negmc)) : 0.f;
+          const float p3 = (2 * j + 3 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 3]), sl2, negmc)) : 0.f;
+          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+          sv[j] = pack_bf16(p0, p1);
+          sv[j + 1] = pack_bf16(p2, p3);
+        }
+        if (g > 0) epilogue(g - 1, pb, ph_, pt);  // also guarantees P V of the previous tile is done with the P region
+#pragma unroll
+        for (int j = 34; j < 68; j += 2) {
+          const float p0 = (2 * j + 0 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 0]), sl2, negmc)) : 0.f;
+          const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), sl2, negmc)) : 0.f;
+          const float p2 = (2 * j + 2 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 2]), sl2, negmc)) : 0.f;
+          const float p3 = (2 * j + 3 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 3]), sl2, negmc)) : 0.f;
+          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+          sv[j] = pack_bf16(p0, p1);
+          sv[j + 1] = pack_bf16(p2, p3);
+        }
+        const float l = (l0 + l1) + (l2 + l3);
+        const uint32_t p_addr = lane_base + VA_COL_P + half * 68;
+        tmem_st32<0>(p_addr, sv);
+        tmem_st32<32>(p_addr + 32, sv);
+        tmem_st4<64>(p_addr + 64, sv);
+        xsum[((g & 1) * 2 + half) * 128 + row] = l;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        pb = b; ph_ = h; pt = t;
+        ++g;
+      }
+    }
+    if (g > 0) {
+      named_bar_sync(1 + quarter, 64);            // the partner's row sum of the last tile is visible
+      epilogue(g - 1, pb, ph_, pt);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 va_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  return fn;
+}
+
+}  // namespace tgb
+
+using namespace tgb;
+
+extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int frames,
+                                      float scale, tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(qkv && out && frames >= 0, "vit_attention: null pointer");
+  TGB_CHECK_ARG(ld_qkv % 8 == 0 && ld_qkv >= 3 * VA_H * VA_D && ld_out % 8 == 0 && ld_out >= VA_H * VA_D,
+                "vit_attention: leading dims must be multiples of 8 and cover 3*16*88 / 16*88 columns");
+  TGB_CHECK_ARG(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "vit_attention: buffers must be 16-byte aligned");
+  if (frames == 0) return TGB_OK;
+  auto fn = va_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return TGB_ECUDA;
+  }
+  CUtensorMap map;
+  cuuint64_t dims[3] = {VA_D, 3 * VA_H, (cuuint64_t)frames * VA_S};
+  cuuint64_t strides[2] = {VA_D * 2, (cuuint64_t)ld_qkv * 2};
+  cuuint32_t box[3] = {64, 1, VA_BOX_ROWS};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("vit_attention: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return TGB_ECUDA;
+  }
+  static bool configured = false;
+  if (!configured) {
+    TGB_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM_TOTAL));
+    configured = true;
+  }
+  VitAttnParams p;
+  p.qkv = (const __nv_bfloat16*)qkv;
+  p.out = (__nv_bfloat16*)out;
+  p.ld_qkv = ld_qkv;
+  p.ld_out = ld_out;
+  p.frames = frames;
+  p.num_items = frames * VA_H;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
+  vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM_TOTAL, (cudaStream_t)stream>>>(map, p);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}

@@ -122,6 +122,7 @@ class Blip2VisionModel(_KernelModule):
             raise ValueError(f"embed_dim must be divisible by num_heads (got `embed_dim`: {d} and `num_heads`: {self.heads}).")
         self.tokens = (self.image // self.patch) ** 2 + 1
         self.max_frames_per_pass = max_frames_per_pass
+        self.use_tc_attention = True
         self.embeddings = _Holder()
         self.embeddings.class_embedding = nn.Parameter(torch.randn(1, 1, d) * 0.02)
         self.embeddings.position_embedding = nn.Parameter(torch.randn(1, self.tokens, d) * 0.02)
@@ -184,10 +185,14 @@ class Blip2VisionModel(_KernelModule):
         ctx = torch.empty((m, d), dtype=torch.bfloat16, device=dev)
         hid = torch.empty((m, self.mlp), dtype=torch.bfloat16, device=dev)
         scale = self.head_dim ** -0.5
+        tc_attn = self.use_tc_attention and (h, self.head_dim, s) == (16, 88, 257)
         for lw in pk.layers:
             ops.layernorm(x, lw.ln1[0], lw.ln1[1], self.eps, out_bf16=ln)
             ops.gemm(ln, lw.qkv_w, lw.qkv_b, ops.EPI_BF16, out=qkv)
-            ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nf, h, s, s, self.head_dim, scale, out=ctx)
+            if tc_attn:      # EVA-ViT-g shape: tcgen05 attention (S in TMEM, P as TMEM operand, V MN-major)
+                ops.vit_attention(qkv, nf, scale, out=ctx)
+            else:            # any other ViT shape: generic mma.sync flash kernel
+                ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nf, h, s, s, self.head_dim, scale, out=ctx)
             ops.gemm(ctx, lw.proj_w, lw.proj_b, ops.EPI_F32_RESID, out=x, resid=x)
             ops.layernorm(x, lw.ln2[0], lw.ln2[1], self.eps, out_bf16=ln)
             ops.gemm(ln, lw.fc1_w, lw.fc1_b, ops.EPI_BF16_GELU, out=hid)

@@ -332,3 +332,21 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor])
     out = torch.empty((m, n), dtype=torch.float32, device=x.device)
     check(_lib.load().tgb_linear_small_f32(_p(x), ldx, _p(w), _p(bias), m, n, k, _p(out), n, _stream()))
     return out
+
+
+def vit_attention(qkv: torch.Tensor, frames: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tcgen05 self-attention for the EVA-ViT-g shape: qkv bf16 [frames*257, 4224] -> ctx bf16 [frames*257, 1408]."""
+    _need(qkv, torch.bfloat16, "qkv", contiguous=False)
+    if qkv.dim() != 2 or qkv.stride(1) != 1 or qkv.shape[0] != frames * 257 or qkv.shape[1] < 4224:
+        raise _lib.TgbError("vit_attention: qkv must be [frames*257, >=4224] bf16")
+    if out is None:
+        out = torch.empty((frames * 257, 1408), dtype=torch.bfloat16, device=qkv.device)
+    global _PROFILE
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.load().tgb_vit_attention_bf16(_p(qkv), qkv.stride(0), _p(out), out.stride(0), frames, float(scale), _stream()))
+    if _PROFILE is not None:
+        e1.record()
+        _PROFILE.append(("attention", (frames, 16, 257, 257, 88), e0, e1))
+    return out
