@@ -236,24 +236,60 @@ def run_ours(args):
             enc.token_exchange.wait()
         return out
 
-    def step_e2e():
-        batch = to_batch({kk: v.to(dev, non_blocking=True) for kk, v in host.items()})
-        out = enc.encode_u8(batch, generator=gen)
-        if enc.token_exchange is not None:
-            enc.token_exchange.wait()
-        out_host.copy_(out, non_blocking=True)
+    # e2e: the same step through the public API from pinned host buffers.  Input upload (H2D), compute and token
+    # download (D2H) run on three streams with double-buffered device inputs, so step k+1's upload and step k-1's
+    # download overlap step k's compute -- every byte still crosses PCIe inside the timed region.
+    h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    dev_in = [{kk: torch.empty_like(v, device=dev) for kk, v in host.items()} for _ in range(2)]
+
+    def run_e2e(steps):
+        main = torch.cuda.current_stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_out = torch.cuda.Event()
+        h2d_stream.wait_stream(main)
+        d2h_stream.wait_stream(main)
+
+        def upload(sidx):
+            slot = sidx % 2
+            with torch.cuda.stream(h2d_stream):
+                if sidx >= 2:
+                    h2d_stream.wait_event(ev_done[slot])          # the compute that last read this slot
+                for kk, v in host.items():
+                    dev_in[slot][kk].copy_(v, non_blocking=True)
+                ev_in[slot].record(h2d_stream)
+
+        upload(0)
+        for sidx in range(steps):
+            slot = sidx % 2
+            if sidx + 1 < steps:
+                upload(sidx + 1)
+            main.wait_event(ev_in[slot])
+            out = enc.encode_u8(to_batch(dev_in[slot]), generator=gen)
+            if enc.token_exchange is not None:
+                enc.token_exchange.wait()
+            ev_done[slot].record(main)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(ev_done[slot])
+                out_host.copy_(out, non_blocking=True)
+                out.record_stream(d2h_stream)
+                ev_out.record(d2h_stream)
+        main.wait_event(ev_out)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, whole=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        if whole:
+            fn(steps)
+        else:
+            for _ in range(steps):
+                fn()
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
@@ -279,8 +315,8 @@ def run_ours(args):
     launches = ops.LAUNCHES - launches0
     clock_info = clocks.stop() if rank == 0 else None
 
-    step_e2e()                                   # warm the pinned paths
-    ms_e2e = timed(step_e2e, args.steps)
+    run_e2e(2)                                   # warm the pinned paths
+    ms_e2e = timed(run_e2e, args.steps, whole=True)
 
     # ---- roofline leg: CUDA-event time of every GEMM launch of one more step (same stream, same shapes)
     with ops.profile_launches() as prof:

@@ -135,7 +135,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const int m_blk = tile / p.num_n_blocks;
         const int n_blk = tile - m_blk * p.num_n_blocks;
         const int a_row = (m_blk * CG + (int)rank) * BM;
-        const int b_row = n_blk * BN + (int)rank * Cfg::B_ROWS;
+        // a last N tile that is at most half full is computed with a half-width MMA: each CTA then supplies
+        // cur_bn/CG rows of W (the TMA box still has B_ROWS rows; the extra rows are never read)
+        const int cur_bn = (BN == 256 && p.N - n_blk * BN <= BN / 2) ? BN / 2 : BN;
+        const int b_row = n_blk * BN + (int)rank * (cur_bn / CG);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -157,12 +160,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer (one thread of the leader CTA)
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+      constexpr uint32_t idesc_full = umma_idesc_bf16(BM * CG, BN);
+      constexpr uint32_t idesc_half = umma_idesc_bf16(BM * CG, BN / 2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int n_blk_mma = tile % p.num_n_blocks;
+        const uint32_t idesc = (BN == 256 && p.N - n_blk_mma * BN <= BN / 2) ? idesc_half : idesc_full;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
