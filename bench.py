@@ -326,6 +326,14 @@ def run_ours(args):
     attn_ms = sum(t for (nm, shp, t) in prof.records if nm == "attention")
     ln_ms = sum(t for (nm, shp, t) in prof.records if nm == "layernorm")
     n_gemm = sum(1 for r in prof.records if r[0] == "gemm")
+    by_shape = {}
+    for nm, shp, t in prof.records:
+        if nm == "gemm":
+            e = by_shape.setdefault(shp, [0, 0.0])
+            e[0] += 1
+            e[1] += t
+    # the dominant kernel = the GEMM shape with the largest share of the step (fc1 + GELU of the ViT MLP)
+    dom_shape, (dom_n, dom_ms) = max(by_shape.items(), key=lambda kv: kv[1][1])
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -333,7 +341,17 @@ def run_ours(args):
     except OSError:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    achieved_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    achieved_tf = gemm_flops(dom_shape) / (dom_ms / dom_n * 1e-3) / 1e12
+    all_gemm_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    try:                      # DRAM bytes of that launch from the committed `ncu --set full` capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tr = json.load(f)
+        if list(dom_shape) == tr.get("shape"):
+            traffic = tr.get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    epi_names = {0: "bias", 1: "bias+erf-GELU", 2: "bias (fp32 out)", 3: "bias+fp32 residual", 4: "row-bias (patch embed)"}
 
     if rank != 0:
         if world > 1:
@@ -349,9 +367,17 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clock_info,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
-                     "kernel": "gemm_bf16_tcgen05_kernel (all launches of one step)", "launches": n_gemm,
-                     "kernel_ms_per_step": gemm_ms, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                     "kernel": f"gemm_bf16_tcgen05_kernel M={dom_shape[0]} N={dom_shape[1]} K={dom_shape[2]} "
+                               f"epilogue={epi_names.get(dom_shape[3], dom_shape[3])}",
+                     "launches": dom_n, "avg_launch_ms": dom_ms / dom_n, "share_of_step": dom_ms / ms,
+                     "algorithmic_flops_per_launch": gemm_flops(dom_shape),
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                     "all_gemm": {"launches": n_gemm, "ms_per_step": gemm_ms, "tflops": all_gemm_tf,
+                                  "frac": all_gemm_tf / peak_tf if peak_tf else None},
+                     "gemm_shapes": [{"M": k[0], "N": k[1], "K": k[2], "epilogue": epi_names.get(k[3], k[3]), "launches": v[0],
+                                      "ms": round(v[1], 3), "tflops": round(gemm_flops(k) * v[0] / (v[1] * 1e-3) / 1e12, 1)}
+                                     for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]],
                      "attention_ms_per_step": attn_ms, "layernorm_ms_per_step": ln_ms},
         "path_tflops": frames_total / world * GFLOP_PER_FRAME / (ms * 1e-3) / 1e3,
         "path_frac_of_peak": (b * k * GFLOP_PER_FRAME / (ms * 1e-3) / 1e3) / peak_tf if peak_tf else None,

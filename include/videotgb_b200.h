@@ -108,6 +108,8 @@ TGB_API int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw
 
 /* Debug / test knob: 0 = choose per problem (default), 1 = single-CTA 128xBN tiles, 2 = CTA-pair 256xBN tiles.      */
 TGB_API int tgb_gemm_set_cta_group(int cta_group);
+/* Debug / test knob: epilogue warps per CTA, 0 = choose per epilogue (16 for the residual epilogue, else 8).               */
+TGB_API int tgb_gemm_set_epilogue_warps(int warps);
 
 /* ---------------------------------------------------------------- LayerNorm ---------------------------
  * nn.LayerNorm over the last dim (xblip2.py:222-224,511; :703,:782; xropebert.py:91).  x: f32 [M,N] (ldx).

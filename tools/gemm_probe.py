@@ -93,16 +93,12 @@ if __name__ == "__main__":
         ok = probe(*shape) and ok
     if "--bench" in sys.argv and ok:
         M = 257 * 256
-        for cg in (2, 1):
-            ops.gemm_set_cta_group(cg)
-            print("cta_group", cg)
-            for bn in (256, 176, 128):
-                bench(M, 1408, 1408, ops.EPI_F32_RESID, bn)
+        for ew in (8, 16):
+            ops.gemm_set_epilogue_warps(ew)
+            print("cta_group 2, epilogue warps", ew)
+            bench(M, 1408, 1408, ops.EPI_F32_RESID, 256)
             bench(M, 4224, 1408, ops.EPI_BF16, 256)
-            bench(M, 4224, 1408, ops.EPI_BF16, 176)
             bench(M, 6144, 1408, ops.EPI_BF16_GELU, 256)
-            bench(M, 6144, 1408, ops.EPI_BF16, 256)
             bench(M, 1408, 6144, ops.EPI_F32_RESID, 256)
-            bench(M, 1408, 6144, ops.EPI_F32_RESID, 176)
             bench(8192, 8192, 8192, ops.EPI_BF16, 256)
-        ops.gemm_set_cta_group(0)
+        ops.gemm_set_epilogue_warps(0)

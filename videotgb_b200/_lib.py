@@ -31,6 +31,7 @@ SIGNATURES = {
     "tgb_gemm_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_int, c_int,
                        c_vp, c_i64, c_int, c_vp], c_int),
     "tgb_gemm_set_cta_group": ([c_int], c_int),
+    "tgb_gemm_set_epilogue_warps": ([c_int], c_int),
     "tgb_layernorm_f32": ([c_vp, c_i64, c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp], c_int),
     "tgb_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int,
                             c_int, c_f32, c_vp], c_int),

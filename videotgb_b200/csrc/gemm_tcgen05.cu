@@ -26,11 +26,8 @@ namespace tgb {
 constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 16;                       // 4 per TMEM lane quarter / SM sub-partition
-constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int STG_PITCH = 20;                        // floats per staged row: 16 + 4 pad -> conflict-free 16-B phases
-constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;
 
 struct GemmParams {
   int M, N, K;
@@ -44,8 +41,12 @@ struct GemmParams {
   long long ldo, ldr;
 };
 
-template <int BN, int CG>
+// EW = number of epilogue warps (8 or 16: 2 or 4 per TMEM lane quarter).  16 hides the global-memory latency of the
+// residual read-modify-write; 8 leaves room for one more pipeline stage.
+template <int BN, int CG, int EW>
 struct GemmCfg {
+  static constexpr int THREADS = 128 + EW * 32;
+  static constexpr int STG_BYTES = EW * 32 * STG_PITCH * 4;
   static constexpr int B_ROWS = BN / CG;                 // W rows staged per CTA
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
@@ -82,12 +83,13 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, float4 v, c
   }
 }
 
-template <int BN, int EPI, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int EPI, int CG, int EW>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, EW>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int STG_BYTES = Cfg::STG_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -116,7 +118,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], CG * EPI_WARPS);  // lane 0 of every epilogue warp of every CTA of the pair
+      mbar_init(&tmem_empty[s], CG * EW);  // lane 0 of every epilogue warp of every CTA of the pair
     }
     fence_mbar_init();
   }
@@ -192,14 +194,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ------------------------------------------------------------- epilogue (16 warps)
+    // ------------------------------------------------------------- epilogue (EW warps)
     // TMEM hands every thread one ROW (lane == row) of a 16-column chunk.  The chunk is transposed through a padded
     // per-warp shared-memory tile so that the global side is coalesced: thread -> (row = i*8 + lane/4, 4 columns at
     // (lane%4)*4), i.e. 64 contiguous bytes per row and 8 rows per instruction for the residual read and the store.
     const int ew = warp - 4;
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
     const int sub = ew >> 2;                       // which 16-column chunks: sub, sub+NSUB, ...
-    constexpr int NSUB = EPI_WARPS / 4;
+    constexpr int NSUB = EW / 4;
     constexpr int NCHUNK = BN / 16;
     float* stg = staging + ew * (32 * STG_PITCH);
     const int trow = lane >> 2;
@@ -333,9 +335,11 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
 
 static int g_force_cg = 0;     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
-template <int BN, int EPI, int CG>
-static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
+static int g_force_ew = 0;     // 0 = choose per epilogue, 8 / 16 = force
+
+template <int BN, int EPI, int CG, int EW>
+static int launch_gemm_ew(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG, EW>;
   p.num_m_blocks = (p.M + BM * CG - 1) / (BM * CG);
   p.num_n_blocks = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
@@ -344,7 +348,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
   if (st != TGB_OK) return st;
   st = make_tmap(&tb, W, p.N, p.K, ldw, Cfg::B_ROWS);
   if (st != TGB_OK) return st;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, EW>;
   static bool configured = false;
   if (!configured) {
     TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -355,7 +359,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -367,6 +371,15 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
   cfg.numAttrs = 1;
   TGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return TGB_OK;
+}
+
+template <int BN, int EPI, int CG>
+static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmParams& p, cudaStream_t stream) {
+  // measured (tools/gemm_ab.py, interleaved medians): 16 warps help the fp32-residual epilogue at short K (proj: 940 vs
+  // 799 TF/s); bias / GELU epilogues are marginally better with 8 warps and the extra pipeline stage
+  int ew = g_force_ew ? g_force_ew : (EPI == TGB_EPI_F32_RESID ? 16 : 8);
+  if (ew == 16) return launch_gemm_ew<BN, EPI, CG, 16>(A, lda, W, ldw, p, stream);
+  return launch_gemm_ew<BN, EPI, CG, 8>(A, lda, W, ldw, p, stream);
 }
 
 template <int BN, int CG>
@@ -424,6 +437,15 @@ static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
 }  // namespace tgb
 
 using namespace tgb;
+
+extern "C" int tgb_gemm_set_epilogue_warps(int warps) {
+  if (warps != 0 && warps != 8 && warps != 16) {
+    set_last_error("epilogue warps must be 0 (auto), 8 or 16");
+    return TGB_EINVAL;
+  }
+  g_force_ew = warps;
+  return TGB_OK;
+}
 
 extern "C" int tgb_gemm_set_cta_group(int cta_group) {
   if (cta_group < 0 || cta_group > 2) {

@@ -195,6 +195,11 @@ def gemm_set_cta_group(cta_group: int) -> None:
     check(_lib.load().tgb_gemm_set_cta_group(int(cta_group)))
 
 
+def gemm_set_epilogue_warps(warps: int) -> None:
+    """0 = auto (16 for the residual epilogue, else 8), 8 or 16; test / debug knob."""
+    check(_lib.load().tgb_gemm_set_epilogue_warps(int(warps)))
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, want_bf16: bool = True,
               want_f32: bool = False, out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
