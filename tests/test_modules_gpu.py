@@ -218,3 +218,64 @@ def test_pipeline_end_to_end():
     out_mean = enc.encode(batch, gumbel=[x.to(DEV) for x in gum], assemble="mean")
     assert out_mean.shape == (b, 32, 2048)
     assert_parity(out_mean, torch_ref.project_tokens(to_dev(hsd), qo, b, mode="mean"), "mean-pooled tokens")
+
+
+def test_pipeline_instructblip_long_video():
+    """BASELINE config 3 shape (reduced depth): one long video, T flow frames == candidates, the sampler selects k frames,
+    instruction-conditioned Q-Former with a padded instruction, mode="multi_modal", H_llm = 4096, mean-pooled assembly."""
+    b, t_frames, tq, tt, k = 1, 40, 8, 12, 8
+    enc = VideoTGBEncoder(NS(num_hidden_layers=2), None, NS(fusion_layer=6, encoder_width=768), llm_hidden=4096,
+                          instruct=True).to(DEV)
+    vsd = syn.vision_state_dict(syn.VisionCfg(layers=2))
+    isd = syn.qformer_state_dict(syn.QFormerCfg(instruct=True))
+    ssd, hsd = syn.sampler_state_dict(), syn.head_state_dict(llm_hidden=4096)
+    enc.model.vision_model.load_state_dict(vsd)
+    enc.model.qformer.load_state_dict(isd)
+    enc.temporal_encoder.load_state_dict(ssd)
+    enc.load_state_dict({"model." + kk: v for kk, v in hsd.items()}, strict=False)
+    g = torch.Generator().manual_seed(123)
+    u8 = torch.randint(0, 256, (b, t_frames, 224, 224, 3), generator=g, dtype=torch.uint8)
+    of = syn.synthetic_flow(b, t_frames, seed=17)
+    of_mask = torch.ones(b, t_frames + 2, dtype=torch.long)
+    qids = torch.randint(1000, 30522, (b, tq), generator=g)
+    tids = torch.randint(1000, 30522, (b, tt), generator=g)
+    tmask = torch.ones(b, tt, dtype=torch.long)
+    tmask[:, 9:] = 0
+    gum = [-torch.empty(2 * b, t_frames, 1).exponential_(generator=g).log() for _ in range(2)]
+    batch = dict(frames_u8=u8.to(DEV), of=of.to(DEV), of_mask=of_mask.to(DEV), of_lengths=[t_frames],
+                 sampler_question=qids.to(DEV), sampler_question_attention_mask=torch.ones(b, tq, dtype=torch.long, device=DEV),
+                 qformer_text=tids.to(DEV), qformer_text_attention_mask=tmask.to(DEV), nframe=k)
+    out, aux = enc.encode_u8(batch, mode="multi_modal", variant="ratio", assemble="mean", gumbel=[x.to(DEV) for x in gum],
+                             return_aux=True)
+    assert out.shape == (b, 32, 4096)
+    sl, el = aux.start_logits.cpu(), aux.end_logits.cpu()
+    cs, ce = zip(*[select_ref.gumbel_argmax(sl, el, gg) for gg in gum])
+    want_idx = select_ref.select_batch(list(cs), list(ce), [t_frames], t_frames, k, mapping="ratio")
+    assert torch.equal(aux.indices.cpu(), want_idx)
+    from oracle.transform_ref import normalize_u8_thwc
+    px = torch.from_numpy(normalize_u8_thwc(u8.view(-1, 224, 224, 3).numpy())).view(b, t_frames, 3, 224, 224)
+    with torch.no_grad():
+        sampled = select_ref.gather_frames(px, want_idx).to(DEV)
+        img, _ = torch_ref.vit_forward(to_dev(vsd), sampled, layers=2)
+        qt = hsd["query_tokens"].to(DEV).expand(b * k, -1, -1)
+        ids = torch.repeat_interleave(tids, k, 0).to(DEV)
+        am = torch.cat([torch.ones(b * k, 32, dtype=torch.long), torch.repeat_interleave(tmask, k, 0)], 1).to(DEV)
+        qo = torch_ref.qformer_forward(to_dev(isd), qt, img, None, input_ids=ids, attention_mask=am, instruct=True)[:, :32]
+        want = torch_ref.project_tokens(to_dev(hsd), qo, b, mode="mean")
+        _, rlogits = torch_ref.sampler_forward(to_dev(ssd), of.to(DEV), of_mask.to(DEV), qids.to(DEV),
+                                               torch.ones(b, tq, dtype=torch.long, device=DEV), mode="multi_modal")
+    assert_parity(out, want, "instructblip mean-pooled tokens")
+    assert_parity(torch.cat([aux.start_logits, aux.end_logits], -1), rlogits, "multi_modal scores")
+
+
+def test_ragged_widths_mean_assembly():
+    """LSTP_Vicuna_IV_module.py:233-242: per-video frame counts (`widths`) differ."""
+    enc = VideoTGBEncoder(NS(num_hidden_layers=1), None, NS(num_hidden_layers=1), llm_hidden=2048).to(DEV)
+    hsd = syn.head_state_dict()
+    enc.load_state_dict({"model." + kk: v for kk, v in hsd.items()}, strict=False)
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(9, 32, 768, generator=g)
+    widths = [2, 4, 3]
+    got = enc.assemble(q.to(DEV), 3, "mean", widths=widths)
+    want = torch_ref.project_tokens(hsd, q, 3, mode="mean", widths=widths)
+    assert_parity(got, want, "ragged mean pooling", rel=1e-2)
