@@ -279,3 +279,14 @@ def test_ragged_widths_mean_assembly():
     got = enc.assemble(q.to(DEV), 3, "mean", widths=widths)
     want = torch_ref.project_tokens(hsd, q, 3, mode="mean", widths=widths)
     assert_parity(got, want, "ragged mean pooling", rel=1e-2)
+
+
+def test_cuda_graph_replay_matches_eager(vit2):
+    """Small batches replay a captured CUDA graph of the ~270-launch ViT pass; results must equal the eager launches."""
+    sd, m, px, out = vit2                       # the fixture ran with graphs enabled (2 frames <= graph_max_rows)
+    assert ("vit", 2, 592) in m._graphs.entries
+    m.graph_max_rows = 0
+    eager = m(pixel_values=px).last_hidden_state
+    m.graph_max_rows = 64
+    again = m(pixel_values=px).last_hidden_state          # second replay of the same graph
+    assert torch.equal(eager, out.last_hidden_state) and torch.equal(again, eager)

@@ -12,10 +12,36 @@ __device__ __forceinline__ float norm_px(uint8_t u, float mean, float stdv) {
   return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u), 255.0f), mean), stdv);
 }
 
-// u8 [T,H,W,3] -> f32 [T,3,H,W].  One thread handles 4 consecutive pixels of one frame: reads 12 bytes (three
-// 4-byte words, coalesced across the warp) and writes one float4 per channel plane.
+// Division-free evaluation of norm_px: q = a*(1/255) and p = t*(1/std), each corrected by one FMA residual step.  For
+// divisors that are compile/run-time constants this reproduces the correctly rounded IEEE quotient for (almost) every
+// input; the HOST verifies all 3 x 256 possible inputs against real IEEE division before a kernel is allowed to use it
+// (norm_fast_is_exact), otherwise the shared-memory table of exact results is used.
+struct NormFast { float r255; float mean[3]; float stdv[3]; float rstd[3]; };
+__host__ __device__ __forceinline__ float norm_px_fast(float a, float r255, float mean, float stdv, float rstd) {
+#ifdef __CUDA_ARCH__
+  float q = __fmul_rn(a, r255);
+  q = __fmaf_rn(__fmaf_rn(-q, 255.0f, a), r255, q);
+  const float t = __fsub_rn(q, mean);
+  float p = __fmul_rn(t, rstd);
+  return __fmaf_rn(__fmaf_rn(-p, stdv, t), rstd, p);
+#else
+  volatile float q0 = a * r255;
+  volatile float q = fmaf(fmaf(-q0, 255.0f, a), r255, q0);
+  volatile float t = q - mean;
+  volatile float p0 = t * rstd;
+  return fmaf(fmaf(-p0, stdv, t), rstd, p0);
+#endif
+}
+
+// u8 [T,H,W,3] -> f32 [T,3,H,W].  The 3 x 256 possible results are computed once per CTA with the exact reference
+// arithmetic (IEEE division is ~10 instructions; doing it per pixel made the kernel ALU-bound at 55 % of HBM) and
+// looked up from shared memory, so the result stays bit-exact.  One thread handles 4 consecutive pixels: reads 12
+// bytes (three 4-byte words, coalesced across the warp) and writes one float4 per channel plane.
 __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
                                                            long long n_quads, int hw, Norm3 nm) {
+  __shared__ float lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i >> 8][i & 255] = norm_px((uint8_t)(i & 255), nm.mean[i >> 8], nm.stdv[i >> 8]);
+  __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += stride) {
     const long long pix = q * 4;                 // global pixel index (t*hw + p), hw % 4 == 0
@@ -33,55 +59,130 @@ __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __rest
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float4 o;
-      o.x = norm_px(b[0 + c], nm.mean[c], nm.stdv[c]);
-      o.y = norm_px(b[3 + c], nm.mean[c], nm.stdv[c]);
-      o.z = norm_px(b[6 + c], nm.mean[c], nm.stdv[c]);
-      o.w = norm_px(b[9 + c], nm.mean[c], nm.stdv[c]);
-      *reinterpret_cast<float4*>(dst + (t * 3 + c) * hw + p) = o;
+      o.x = lut[c][b[0 + c]];
+      o.y = lut[c][b[3 + c]];
+      o.z = lut[c][b[6 + c]];
+      o.w = lut[c][b[9 + c]];
+      __stcs(reinterpret_cast<float4*>(dst + (t * 3 + c) * hw + p), o);
     }
   }
 }
 
-// Patchify: one thread produces 8 consecutive bf16 of one im2col row (16-byte store).  Row = (frame, patch),
-// column = (c*P + ky)*P + kx.  P is even so an 8-group never needs more than two source segments... it may cross
-// a ky boundary, so elements are fetched individually through the read-only path (the source frame is re-read
-// from L1/L2; HBM sees each byte once).
-template <bool U8>
+// Patchify (im2col for the 14x14/14 patch-embed GEMM).  Persistent CTAs walk (frame, band of P image rows) items with a
+// two-deep cp.async pipeline: the band (u8: P*S*3 contiguous bytes; f32: 3 planes x P*S floats) is fetched with 16-byte
+// asynchronous copies while the previous band is re-laid out in shared memory as the S/P im2col rows it produces
+// (column = (c*P + ky)*P + kx, zero padded to ld; u8 goes through a 3x256 bf16 table of the exact reference
+// arithmetic) and streamed out with 16-byte coalesced stores (the rows of a band are contiguous in the output).
+__device__ __forceinline__ void cp_async16_g2s(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+
+template <bool U8, int PC, bool FAST>   // PC: compile-time patch size (unrolled loops) or 0; FAST: verified division-free normalise
 __global__ void __launch_bounds__(256) patchify_kernel(const void* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                       long long n_groups, int S, int P, int ld, Norm3 nm) {
+                                                       int n_items, int S, int P_rt, int ld, Norm3 nm, NormFast nf) {
+  extern __shared__ __align__(16) uint8_t psm[];
+  const int P = PC > 0 ? PC : P_rt;
   const int g = S / P;
+  const int band = P * S;                                   // pixels per channel in a band
+  const int raw_bytes = U8 ? ((band * 3 + 15) & ~15) : 3 * band * 4;
+  __nv_bfloat16* lut = reinterpret_cast<__nv_bfloat16*>(psm);                 // [3][256] (u8 only)
+  uint8_t* raw0 = psm + 1536;
+  __nv_bfloat16* outs = reinterpret_cast<__nv_bfloat16*>(psm + 1536 + 2 * raw_bytes);
+  if (U8 && !FAST)
+    for (int i = threadIdx.x; i < 768; i += blockDim.x)
+      lut[i] = __float2bfloat16(norm_px((uint8_t)(i & 255), nm.mean[i >> 8], nm.stdv[i >> 8]));
+  const uint16_t* lut16 = reinterpret_cast<const uint16_t*>(lut);
   const int kdim = 3 * P * P;
-  const int groups_per_row = ld / 8;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += stride) {
-    const long long row = i / groups_per_row;
-    const int col0 = static_cast<int>(i - row * groups_per_row) * 8;
-    const long long f = row / (g * g);
-    const int pidx = static_cast<int>(row - f * (g * g));
-    const int py = pidx / g, px = pidx - py * g;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = col0 + j;
-      float x = 0.0f;
-      if (col < kdim) {
-        const int c = col / (P * P);
-        const int r = col - c * P * P;
-        const int ky = r / P, kx = r - ky * P;
-        const int y = py * P + ky, xx = px * P + kx;
+
+  auto fetch = [&](int item, int buf) {
+    const int f = item / g, py = item - f * g;
+    uint8_t* rb = raw0 + buf * raw_bytes;
+    if (U8) {
+      const uint8_t* sp = reinterpret_cast<const uint8_t*>(src) + ((long long)f * S + (long long)py * P) * S * 3;
+      for (int i = threadIdx.x; i < band * 3 / 16; i += blockDim.x) cp_async16_g2s(rb + i * 16, sp + i * 16);
+    } else {
+      for (int c = 0; c < 3; ++c) {
+        const uint8_t* sp = reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(src) +
+                                                             (((long long)f * 3 + c) * S + (long long)py * P) * S);
+        for (int i = threadIdx.x; i < band / 4; i += blockDim.x) cp_async16_g2s(rb + c * band * 4 + i * 16, sp + i * 16);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int item = blockIdx.x;
+  if (item < n_items) fetch(item, 0);
+  int it = 0;
+  for (; item < n_items; item += gridDim.x, ++it) {
+    const int nxt = item + gridDim.x;
+    if (nxt < n_items) {
+      fetch(nxt, (it + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint8_t* raw = raw0 + (it & 1) * raw_bytes;
+    const float* rawf = reinterpret_cast<const float*>(raw);
+    // re-layout: one task = the P contiguous kx of one (channel, ky, patch)
+    const int ntask = 3 * P * g;
+    for (int t = threadIdx.x; t < ntask; t += blockDim.x) {
+      const int c = t / (P * g);
+      const int r = t - c * (P * g);
+      const int ky = r / g, px = r - ky * g;
+      const int pix0 = ky * S + px * P;
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(outs + px * ld + (c * P + ky) * P);
+      if (PC > 0) {
+        uint32_t w[PC > 0 ? PC / 2 : 1];
         if (U8) {
-          const uint8_t u = __ldg(reinterpret_cast<const uint8_t*>(src) + ((f * S + y) * S + xx) * 3 + c);
-          x = norm_px(u, nm.mean[c], nm.stdv[c]);
+          uint8_t bytes[PC > 0 ? PC : 1];
+#pragma unroll
+          for (int kx = 0; kx < PC; ++kx) bytes[kx] = raw[(pix0 + kx) * 3 + c];
+          if (FAST) {
+            const float mean = nf.mean[c], stdv = nf.stdv[c], rstd = nf.rstd[c];
+#pragma unroll
+            for (int kx = 0; kx < PC; kx += 2)
+              // byte -> float through the 2^23 mantissa trick (ALU/FMA pipes; I2F would go to the quarter-rate XU pipe)
+              w[kx >> 1] = pack_bf16(
+                  norm_px_fast(__uint_as_float(0x4B000000u | bytes[kx]) - 8388608.0f, nf.r255, mean, stdv, rstd),
+                  norm_px_fast(__uint_as_float(0x4B000000u | bytes[kx + 1]) - 8388608.0f, nf.r255, mean, stdv, rstd));
+          } else {
+#pragma unroll
+            for (int kx = 0; kx < PC; kx += 2)
+              w[kx >> 1] = (uint32_t)lut16[c * 256 + bytes[kx]] | ((uint32_t)lut16[c * 256 + bytes[kx + 1]] << 16);
+          }
         } else {
-          x = __ldg(reinterpret_cast<const float*>(src) + ((f * 3 + c) * S + y) * (long long)S + xx);
+#pragma unroll
+          for (int kx = 0; kx < PC; kx += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(rawf + c * band + pix0 + kx);
+            w[kx >> 1] = pack_bf16(v.x, v.y);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < PC / 2; ++q) d32[q] = w[q];
+      } else {
+        for (int kx = 0; kx < P; kx += 2) {
+          if (U8) {
+            const uint32_t lo = lut16[c * 256 + raw[(pix0 + kx) * 3 + c]];
+            const uint32_t hi = lut16[c * 256 + raw[(pix0 + kx + 1) * 3 + c]];
+            d32[kx >> 1] = lo | (hi << 16);
+          } else {
+            const float2 v = *reinterpret_cast<const float2*>(rawf + c * band + pix0 + kx);
+            d32[kx >> 1] = pack_bf16(v.x, v.y);
+          }
         }
       }
-      v[j] = x;
     }
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-    o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(dst + row * ld + col0) = o;
+    for (int i = threadIdx.x; i < g * (ld - kdim); i += blockDim.x) {
+      const int px = i / (ld - kdim);
+      outs[px * ld + kdim + (i - px * (ld - kdim))] = __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    const int f = item / g, py = item - f * g;
+    uint4* out4 = reinterpret_cast<uint4*>(dst + ((long long)f * g + py) * g * ld);
+    const uint4* in4 = reinterpret_cast<const uint4*>(outs);
+    for (int i = threadIdx.x; i < g * ld / 8; i += blockDim.x) __stcs(out4 + i, in4[i]);
+    __syncthreads();
   }
 }
 
@@ -153,11 +254,48 @@ static int patchify_common(const void* src, void* out, int F, int S, int P, int 
   TGB_CHECK_ARG(F >= 0 && S > 0 && P > 0 && S % P == 0, "patchify: image %d not divisible by patch %d", S, P);
   TGB_CHECK_ARG(ld % 8 == 0 && ld >= 3 * P * P && ((uintptr_t)out % 16) == 0, "patchify: ld must be a multiple of 8 >= 3*P*P");
   if (F == 0) return TGB_OK;
-  const long long groups = (long long)F * (S / P) * (S / P) * (ld / 8);
-  if (u8)
-    patchify_kernel<true><<<grid_for(groups, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)out, groups, S, P, ld, nm);
-  else
-    patchify_kernel<false><<<grid_for(groups, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)out, groups, S, P, ld, nm);
+  TGB_CHECK_ARG(((uintptr_t)src % 16) == 0 && (u8 ? ((long long)P * S * 3) % 16 == 0 : ((long long)P * S) % 4 == 0),
+                "patchify: source band must be 16-byte aligned (P*S*3 %% 16 == 0 for u8 frames)");
+  TGB_CHECK_ARG(P % 2 == 0 && (!u8 || ((long long)P * S * 3) % 16 == 0), "patchify: patch size must be even (and P*S*3 %% 16 == 0 for u8)");
+  const size_t raw_bytes = u8 ? (((size_t)P * S * 3 + 15) & ~(size_t)15) : (size_t)3 * P * S * 4;
+  const size_t smem = 1536 + 2 * raw_bytes + (size_t)(S / P) * ld * 2;
+  TGB_CHECK_ARG(smem <= 200 * 1024, "patchify: band of %d x %d pixels does not fit in shared memory", P, S);
+  const int items = F * (S / P);
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 56 * 1024 ? 2 : 4);
+  const int grid = items < sm_count() * per_sm ? items : sm_count() * per_sm;
+  cudaStream_t st_ = (cudaStream_t)stream;
+#define TGB_PATCHIFY(U, PCV, FST)                                                                                      \
+  do {                                                                                                                \
+    static bool cfg = false;                                                                                          \
+    if (!cfg) {                                                                                                       \
+      TGB_CUDA(cudaFuncSetAttribute(patchify_kernel<U, PCV, FST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      cfg = true;                                                                                                     \
+    }                                                                                                                 \
+    patchify_kernel<U, PCV, FST><<<grid, 256, smem, st_>>>(src, (__nv_bfloat16*)out, items, S, P, ld, nm, nf);        \
+  } while (0)
+  NormFast nf = {};
+  bool fast = false;
+  if (u8) {                       // exhaustive host check of the division-free path against IEEE division
+    nf.r255 = 1.0f / 255.0f;
+    fast = true;
+    for (int c = 0; c < 3; ++c) {
+      nf.mean[c] = nm.mean[c]; nf.stdv[c] = nm.stdv[c]; nf.rstd[c] = 1.0f / nm.stdv[c];
+      for (int v = 0; v < 256 && fast; ++v) {
+        volatile float x = (float)v / 255.0f;
+        volatile float y = x - nm.mean[c];
+        volatile float z = y / nm.stdv[c];
+        if (norm_px_fast((float)v, nf.r255, nf.mean[c], nf.stdv[c], nf.rstd[c]) != z) fast = false;
+      }
+    }
+  }
+  if (u8) {
+    if (P == 14 && fast) TGB_PATCHIFY(true, 14, true);
+    else if (P == 14) TGB_PATCHIFY(true, 14, false);
+    else TGB_PATCHIFY(true, 0, false);
+  } else {
+    if (P == 14) TGB_PATCHIFY(false, 14, false); else TGB_PATCHIFY(false, 0, false);
+  }
+#undef TGB_PATCHIFY
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

@@ -70,14 +70,21 @@ class _KernelModule(nn.Module):
     def __init__(self):
         super().__init__()
         self._packed = None
+        self._graphs = _GraphCache()
+        self.graph_max_rows = 64           # batches up to this many frames replay a captured CUDA graph; 0 disables
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     def _invalidate(self):
         self._packed = None
+        self._graphs.clear()
 
     def _apply(self, fn, *a, **k):
         self._packed = None
+        self._graphs.clear()
         return super()._apply(fn, *a, **k)
+
+    def _use_graph(self, rows: int) -> bool:
+        return 0 < rows <= self.graph_max_rows and not torch.cuda.is_current_stream_capturing() and ops._PROFILE is None
 
     def train(self, mode: bool = True):
         if mode:
@@ -96,6 +103,36 @@ class _KernelModule(nn.Module):
     def _device_check(self, t: torch.Tensor):
         if not t.is_cuda:
             raise TgbError("videotgb_b200 modules run on a B200 only (inputs must be CUDA tensors); no CPU fallback")
+
+
+class _GraphCache:
+    """CUDA-graph replay of a fixed-shape kernel sequence (launch-bound small batches: ~270 launches per ViT pass).
+    `build(key, make_inputs, body)` captures `body(*static_inputs) -> tuple(static_outputs)` once per key."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def clear(self):
+        self.entries.clear()
+
+    def run(self, key, inputs, body):
+        ent = self.entries.get(key)
+        if ent is None:
+            static_in = [t.clone() for t in inputs]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up outside capture (lazy inits, allocator)
+                body(*static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = body(*static_in)
+            ent = self.entries[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = ent
+        for dst, src in zip(static_in, inputs):
+            dst.copy_(src)
+        graph.replay()
+        return tuple(t.clone() for t in static_out)
 
 
 def _model_output(cls_name: str, **kw):
@@ -203,6 +240,14 @@ class Blip2VisionModel(_KernelModule):
         """im2col'ed frames (bf16 [nf*256, kpad]) -> (last_hidden_state f32 [nf,257,D], bf16 copy)."""
         pk = self._pack()
         d, s = self.hidden, self.tokens
+        if self._use_graph(nf):
+            def body(c):
+                lf = torch.empty((nf * s, d), dtype=torch.float32, device=c.device)
+                lb = torch.empty((nf * s, d), dtype=torch.bfloat16, device=c.device)
+                self._encode(pk, c, nf, lf, lb)
+                return lf, lb
+            last, last_bf16 = self._graphs.run(("vit", nf, cols.shape[1]), [cols], body)
+            return last.view(nf, s, d), last_bf16.view(nf, s, d)
         last = torch.empty((nf * s, d), dtype=torch.float32, device=cols.device)
         last_bf16 = torch.empty((nf * s, d), dtype=torch.bfloat16, device=cols.device)
         step = self.max_frames_per_pass
@@ -428,7 +473,12 @@ class Blip2QFormerModel(_QFormerBase):
         self_mask = self._additive(attention_mask, -10000.0)
         # image masks are all-ones on this path (LSTP_SF_blip2_module.py:469); the additive form is exact either way
         cross_mask = self._additive(encoder_attention_mask, torch.finfo(torch.float32).min)
-        x = self._run_layers(pk.layers, x_f32, x_bf16, nf, nq, nq, img, s_img, self_mask, cross_mask)
+        if self_mask is None and cross_mask is None and img is not None and self._use_graph(nf):
+            def body(xf, xb, im):
+                return (self._run_layers(pk.layers, xf, xb, nf, nq, nq, im, s_img, None, None),)
+            (x,) = self._graphs.run(("qformer", nf, nq, s_img), [x_f32, x_bf16, img], body)
+        else:
+            x = self._run_layers(pk.layers, x_f32, x_bf16, nf, nq, nq, img, s_img, self_mask, cross_mask)
         return self._finish(x, nf, nq, return_dict)
 
 
