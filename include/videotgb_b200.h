@@ -70,6 +70,19 @@ TGB_API int tgb_spans_to_indices(const int64_t* cand_start, const int64_t* cand_
                          int B, int num_frames, int nframe, int mapping, int inclusive, int host_ints,
                          int64_t* indices, tgb_stream_t stream);
 
+/* ---------------------------------------------------------------- N2  self-refinement pseudo labels --
+ * src/models/LSTP_SF_blip2_module.py:195-222: per-frame answer scores f32 [B, num_frames] -> largest-rectangle
+ * monotone stack over the min-shifted zero-padded scores -> (start, end) frame span -> rescale to flow positions
+ * int(t / (num_frames-1) * (of_lengths[b]-1)) in float64 (the reference computes on Python floats).
+ * start_targets / end_targets: i64 [B].  Bit-exact.  2 <= num_frames <= 3000.                              */
+TGB_API int tgb_pseudo_span(const float* scores, const int32_t* of_lengths, int B, int num_frames,
+                            int64_t* start_targets, int64_t* end_targets, tgb_stream_t stream);
+/* src/models/LSTP_SF_blip2_module.py:238-253 ("mrc_loss"): logits f32 [B, L, 2] as the mrc head emits them;
+ * CrossEntropyLoss(ignore_index=L) on start and end rows with targets clamped to [0, L]; loss f32 [1] =
+ * (CE_start + CE_end) / 2.  fp32.                                                                          */
+TGB_API int tgb_span_ce_loss(const float* logits, const int64_t* start_targets, const int64_t* end_targets, int B, int L,
+                             float* loss, tgb_stream_t stream);
+
 /* ---------------------------------------------------------------- A9  frame gather --------------------
  * src/models/LSTP_SF_blip2_module.py:417-419,460-464: sampled[j] = index_select(pixel_values[j], 0, idx_j).
  * src: [B, N, frame_bytes], indices: i64 [B, k] -> dst: [B*k, frame_bytes].  Pure byte copy (bit-exact);

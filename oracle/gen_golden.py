@@ -6,6 +6,8 @@ What it pins:
   select_kat.json      -- A8: the reference's inline selection statements are read from
                           /root/reference/src/models/LSTP_SF_blip2_module.py (eval :431-459, train :282-312),
                           LSTP_module.py (ratio mapping) and executed unmodified on real 0-dim int64 tensors.
+  pseudo_span_kat.json -- N2: the monotone-stack pseudo-label statements (:193-224), the span cross-entropy
+                          statements (:241-253) and rouge_n (my_metrics.py:131-179), executed from the reference source.
   gumbel.npz           -- A7: F.gumbel_softmax(...).argmax with a fixed torch seed, plus the explicit noise.
   transform.npz        -- A0: reference ToTensorVideo/NormalizeVideo on random u8 frames.
   vit_small.npz ...    -- A10-A16, A1-A6: the reference classes (through reference_shim) loaded with the
@@ -102,6 +104,63 @@ def gen_select():
     with open(os.path.join(GOLD, "select_kat.json"), "w") as f:
         json.dump(cases, f)
     print("select cases:", len(cases))
+
+
+def gen_pseudo_span():
+    """N2: execute the reference's monotone-stack pseudo-label statements (LSTP_SF_blip2_module.py:193-224) verbatim."""
+    src = _ref_lines("src/models/LSTP_SF_blip2_module.py", 193, 224)
+    assert "monotone stack" in src and "flow_lengths" in src
+    rng = np.random.default_rng(77)
+    cases = []
+    for t in range(60):
+        b = int(rng.integers(1, 6))
+        n = int(rng.choice([4, 8, 32, 64]))
+        kind = t % 4
+        if kind == 0:
+            sc = rng.random((b, n)).astype(np.float32)
+        elif kind == 1:
+            sc = np.round(rng.random((b, n)) * 4).astype(np.float32) / 4          # many ties
+        elif kind == 2:
+            sc = np.zeros((b, n), np.float32); sc[:, rng.integers(0, n)] = 1.0      # single peak
+        else:
+            sc = np.sort(rng.random((b, n)).astype(np.float32), axis=1)           # monotone
+        lengths = [int(x) for x in rng.integers(2, 65, size=b)]
+        env = dict(torch=torch, scores=torch.tensor(sc).view(-1), batch_size=b, num_frames=n,
+                   batch={"of_lengths": lengths}, pixel_values=torch.zeros(1))
+        exec(src, env)
+        cases.append(dict(scores=sc.tolist(), of_lengths=lengths, start=[int(v) for v in env["start_targets"]],
+                          end=[int(v) for v in env["end_targets"]]))
+    # span cross-entropy: the reference statements :241-253 executed on random logits (incl. ignored / clamped targets)
+    ce_src = _ref_lines("src/models/LSTP_SF_blip2_module.py", 241, 253)
+    assert "ignore_index=ignored_index" in ce_src and "mrc_loss" in ce_src
+    ce = []
+    for t in range(12):
+        b, l = int(rng.integers(1, 9)), int(rng.choice([4, 32, 64, 100]))
+        logits = torch.tensor(rng.normal(size=(b, l, 2)).astype(np.float32) * 3)
+        st = torch.tensor(rng.integers(-2, l + 3, size=b))
+        en = torch.tensor(rng.integers(0, l, size=b))
+        if t == 0:
+            st = torch.full((b,), l)                       # every start row ignored -> NaN
+        env = dict(torch=torch, CrossEntropyLoss=torch.nn.CrossEntropyLoss, of_logits=logits, start_targets=st.clone(),
+                   end_targets=en.clone())
+        exec(ce_src, env)
+        ce.append(dict(logits=logits.tolist(), start=st.tolist(), end=en.tolist(), loss=float(env["mrc_loss"])))
+    # rouge_n (src/gadgets/my_metrics.py:131-179), executed from the reference source (torchmetrics is not installed)
+    env = {}
+    exec(_ref_lines("src/gadgets/my_metrics.py", 131, 179), env)
+    words = "a the cat sat on mat , . dog runs fast in park it is".split()
+    rouge = []
+    for t in range(40):
+        n = int(rng.integers(1, 5))
+        gold = [" ".join(rng.choice(words, size=int(rng.integers(1, 8)))) for _ in range(n)]
+        pred = [" ".join(rng.choice(words, size=int(rng.integers(0, 8)))) for _ in range(n)]
+        ignore = None if t % 7 == 6 else [",", "."]
+        if t % 5 == 4:
+            gold, pred = gold[0], pred[0]
+        rouge.append(dict(gold=gold, pred=pred, ignore=ignore, score=env["rouge_n"](gold, pred, ignore)))
+    with open(os.path.join(GOLD, "pseudo_span_kat.json"), "w") as f:
+        json.dump(dict(span=cases, ce=ce, rouge=rouge), f)
+    print("pseudo-span cases:", len(cases), "ce:", len(ce), "rouge:", len(rouge))
 
 
 def gen_gumbel():
@@ -230,7 +289,7 @@ def gen_models():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     reference_shim.install()
-    which = sys.argv[1:] or ["select", "gumbel", "transform", "models"]
+    which = sys.argv[1:] or ["select", "pseudo_span", "gumbel", "transform", "models"]
     for w in which:
         globals()["gen_" + w]()
         print("generated", w)

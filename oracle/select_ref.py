@@ -103,3 +103,43 @@ def gather_frames(pixel_values: torch.Tensor, indices: torch.Tensor) -> torch.Te
     for j in range(b):
         out[j] = torch.index_select(pixel_values[j], 0, indices[j])
     return out.view((b * k,) + tuple(pixel_values.shape[2:]))
+
+
+# --------------------------------------------------------------------------------------------
+# self-refinement pseudo-labels (training forward)
+#   src/models/LSTP_SF_blip2_module.py:195-227  per-frame scores -> monotone-stack span -> flow-index targets
+#   src/models/LSTP_SF_blip2_module.py:241-253  span cross-entropy ("mrc") loss with ignore_index = Lof
+# --------------------------------------------------------------------------------------------
+def pseudo_span(scores, flow_length: int):
+    """One video: per-frame scores (list of floats, as `tensor.tolist()` yields them) -> (start_target, end_target).
+
+    Restates :197-217 (largest-rectangle monotone stack on the min-shifted, zero-padded scores) and the rescale of
+    :221-222 (`int(t / (num_frames-1) * (flow_length-1))`, Python float64)."""
+    num_frames = len(scores)
+    bs = 0
+    start_target, end_target = 0, num_frames - 1
+    stack = []
+    lo = min(scores)
+    score = [0] + [s - lo for s in scores] + [0]
+    for i in range(len(score)):
+        while stack and score[stack[-1]] > score[i]:
+            tmp = stack.pop()
+            tmp_bs = (i - stack[-1] - 1) * score[tmp]
+            if tmp_bs > bs:
+                bs = tmp_bs
+                start_target, end_target = stack[-1], i - 2
+        stack.append(i)
+    return (int(start_target / (num_frames - 1) * (flow_length - 1)),
+            int(end_target / (num_frames - 1) * (flow_length - 1)))
+
+
+def span_ce_loss(start_logits: torch.Tensor, end_logits: torch.Tensor, start_targets: torch.Tensor,
+                 end_targets: torch.Tensor) -> torch.Tensor:
+    """`mrc_loss` of :241-253: CrossEntropyLoss(ignore_index=Lof) on the squeezed start / end logits, averaged."""
+    ignored_index = start_logits.size(1)
+    loss_fct = torch.nn.CrossEntropyLoss(ignore_index=ignored_index)
+    st = start_targets.clamp(0, ignored_index)
+    et = end_targets.clamp(0, ignored_index)
+    start_loss = loss_fct(start_logits.squeeze(-1).contiguous(), st)
+    end_loss = loss_fct(end_logits.squeeze(-1).contiguous(), et)
+    return (start_loss + end_loss) / 2

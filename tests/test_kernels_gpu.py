@@ -118,6 +118,35 @@ def test_spans_to_indices_random_vs_oracle():
         assert torch.equal(got, want), (t, b, lof, n, k, mapping, inclusive, host_ints)
 
 
+# ------------------------------------------------------------------------------------------------ N2
+def test_pseudo_span_and_span_ce_reference_kat():
+    with open(os.path.join(GOLDEN, "pseudo_span_kat.json")) as f:
+        kat = json.load(f)
+    for c in kat["span"]:
+        sc = torch.tensor(c["scores"], dtype=torch.float32, device=DEV)
+        st, en = ops.pseudo_span(sc, torch.tensor(c["of_lengths"], dtype=torch.int32, device=DEV))
+        assert st.tolist() == c["start"] and en.tolist() == c["end"], c["of_lengths"]
+    for c in kat["ce"]:
+        got = float(ops.span_ce_loss(torch.tensor(c["logits"], dtype=torch.float32, device=DEV),
+                                     torch.tensor(c["start"], device=DEV), torch.tensor(c["end"], device=DEV)))
+        assert (np.isnan(got) and np.isnan(c["loss"])) or abs(got - c["loss"]) <= 2e-6 * max(1.0, abs(c["loss"])), c["loss"]
+
+
+def test_pseudo_span_random_vs_oracle():
+    rng = np.random.default_rng(11)
+    for t in range(30):
+        b, n = int(rng.integers(1, 65)), int(rng.choice([2, 3, 32, 257, 1024, 3000]))
+        sc = rng.random((b, n)).astype(np.float32)
+        if t % 3 == 0:
+            sc = np.round(sc * 3) / 3                       # heavy ties
+        if t % 7 == 0:
+            sc[:] = 0.25                                    # flat -> nothing beats area 0 -> (0, n-1)
+        lengths = rng.integers(2, 2000, size=b).astype(np.int32)
+        st, en = ops.pseudo_span(torch.from_numpy(sc).to(DEV), torch.from_numpy(lengths).to(DEV))
+        want = [select_ref.pseudo_span(torch.from_numpy(sc[j]).tolist(), int(lengths[j])) for j in range(b)]
+        assert list(zip(st.tolist(), en.tolist())) == want, (t, b, n)
+
+
 # ------------------------------------------------------------------------------------------------ A9
 def test_gather_bit_exact():
     g = torch.Generator().manual_seed(2)

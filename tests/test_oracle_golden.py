@@ -59,6 +59,32 @@ def test_survey_kat_table():
     assert select_ref.uniform_indices(32, 8) == [1, 5, 9, 13, 17, 21, 25, 29]
 
 
+def _pseudo_kat():
+    with open(os.path.join(GOLDEN, "pseudo_span_kat.json")) as f:
+        return json.load(f)
+
+
+def test_pseudo_span_and_span_ce_vs_executed_reference():
+    kat = _pseudo_kat()
+    assert len(kat["span"]) >= 50
+    for c in kat["span"]:
+        for j, length in enumerate(c["of_lengths"]):
+            # the reference works on `tensor.tolist()` of a float32 tensor
+            row = torch.tensor(c["scores"][j], dtype=torch.float32).tolist()
+            assert select_ref.pseudo_span(row, length) == (c["start"][j], c["end"][j])
+    for c in kat["ce"]:
+        lg = torch.tensor(c["logits"], dtype=torch.float32)
+        s, e = lg.split(1, dim=-1)
+        got = float(select_ref.span_ce_loss(s, e, torch.tensor(c["start"]), torch.tensor(c["end"])))
+        assert (np.isnan(got) and np.isnan(c["loss"])) or abs(got - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"]))
+
+
+def test_rouge_n_host_mirror_vs_executed_reference():
+    from videotgb_b200.selection import rouge_n
+    for c in _pseudo_kat()["rouge"]:
+        assert rouge_n(c["gold"], c["pred"], c["ignore"]) == c["score"], c
+
+
 def test_gumbel_argmax_matches_reference_draw():
     z = np.load(os.path.join(GOLDEN, "gumbel.npz"))
     for tag in "abc":

@@ -165,6 +165,89 @@ __global__ void __launch_bounds__(32) spans_to_indices_kernel(const long long* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// N2: self-refinement pseudo labels, src/models/LSTP_SF_blip2_module.py:195-222.
+// Largest-rectangle monotone stack over the min-shifted, zero-padded per-frame scores, then the rescale to flow
+// positions.  The reference works on `tensor.tolist()` values, i.e. Python float64: every float op below is an
+// explicit double _rn op on the exactly-converted float32 inputs.  One warp per video; the warp finds the minimum,
+// lane 0 runs the (inherently sequential) stack.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) pseudo_span_kernel(const float* __restrict__ scores,
+                                                         const int* __restrict__ of_lengths, int N,
+                                                         long long* __restrict__ start_targets,
+                                                         long long* __restrict__ end_targets) {
+  extern __shared__ double ps_sm[];                  // [N + 2] shifted scores, then [N + 2] int stack
+  double* sc = ps_sm;
+  int* stack = reinterpret_cast<int*>(ps_sm + (N + 2));
+  const int j = blockIdx.x, lane = threadIdx.x;
+  const float* row = scores + (long long)j * N;
+  float lo = INFINITY;
+  for (int i = lane; i < N; i += 32) lo = fminf(lo, row[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+  for (int i = lane; i < N; i += 32) sc[i + 1] = __dsub_rn((double)row[i], (double)lo);
+  if (lane == 0) { sc[0] = 0.0; sc[N + 1] = 0.0; }
+  __syncwarp();
+  if (lane != 0) return;
+  double best = 0.0;
+  int st = 0, en = N - 1, top = 0;
+  for (int i = 0; i < N + 2; ++i) {
+    const double cur = sc[i];
+    while (top > 0 && sc[stack[top - 1]] > cur) {
+      const int tmp = stack[--top];
+      // (a non-negative padded sequence never empties the stack here: sc[0] == 0 is never popped)
+      const double area = __dmul_rn((double)(i - stack[top - 1] - 1), sc[tmp]);
+      if (area > best) { best = area; st = stack[top - 1]; en = i - 2; }
+    }
+    stack[top++] = i;
+  }
+  const double den = (double)(N - 1), mul = (double)(of_lengths[j] - 1);
+  start_targets[j] = (long long)__dmul_rn(__ddiv_rn((double)st, den), mul);
+  end_targets[j] = (long long)__dmul_rn(__ddiv_rn((double)en, den), mul);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// N2: span cross-entropy, LSTP_SF_blip2_module.py:238-253.  logits f32 [B, L, 2] (start | end interleaved, as the
+// mrc head emits them); CrossEntropyLoss(ignore_index = L), targets clamped to [0, L]; loss = (CE_start + CE_end)/2
+// with each CE the mean over its non-ignored rows (0/0 = NaN like torch).  One CTA (B warps round-robin).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CE_THREADS = 256;
+
+__global__ void __launch_bounds__(CE_THREADS) span_ce_loss_kernel(const float* __restrict__ logits,
+                                                                 const long long* __restrict__ start_targets,
+                                                                 const long long* __restrict__ end_targets, int B,
+                                                                 int L, float* __restrict__ loss) {
+  __shared__ float part[2][CE_THREADS / 32];
+  __shared__ int cnt[2][CE_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[2] = {0.f, 0.f};
+  int n[2] = {0, 0};
+  for (int r = warp; r < 2 * B; r += CE_THREADS / 32) {      // row r: video r>>1, head r&1
+    const int b = r >> 1, h = r & 1;
+    long long t = (h ? end_targets : start_targets)[b];
+    t = t < 0 ? 0 : (t > L ? L : t);
+    if (t == L) continue;                                      // ignore_index (warp-uniform)
+    const float* x = logits + (long long)b * L * 2 + h;
+    float m = -INFINITY;
+    for (int i = lane; i < L; i += 32) m = fmaxf(m, x[2 * i]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < L; i += 32) s += expf(x[2 * i] - m);
+    s = warp_sum(s);
+    acc[h] += (m + logf(s)) - x[2 * t];                        // -log_softmax(x)[t]
+    n[h] += 1;
+  }
+  if (lane == 0) { part[0][warp] = acc[0]; part[1][warp] = acc[1]; cnt[0][warp] = n[0]; cnt[1][warp] = n[1]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot[2] = {0.f, 0.f};
+    int c[2] = {0, 0};
+    for (int w = 0; w < CE_THREADS / 32; ++w) { tot[0] += part[0][w]; tot[1] += part[1][w]; c[0] += cnt[0][w]; c[1] += cnt[1][w]; }
+    loss[0] = (tot[0] / (float)c[0] + tot[1] / (float)c[1]) * 0.5f;
+  }
+}
+
 }  // namespace tgb
 
 using namespace tgb;
@@ -202,6 +285,32 @@ extern "C" int tgb_spans_to_indices(const int64_t* cand_start, const int64_t* ca
   spans_to_indices_kernel<<<B, 32, 0, (cudaStream_t)stream>>>((const long long*)cand_start, (const long long*)cand_end, top_k,
                                                               of_lengths, B, num_frames, nframe, mapping, inclusive, host_ints,
                                                               (long long*)indices);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
+extern "C" int tgb_pseudo_span(const float* scores, const int32_t* of_lengths, int B, int num_frames,
+                               int64_t* start_targets, int64_t* end_targets, tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(scores && of_lengths && start_targets && end_targets, "pseudo_span: null pointer");
+  TGB_CHECK_ARG(B >= 0 && num_frames >= 2 && num_frames <= 3000, "pseudo_span: bad shape B=%d num_frames=%d (2..3000)", B, num_frames);
+  if (B == 0) return TGB_OK;
+  const size_t smem = (size_t)(num_frames + 2) * (sizeof(double) + sizeof(int));
+  pseudo_span_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(scores, of_lengths, num_frames, (long long*)start_targets,
+                                                           (long long*)end_targets);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
+extern "C" int tgb_span_ce_loss(const float* logits, const int64_t* start_targets, const int64_t* end_targets, int B, int L,
+                                float* loss, tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(logits && start_targets && end_targets && loss, "span_ce_loss: null pointer");
+  TGB_CHECK_ARG(B > 0 && L > 0, "span_ce_loss: bad shape B=%d L=%d", B, L);
+  span_ce_loss_kernel<<<1, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, (const long long*)start_targets,
+                                                                  (const long long*)end_targets, B, L, loss);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

@@ -110,6 +110,30 @@ def spans_to_indices(cand_start: torch.Tensor, cand_end: torch.Tensor, of_length
     return out
 
 
+def pseudo_span(scores: torch.Tensor, of_lengths: torch.Tensor):
+    """f32 [B, num_frames] per-frame scores, i32 [B] flow lengths -> (start_targets, end_targets) i64 [B]."""
+    sc = _need(scores, torch.float32, "scores")
+    ol = _need(of_lengths, torch.int32, "of_lengths")
+    if sc.dim() != 2 or ol.shape != (sc.shape[0],):
+        raise _lib.TgbError("scores must be [B, num_frames] and of_lengths [B]")
+    st = torch.empty((sc.shape[0],), dtype=torch.int64, device=sc.device)
+    en = torch.empty_like(st)
+    check(_lib.load().tgb_pseudo_span(_p(sc), _p(ol), sc.shape[0], sc.shape[1], _p(st), _p(en), _stream()))
+    return st, en
+
+
+def span_ce_loss(logits: torch.Tensor, start_targets: torch.Tensor, end_targets: torch.Tensor) -> torch.Tensor:
+    """mrc logits f32 [B, L, 2], i64 [B] targets -> 0-dim f32 loss."""
+    lg = _need(logits, torch.float32, "logits")
+    st = _need(start_targets, torch.int64, "start_targets")
+    en = _need(end_targets, torch.int64, "end_targets")
+    if lg.dim() != 3 or lg.shape[2] != 2 or st.shape != (lg.shape[0],) or en.shape != st.shape:
+        raise _lib.TgbError("logits must be [B, L, 2] and the targets [B]")
+    out = torch.empty((1,), dtype=torch.float32, device=lg.device)
+    check(_lib.load().tgb_span_ce_loss(_p(lg), _p(st), _p(en), lg.shape[0], lg.shape[1], _p(out), _stream()))
+    return out[0]
+
+
 def gather_frames(pixel_values: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
     """[B,N,...] , i64 [B,k] -> [B*k, ...] (same dtype as the source; the reference buffer is fp32)."""
     if not pixel_values.is_cuda or not pixel_values.is_contiguous():

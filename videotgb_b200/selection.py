@@ -72,3 +72,38 @@ def select_and_gather(start_logits, end_logits, of_lengths, pixel_values: torch.
     cs, ce = draw_spans(start_logits, end_logits, top_k, tau, gumbel, generator)
     idx = select_indices(cs, ce, of_lengths, pixel_values.shape[1], nframe, variant)
     return ops.gather_frames(pixel_values.contiguous(), idx), idx
+
+
+# ------------------------------------------------------------------------------------------------ N2
+def rouge_n(gold, pred, ignore=(",", ".")):
+    """Host-side token-recall score of the self-refinement pass (src/gadgets/my_metrics.py:131-179), same return
+    conventions: list inputs give one score per pair divided by len(gold) -- the reference's normalisation, kept
+    as is -- and a list call with ignore=None returns after the first pair."""
+    def recall(g, p):
+        g, p = g.split(), p.split()
+        if ignore is None:
+            return sum(tok in p for tok in g) / len(g)
+        kept = [tok for tok in g if tok not in ignore]
+        return sum(tok in p for tok in kept) / len(kept) if kept else 0
+    if type(gold) is list:
+        out = []
+        for g, p in zip(gold, pred):
+            if ignore is None:
+                return recall(g, p)
+            r = recall(g, p)
+            out.append(r / len(gold) if len(gold) > 0 else r)
+        return out
+    return recall(gold, pred)
+
+
+def pseudo_span_targets(scores: torch.Tensor, of_lengths) -> tuple:
+    """Per-frame scores [B, num_frames] (device, fp32) -> (start_targets, end_targets) int64 [B] on the device
+    (LSTP_SF_blip2_module.py:195-224: monotone stack + rescale to flow positions; no `.tolist()` round trip)."""
+    if not torch.is_tensor(of_lengths):
+        of_lengths = torch.tensor(list(of_lengths), dtype=torch.int32, device=scores.device)
+    return ops.pseudo_span(scores.to(torch.float32).contiguous(), of_lengths.to(torch.int32).contiguous())
+
+
+def mrc_loss(of_logits: torch.Tensor, start_targets: torch.Tensor, end_targets: torch.Tensor) -> torch.Tensor:
+    """Span cross-entropy on the sampler's mrc logits [B, Lof, 2] (LSTP_SF_blip2_module.py:238-253)."""
+    return ops.span_ce_loss(of_logits.to(torch.float32).contiguous(), start_targets.contiguous(), end_targets.contiguous())
