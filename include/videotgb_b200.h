@@ -97,6 +97,8 @@ TGB_API int tgb_gather_frames(const void* src, const int64_t* indices, void* dst
 TGB_API int tgb_patchify_f32(const float* pixels_tchw, void* out_bf16, int F, int S, int P, int ld, tgb_stream_t stream);
 TGB_API int tgb_patchify_u8(const uint8_t* frames_thwc, void* out_bf16, int F, int S, int P, int ld,
                     const float* mean3_host, const float* std3_host, tgb_stream_t stream);
+/* Debug / test knob: 0 = choose (default), 1 = never use the single-fma pair kernel for u8 frames.                  */
+TGB_API int tgb_patchify_set_variant(int variant);
 /* hidden[f, 0, :] = class_embedding + position_embedding[0]   (xblip2.py:114-116)   hidden: f32 [F, tokens, D] */
 TGB_API int tgb_fill_cls_rows(float* hidden, const float* cls, const float* pos0, int F, int tokens, int D,
                       tgb_stream_t stream);

@@ -170,8 +170,24 @@ def test_patchify_matches_unfold():
     u8 = torch.randint(0, 256, (2, 224, 224, 3), generator=g, dtype=torch.uint8)
     norm = torch.from_numpy(transform_ref.normalize_u8_thwc(u8.numpy()))
     want = torch.nn.functional.unfold(norm, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588).to(torch.bfloat16)
-    got = ops.patchify_u8(u8.to(DEV), 14, 592).cpu()
-    assert torch.equal(got[:, :588], want)
+    u8[0, :2].copy_(torch.arange(2 * 224 * 3, dtype=torch.int64).remainder(256).to(torch.uint8).view(2, 224, 3))  # all values
+    norm = torch.from_numpy(transform_ref.normalize_u8_thwc(u8.numpy()))
+    want = torch.nn.functional.unfold(norm, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588).to(torch.bfloat16)
+    try:
+        for variant in (0, 1):             # 0: single-fma pair kernel (host-verified exact), 1: generic kernel
+            ops.patchify_set_variant(variant)
+            got = ops.patchify_u8(u8.to(DEV), 14, 592).cpu()
+            assert torch.equal(got[:, :588], want) and got[:, 588:].abs().max() == 0, variant
+            got = ops.patchify_u8(u8.to(DEV), 14, 608).cpu()
+            assert torch.equal(got[:, :588], want) and got[:, 588:].abs().max() == 0, variant
+    finally:
+        ops.patchify_set_variant(0)
+    # other normalisation constants (the exactness check may route these to the fallback kernels): still bit-exact
+    for mean, std in [((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)), ((0.1, 0.7, 0.3), (1.3, 0.011, 0.9))]:
+        norm = torch.from_numpy(transform_ref.normalize_u8_thwc(u8.numpy(), mean, std))
+        want = torch.nn.functional.unfold(norm, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588).to(torch.bfloat16)
+        got = ops.patchify_u8(u8.to(DEV), 14, 592, mean=mean, std=std).cpu()
+        assert torch.equal(got[:, :588], want), (mean, std)
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm

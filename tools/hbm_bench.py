@@ -47,7 +47,11 @@ def main():
     ms = timeit(lambda: ops.normalize_frames_u8(u8))
     report("normalize_u8_kernel (u8 THWC -> f32 TCHW)", f * (150528 + 602112), ms, f"{f} frames")
     ms = timeit(lambda: ops.patchify_u8(u8, 14, 592))
-    report("patchify_kernel<u8> (normalise + im2col -> bf16)", f * (150528 + 256 * 592 * 2), ms, f"{f} frames")
+    report("patchify_u8_pair_kernel (normalise + im2col -> bf16)", f * (150528 + 256 * 592 * 2), ms, f"{f} frames")
+    ops.patchify_set_variant(1)
+    ms = timeit(lambda: ops.patchify_u8(u8, 14, 592))
+    ops.patchify_set_variant(0)
+    report("patchify_kernel<u8> (generic fallback: residual-corrected normalise)", f * (150528 + 256 * 592 * 2), ms, f"{f} frames")
     px = torch.randn(1024, 3, 224, 224, device=dev)
     ms = timeit(lambda: ops.patchify(px, 14, 592))
     report("patchify_kernel<f32> (im2col -> bf16)", 1024 * (602112 + 256 * 592 * 2), ms, "1024 frames")

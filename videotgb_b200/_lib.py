@@ -29,6 +29,7 @@ SIGNATURES = {
     "tgb_gather_frames": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_sz, c_vp], c_int),
     "tgb_patchify_f32": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp], c_int),
     "tgb_patchify_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
+    "tgb_patchify_set_variant": ([c_int], c_int),
     "tgb_fill_cls_rows": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp], c_int),
     "tgb_gemm_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_int, c_int,
                        c_vp, c_i64, c_int, c_vp], c_int),

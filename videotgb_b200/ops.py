@@ -168,6 +168,11 @@ def patchify_u8(frames_thwc: torch.Tensor, patch: int, ld: int, mean=CLIP_MEAN, 
     return out
 
 
+def patchify_set_variant(variant: int) -> None:
+    """Test knob: 1 keeps u8 frames off the single-fma pair kernel (table / residual-corrected kernels instead)."""
+    check(_lib.load().tgb_patchify_set_variant(int(variant)))
+
+
 def fill_cls_rows(hidden: torch.Tensor, cls: torch.Tensor, pos0: torch.Tensor) -> None:
     h = _need(hidden, torch.float32, "hidden")
     f, tokens, d = h.shape
