@@ -146,6 +146,10 @@ TGB_API int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int64_
 TGB_API int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int frames, float scale,
                                    tgb_stream_t stream);
 
+/* Debug / test knob: 0 = ping-pong kernel (two query tiles in flight, online softmax over two key blocks; default),
+ * 1 = one-shot kernel (whole score row in tensor memory; kept as a cross-check).                                    */
+TGB_API int tgb_vit_attention_set_variant(int variant);
+
 /* ---------------------------------------------------------------- A1/A2/A4 temporal sampler -----------
  * TemporalOFEmbedding (src/models/components/xropebert.py:103-129): Conv2d(2,768,k16,s16) -> flatten(2) ->
  * Linear(196,1) has no non-linearity in between, so it reassociates exactly to

@@ -335,14 +335,29 @@ def test_attention(b, h, sq, sk, d, masked):
     assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
 
 
-@pytest.mark.parametrize("frames,scale_in", [(1, 1.0), (3, 1.0), (19, 2.5)])
-def test_vit_attention_tcgen05(frames, scale_in):
-    """The tensor-memory attention kernel (S in TMEM, P as TMEM A operand, V MN-major) vs torch and vs the mma.sync kernel."""
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("frames,scale_in,late_peak", [(1, 1.0, False), (3, 1.0, False), (19, 2.5, False), (2, 1.0, True),
+                                                       (150, 1.0, False)])
+def test_vit_attention_tcgen05(frames, scale_in, late_peak, variant):
+    """The tensor-memory attention kernels (0: ping-pong, two key blocks with online softmax; 1: one-shot) vs torch and
+    vs the mma.sync kernel.  `late_peak` plants dominant keys in the second key block (rows >= 144) for half of the
+    queries, which forces the ping-pong kernel through its accumulator-rescale path."""
     g = torch.Generator().manual_seed(frames)
     qkv = (torch.randn(frames * 257, 4224, generator=g) * scale_in).to(torch.bfloat16)
+    if late_peak:
+        x = qkv.float().view(frames, 257, 3, 16, 88)
+        x[:, 200, 1] = x[:, 5, 0] * 3.0            # key 200 aligned with query 5 (and correlated with nothing else)
+        x[:, 150:160, 1] *= 4.0                    # a band of large keys
+        x[:, 1::2, 0] *= 2.0                       # odd queries sharper than even ones -> per-row decisions differ
+        qkv = x.view(frames * 257, 4224).to(torch.bfloat16)
     want = _attn_ref(qkv[:, :1408], qkv[:, 1408:2816], qkv[:, 2816:], frames, 16, 257, 257, 88, 88 ** -0.5)
     qd = qkv.to(DEV)
-    got = ops.vit_attention(qd, frames, 88 ** -0.5)
+    ops.vit_attention_set_variant(variant)
+    try:
+        got = ops.vit_attention(qd, frames, 88 ** -0.5)
+        torch.cuda.synchronize()
+    finally:
+        ops.vit_attention_set_variant(0)
     err = _relerr(got.cpu(), want)
     assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
     other = ops.attention(qd[:, :1408], qd[:, 1408:2816], qd[:, 2816:], frames, 16, 257, 257, 88, 88 ** -0.5)

@@ -46,7 +46,12 @@ def probe(f, seed=0, scale_v=1.0):
 def bench(f, iters=10):
     qkv = torch.randn(f * 257, 4224, device="cuda").to(torch.bfloat16)
     out = torch.empty(f * 257, 1408, dtype=torch.bfloat16, device="cuda")
-    for name, fn in (("tcgen05", lambda: ops.vit_attention(qkv, f, 88 ** -0.5, out=out)),
+    def one_shot():
+        ops.vit_attention_set_variant(1)
+        ops.vit_attention(qkv, f, 88 ** -0.5, out=out)
+        ops.vit_attention_set_variant(0)
+    for name, fn in (("tcgen05 ping-pong", lambda: ops.vit_attention(qkv, f, 88 ** -0.5, out=out)),
+                     ("tcgen05 one-shot", one_shot),
                      ("mma.sync", lambda: ops.attention(qkv[:, :1408], qkv[:, 1408:2816], qkv[:, 2816:], f, 16, 257, 257, 88, 88 ** -0.5, out=out))):
         for _ in range(3):
             fn()

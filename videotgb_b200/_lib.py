@@ -45,6 +45,7 @@ SIGNATURES = {
     "tgb_rope_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp], c_int),
     "tgb_linear_small_f32": ([c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp], c_int),
     "tgb_vit_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_vp], c_int),
+    "tgb_vit_attention_set_variant": ([c_int], c_int),
     "tgb_cast_f32_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp], c_int),
     "tgb_group_mean_f32": ([c_vp, c_vp, c_int, c_int, c_i64, c_vp], c_int),
 }

@@ -466,6 +466,547 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const VitAttnP
   }
 }
 
+#ifdef TGB_ATTN_TRACE
+// Debug timeline (tools/attn_trace.py builds a private copy of the library with -DTGB_ATTN_TRACE): CTA 0 logs
+// (tag, clock64) per role; role 0 TMA, 1 MMA, 2/3 CLS warps, 4/5 lane 0 of the first warp of softmax warpgroup 0/1.
+constexpr int TR_ROLES = 6, TR_CAP = 1024;
+__device__ long long g_attn_trace[TR_ROLES][TR_CAP][2];
+__device__ int g_attn_trace_n[TR_ROLES];
+#define TRACE_DECL int tr_n = 0;
+#define TRACE(role, tag)                                                        \
+  do {                                                                          \
+    if (blockIdx.x == 0 && tr_n < TR_CAP) {                                     \
+      g_attn_trace[role][tr_n][0] = (tag);                                      \
+      g_attn_trace[role][tr_n][1] = clock64();                                  \
+      g_attn_trace_n[role] = ++tr_n;                                            \
+    }                                                                           \
+  } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(role, tag) do { } while (0)
+#endif
+
+// =====================================================================================================================
+// Ping-pong variant (default).  The two 128-row query tiles of an item are two independent chains, each with its own
+// S/P and O accumulators in tensor memory and its own softmax warpgroup (one thread per query row, no cross-thread
+// exchange), so the TMEM reads + exponentials of one tile overlap the tensor-core work of the other:
+//   TMEM   S_t fp32 [t*144, t*144+144)  (P_t bf16 aliases its first 72 columns)   O_t fp32 [288 + t*96, +96)
+//   keys   block 0 = keys [0,144) (one N=144 MMA per k-step), block 1 = keys [144,272) (N=128, 113 valid)
+//   chain  S(t,0) -> softmax -> P V(t,0) -> S(t,1) -> online softmax (running max m; O_t and l are rescaled only if the
+//          new block raises the max by more than 2^8 -- then p <= 256 is still exact enough in bf16/fp32) -> P V(t,1)
+//          -> epilogue O_t / l.  The tensor pipe executes in issue order, so overwriting the P/S alias needs no barrier.
+//   warp 0 TMEM alloc + TMA producer, warp 1 MMA issuer, warps 2/3 CLS query row (alternate items), warps 4-7 / 8-11
+//   softmax warpgroups of tile 0 / tile 1.
+// =====================================================================================================================
+constexpr uint32_t PP_COL_S = 0, PP_S_STRIDE = 144, PP_COL_O = 288, PP_O_STRIDE = 96;
+constexpr int PP_KEYS0 = 144;                  // keys in block 0; block 1 holds keys [144, 272)
+constexpr int PP_VALID1 = VA_S - PP_KEYS0;     // 113 valid keys in block 1
+constexpr float PP_RESCALE_THRESHOLD = 8.0f;   // log2 units
+// shared memory: Q [tile][dblk][128 x 128 B] | K [dblk][272 x 128 B] | V [dblk][272 x 128 B] | barriers.  K and V are
+// loaded (and released) per key block -- rows [0,144) through a 144-row TMA box, rows [144,272) through a 128-row box --
+// so the next item's operands stream in while the current item is still being computed.
+constexpr int PP_Q_BYTES = 128 * 128;                          // one (tile, d block)
+constexpr int PP_SMEM_Q = 0;
+constexpr int PP_SMEM_K = 4 * PP_Q_BYTES;
+constexpr int PP_SMEM_V = PP_SMEM_K + 2 * VA_KBLK_BYTES;
+constexpr int PP_SMEM_BAR = PP_SMEM_V + 2 * VA_KBLK_BYTES;     // 204800
+constexpr int PP_SMEM_TOTAL = PP_SMEM_BAR + 256 + 1024;        // + alignment slack
+constexpr int PP_BLK0_BYTES = PP_KEYS0 * 128;                  // one d block of key block 0
+constexpr int PP_BLK1_BYTES = (272 - PP_KEYS0) * 128;
+
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[NREG]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), TGB_W8(v, OFF) : "memory");
+}
+
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[NREG]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), TGB_W8(v, OFF), TGB_W8(v, OFF + 8) : "memory");
+}
+// Row max of the first NVALID of NCOLS fp32 score columns at `s_addr`: every tcgen05.ld is in flight at once (the only
+// moment a thread holds a whole score row), 3-input max tree.
+template <int NCOLS, int NVALID>
+__device__ __forceinline__ float pp_row_max(uint32_t s_addr) {
+  static_assert(NCOLS == 128 || NCOLS == 144, "two key-block widths");
+  uint32_t v[NCOLS];
+  tmem_ld32<0>(s_addr, v);
+  tmem_ld32<32>(s_addr + 32, v);
+  tmem_ld32<64>(s_addr + 64, v);
+  tmem_ld32<96>(s_addr + 96, v);
+  if (NCOLS == 144) tmem_ld16<128>(s_addr + 128, v);
+  tmem_ld_wait();
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NVALID; j += 4) {
+    m0 = fmaxf(m0, __uint_as_float(v[j]));
+    if (j + 1 < NVALID) m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+    if (j + 2 < NVALID) m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+    if (j + 3 < NVALID) m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// 16 score columns -> 8 packed bf16 probability registers; staged (fma, ex2, add/pack) so the MUFU pipe is fed back to
+// back.  NV = valid columns of the chunk (the rest produce p = 0).
+template <int NV>
+__device__ __forceinline__ void pp_exp16(uint32_t (&v)[16], float sl2, float negm, float& l0, float& l1, float& l2, float& l3) {
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = fmaf(__uint_as_float(v[j]), sl2, negm);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = (j < NV) ? ex2_approx(x[j]) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    l0 += x[j]; l1 += x[j + 1]; l2 += x[j + 2]; l3 += x[j + 3];
+    v[j >> 1] = pack_bf16(x[j], x[j + 1]);
+    v[(j >> 1) + 1] = pack_bf16(x[j + 2], x[j + 3]);
+  }
+}
+
+// Pass 2 over one key block: NFULL all-valid 16-column chunks in a ROLLED loop (the unrolled form was instruction-fetch
+// bound: every warp streamed ~10 KB of straight-line code per block) plus one peeled chunk with TAIL valid columns
+// (TAIL = 16: a plain extra chunk; 0 < TAIL < 16: masked; the P columns of a fully masked remainder are zeroed).
+// P chunk c (8 bf16x2 columns) is stored behind the read position; the next chunk's tcgen05.ld is issued before the
+// current chunk is processed.  Returns the row sum.
+template <int NFULL, int TAIL>
+__device__ __forceinline__ float pp_exp_block(uint32_t s_addr, float sl2, float negm) {
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  uint32_t cur[16], nxt[16];
+  tmem_ld16<0>(s_addr, cur);
+#pragma unroll 1
+  for (int c = 0; c < NFULL; ++c) {
+    tmem_ld_wait();
+    if (TAIL > 0 || c + 1 < NFULL) tmem_ld16<0>(s_addr + (c + 1) * 16, nxt);   // (never reads past the block)
+    pp_exp16<16>(cur, sl2, negm, l0, l1, l2, l3);
+    tmem_st8<0>(s_addr + c * 8, cur);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+  }
+  if (TAIL > 0) {
+    tmem_ld_wait();
+    pp_exp16<TAIL>(cur, sl2, negm, l0, l1, l2, l3);
+    tmem_st8<0>(s_addr + NFULL * 8, cur);
+  }
+  return (l0 + l1) + (l2 + l3);
+}
+
+// One CLS query row (row 0 of the image) on the warp-level tensor-core path (mma.sync.m16n8k16), one warp per item,
+// reading the SAME swizzled K/V tiles TMA staged for tcgen05 (element (key r, d c) of a 64-wide d block lives at
+// (r/8)*1024 + (r%8)*128 + (((c/8) ^ (r%8)) * 16) + (c%8)*2) -- no extra global traffic.  Transposed formulation so that
+// the single query occupies the N side (8 columns, one valid) instead of the 16-row M side:
+//   S^T[keys x 1] = K[keys x d] q^T      A = K through ldmatrix,        B = q (lanes 0..3 hold it, the rest are zero)
+//   O^T[d x 1]    = V^T[d x keys] p      A = V through ldmatrix.trans,  B = p (moved from the lanes that own column 0)
+// Column 0 of an accumulator tile lives in lanes 0,4,..,28 (c0: row lane/4, c2: row lane/4 + 8).
+__device__ __forceinline__ void va_ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void va_ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void va_mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// byte offset of the 16-byte chunk holding d [8*chunk, 8*chunk+8) of key `r` (chunk in 0..11: 0..7 in d block 0)
+__device__ __forceinline__ uint32_t va_tile_off(int r, int chunk) {
+  return (uint32_t)((chunk >> 3) * VA_KBLK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((((chunk & 7) ^ (r & 7))) << 4));
+}
+
+__device__ __forceinline__ void cls_row_item(const VitAttnParams& p, int w, uint32_t ph, uint32_t sK, uint32_t sV,
+                                             uint64_t* k_full, uint64_t* k_free, uint64_t* v_full, uint64_t* v_free,
+                                             int lane) {          // the four barrier arguments are [2]: one per key block
+  const int b = w / VA_H, h = w - b * VA_H;
+  const long long row0 = (long long)b * VA_S;
+  const int g = lane >> 2, t = lane & 3;
+  // B fragments of q: b0 = d (16ks + 2t, +1), b1 = d (16ks + 8 + 2t, +1), column n = g -> only g == 0 is the real query
+  uint32_t qb[6][2];
+  {
+    const uint32_t* q32 = reinterpret_cast<const uint32_t*>(p.qkv + row0 * p.ld_qkv + h * VA_D);
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) {
+      qb[ks][0] = (g == 0) ? __ldg(q32 + ks * 8 + t) : 0u;
+      qb[ks][1] = (g == 0 && ks < 5) ? __ldg(q32 + ks * 8 + 4 + t) : 0u;      // d 88..95 does not exist
+    }
+  }
+  const int lrow = lane & 7, lmat = lane >> 3;
+  mbar_wait(&k_full[0], ph);
+  mbar_wait(&k_full[1], ph);
+  float sc[17][2];
+  // groups of up to 4 key tiles: the ldmatrix loads of a k-step are issued together, then the (independent) MMAs
+#pragma unroll
+  for (int mg = 0; mg < 17; mg += 4) {
+    float c[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) {
+      uint32_t a[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (mg + u < 17) {
+          const int key = (mg + u) * 16 + (lmat & 1) * 8 + lrow;   // matrices: (keys lo, d lo) (keys hi, d lo) (keys lo, d hi) (keys hi, d hi)
+          va_ldsm_x4(sK + va_tile_off(key, 2 * ks + (lmat >> 1)), a[u]);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (mg + u < 17) va_mma_16816(c[u], a[u], qb[ks][0], qb[ks][1]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (mg + u < 17) { sc[mg + u][0] = c[u][0]; sc[mg + u][1] = c[u][2]; }
+  }
+  __syncwarp();
+  if (lane == 0) { mbar_arrive(&k_free[0]); mbar_arrive(&k_free[1]); }   // done reading K (second arrival: tcgen05.commit)
+  // softmax over the 257 valid keys; lanes with t == 0 own key mt*16 + g (sc[mt][0]) and mt*16 + 8 + g (sc[mt][1])
+  float m = -INFINITY;
+#pragma unroll
+  for (int mt = 0; mt < 17; ++mt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool valid = t == 0 && (mt * 16 + e * 8 + g) < VA_S;
+      sc[mt][e] = valid ? sc[mt][e] * p.scale_log2 : -INFINITY;
+      m = fmaxf(m, sc[mt][e]);
+    }
+  }
+  m = warp_max(m);
+  float l = 0.f;
+  uint32_t pk[17];                                               // bf16x2 (p[key g], p[key g + 8]) of k-step mt
+#pragma unroll
+  for (int mt = 0; mt < 17; ++mt) {
+    const float p0 = ex2_approx(sc[mt][0] - m), p1 = ex2_approx(sc[mt][1] - m);     // exp2(-inf) = 0
+    l += p0 + p1;
+    pk[mt] = pack_bf16(p0, p1);
+  }
+  l = warp_sum(l);
+  mbar_wait(&v_full[0], ph);
+  mbar_wait(&v_full[1], ph);
+  float o[6][4];
+#pragma unroll
+  for (int mt = 0; mt < 6; ++mt) { o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 17; ++kk) {
+    // B fragment of p for keys [16kk, 16kk+16): b0 = keys (2t, 2t+1), b1 = keys (8+2t, 9+2t), column n = g
+    const uint32_t x0 = __shfl_sync(0xffffffffu, pk[kk], 8 * t);        // owner of key 2t   (low half) and 8+2t (high half)
+    const uint32_t x1 = __shfl_sync(0xffffffffu, pk[kk], 8 * t + 4);    // owner of key 2t+1 and 9+2t
+    const uint32_t b0 = (g == 0) ? __byte_perm(x0, x1, 0x5410) : 0u;
+    const uint32_t b1 = (g == 0) ? __byte_perm(x0, x1, 0x7632) : 0u;
+    const int key = kk * 16 + (lmat >> 1) * 8 + lrow;            // matrices: (keys lo, d lo) (keys lo, d hi) (keys hi, d lo) (keys hi, d hi)
+    uint32_t a[6][4];
+#pragma unroll
+    for (int mt = 0; mt < 6; ++mt) va_ldsm_x4_t(sV + va_tile_off(key, 2 * mt + (lmat & 1)), a[mt]);
+#pragma unroll
+    for (int mt = 0; mt < 6; ++mt) va_mma_16816(o[mt], a[mt], b0, b1);
+  }
+  __syncwarp();
+  if (lane == 0) { mbar_arrive(&v_free[0]); mbar_arrive(&v_free[1]); }   // done reading V
+  if (t == 0) {
+    const float inv = 1.f / l;
+    __nv_bfloat16* dst = p.out + row0 * p.ld_out + h * VA_D;
+#pragma unroll
+    for (int mt = 0; mt < 6; ++mt) {
+      dst[mt * 16 + g] = __float2bfloat16(o[mt][0] * inv);
+      if (mt < 5) dst[mt * 16 + 8 + g] = __float2bfloat16(o[mt][2] * inv);
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(VA_THREADS, 1)
+vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __grid_constant__ CUtensorMap tmap128,
+                        const VitAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + PP_SMEM_Q;
+  uint8_t* sK = smem + PP_SMEM_K;
+  uint8_t* sV = smem + PP_SMEM_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PP_SMEM_BAR);
+  uint64_t* q_full = bars + 0;     // [2] per query tile
+  uint64_t* q_free = bars + 2;     // [2]
+  uint64_t* k_full = bars + 4;     // [2] per key block
+  uint64_t* k_free = bars + 6;     // [2]
+  uint64_t* v_full = bars + 8;     // [2]
+  uint64_t* v_free = bars + 10;    // [2]
+  uint64_t* s_full = bars + 12;    // [2] per query tile, one completion per (item, key block)
+  uint64_t* p_full = bars + 14;    // [2]
+  uint64_t* o_full = bars + 16;    // [2] one completion per item
+  uint64_t* o_free = bars + 18;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmap144);
+    tma_prefetch_desc(&tmap128);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1); mbar_init(&q_free[t], 1);
+      mbar_init(&k_full[t], 1); mbar_init(&k_free[t], 2);      // tcgen05.commit + the CLS warp of the item
+      mbar_init(&v_full[t], 1); mbar_init(&v_free[t], 2);
+      mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128);
+      mbar_init(&o_full[t], 1); mbar_init(&o_free[t], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    // Loads are issued in the order the previous item releases their buffers: K0, Q0, V0, K1, Q1, V1.
+    if (lane == 0) {
+      TRACE_DECL
+      int i = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+        const int b = w / VA_H, h = w - b * VA_H;
+        const int row0 = b * VA_S;
+        const uint32_t ph = i & 1;
+        auto load_kv = [&](uint8_t* dst, uint64_t* full, int blk, int col_h) {
+          mbar_arrive_expect_tx(full, 2 * (blk == 0 ? PP_BLK0_BYTES : PP_BLK1_BYTES));
+#pragma unroll
+          for (int db = 0; db < 2; ++db)
+            tma_load_3d(dst + db * VA_KBLK_BYTES + blk * PP_BLK0_BYTES, blk == 0 ? &tmap144 : &tmap128, full, db * 64, col_h,
+                        row0 + blk * PP_KEYS0);
+        };
+        auto load_q = [&](int t) {
+          mbar_wait(&q_free[t], ph ^ 1);
+          TRACE(0, i * 100 + 2 + t);                             // Q_t load issued
+          mbar_arrive_expect_tx(&q_full[t], 2 * PP_Q_BYTES);
+#pragma unroll
+          for (int db = 0; db < 2; ++db)
+            tma_load_3d(sQ + (t * 2 + db) * PP_Q_BYTES, &tmap128, &q_full[t], db * 64, h, row0 + 1 + t * 128);
+        };
+        mbar_wait(&k_free[0], ph ^ 1);
+        TRACE(0, i * 100 + 1);                                   // K block 0 load issued
+        load_kv(sK, &k_full[0], 0, VA_H + h);
+        load_q(0);
+        mbar_wait(&v_free[0], ph ^ 1);
+        TRACE(0, i * 100 + 4);                                   // V block 0 load issued
+        load_kv(sV, &v_full[0], 0, 2 * VA_H + h);
+        mbar_wait(&k_free[1], ph ^ 1);
+        TRACE(0, i * 100 + 5);                                   // K block 1 load issued
+        load_kv(sK, &k_full[1], 1, VA_H + h);
+        load_q(1);
+        mbar_wait(&v_free[1], ph ^ 1);
+        TRACE(0, i * 100 + 6);                                   // V block 1 load issued
+        load_kv(sV, &v_full[1], 1, 2 * VA_H + h);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      TRACE_DECL
+      constexpr uint32_t idesc_s144 = umma_idesc_bf16(128, 144);
+      constexpr uint32_t idesc_s128 = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 96) | (1u << 16);     // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      auto issue_s = [&](int t, int blk) {                      // S_t = Q_t K_blk^T, then publish it
+        const uint32_t d = tmem_base + PP_COL_S + t * PP_S_STRIDE;
+        uint32_t accum = 0;
+#pragma unroll
+        for (int db = 0; db < 2; ++db) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (db == 1 && ks >= 2) break;                       // d = 96..127 is all zero
+            const uint64_t da = umma_desc_sw128(q_addr + (t * 2 + db) * PP_Q_BYTES + ks * 32);
+            const uint64_t dk = umma_desc_sw128(k_addr + db * VA_KBLK_BYTES + blk * PP_BLK0_BYTES + ks * 32);
+            umma_bf16_ss(d, da, dk, blk == 0 ? idesc_s144 : idesc_s128, accum);
+            accum = 1;
+          }
+        }
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int blk) {                     // O_t (+)= P_t V_blk
+        const uint32_t d = tmem_base + PP_COL_O + t * PP_O_STRIDE;
+        const uint32_t a = tmem_base + PP_COL_S + t * PP_S_STRIDE;
+        const int kk0 = blk == 0 ? 0 : PP_KEYS0 / 16, kk1 = blk == 0 ? PP_KEYS0 / 16 : 17;
+        for (int kk = kk0; kk < kk1; ++kk) {
+          const uint64_t db = umma_desc_mn_sw128(v_addr + kk * 2048, VA_KBLK_BYTES, 1024);
+          umma_bf16_ts(d, a + (kk - kk0) * 8, db, idesc_pv, (blk > 0 || kk > kk0) ? 1u : 0u);
+        }
+      };
+      int i = 0;
+      if (blockIdx.x < p.num_items) {
+        mbar_wait(&k_full[0], 0);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_full[t], 0);
+          tc_fence_after();
+          issue_s(t, 0);
+        }
+        umma_commit(&k_free[0]);
+      }
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+        const uint32_t ph = i & 1;
+        const bool has_next = w + (int)gridDim.x < p.num_items;
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {                            // key block 0 done by the softmax warps -> P V, next S
+          mbar_wait(&p_full[t], 0);
+          TRACE(1, i * 100 + 10 + t);                            // P(t,0) seen
+          if (t == 0) { mbar_wait(&v_full[0], ph); mbar_wait(&k_full[1], ph); }
+          mbar_wait(&o_free[t], ph ^ 1);                         // the previous item's epilogue has read O_t
+          TRACE(1, i * 100 + 12 + t);                            // V / K1 / O_t available -> issue
+          tc_fence_after();
+          issue_pv(t, 0);
+          issue_s(t, 1);
+          umma_commit(&q_free[t]);
+          if (t == 1) { umma_commit(&v_free[0]); umma_commit(&k_free[1]); }
+        }
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], 1);
+          TRACE(1, i * 100 + 20 + t);                            // P(t,1) seen
+          if (t == 0) mbar_wait(&v_full[1], ph);
+          tc_fence_after();
+          issue_pv(t, 1);
+          umma_commit(&o_full[t]);
+          if (t == 1) umma_commit(&v_free[1]);
+          if (has_next) {
+            if (t == 0) mbar_wait(&k_full[0], ph ^ 1);
+            mbar_wait(&q_full[t], ph ^ 1);
+            TRACE(1, i * 100 + 22 + t);                          // next item's K0 / Q_t landed -> issue S(t,0)
+            tc_fence_after();
+            issue_s(t, 0);
+            if (t == 1) umma_commit(&k_free[0]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ================================================================ CLS query rows: warp 2 even items, warp 3 odd items
+    const uint32_t sK32 = smem_u32(sK), sV32 = smem_u32(sV);
+    TRACE_DECL
+    int i = 0;
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+      if ((i & 1) == (warp - 2)) {
+        if (lane == 0) TRACE(warp, i * 100 + 30);
+        cls_row_item(p, w, i & 1, sK32, sV32, k_full, k_free, v_full, v_free, lane);
+        if (lane == 0) TRACE(warp, i * 100 + 31);
+      } else {
+        // keep in step with the barrier phases of the items the other warp handles (a parity wait is only
+        // meaningful for the current or the previous phase)
+        mbar_wait(&k_full[0], i & 1);
+        mbar_wait(&k_full[1], i & 1);
+        mbar_wait(&v_full[0], i & 1);
+        mbar_wait(&v_full[1], i & 1);
+      }
+    }
+  } else {
+    // ================================================================ softmax warpgroups: one thread per query row
+    // Streaming two-pass softmax over 32-column chunks of S_t: pass 1 finds the row max, pass 2 re-reads S (tensor
+    // memory reads are cheap: ~68 B/clk per warp), exponentiates and writes the packed bf16 P chunk behind the read
+    // position (P aliases the first half of S).  Each tcgen05.ld is issued one chunk ahead of its use; at most two
+    // chunks are live, so nothing spills.
+    const int t = (warp - 4) >> 2;               // query tile of this warpgroup
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t s_addr = lane_base + PP_COL_S + t * PP_S_STRIDE;
+    const uint32_t o_addr = lane_base + PP_COL_O + t * PP_O_STRIDE;
+    const float sl2 = p.scale_log2;
+    TRACE_DECL
+#ifdef TGB_ATTN_TRACE
+    const bool tr_on = (quarter == 0 && lane == 0);
+#define STRACE(tag) do { if (tr_on) TRACE(4 + t, tag); } while (0)
+#else
+#define STRACE(tag) do { } while (0)
+#endif
+    int i = 0;
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+      const int b = w / VA_H, h = w - b * VA_H;
+      float mx, l;
+      {
+        // ------------------------------------------------------------ key block 0: keys [0,144), all valid
+        mbar_wait(&s_full[t], 0);
+        STRACE(i * 100 + 40);                                    // S(t,0) seen
+        tc_fence_after();
+        mx = pp_row_max<PP_KEYS0, PP_KEYS0>(s_addr) * sl2;
+        STRACE(i * 100 + 41);                                    // row max known
+        l = pp_exp_block<PP_KEYS0 / 16 - 1, 16>(s_addr, sl2, -mx);
+        STRACE(i * 100 + 42);                                    // exponentials done
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        STRACE(i * 100 + 43);                                    // P(t,0) published
+      }
+      {
+        // ------------------------------------------------------------ key block 1: keys [144,272), 113 valid
+        mbar_wait(&s_full[t], 1);                                 // also implies P V of block 0 has completed
+        STRACE(i * 100 + 50);                                    // S(t,1) seen
+        tc_fence_after();
+        const float m1x = pp_row_max<128, PP_VALID1>(s_addr) * sl2;
+        STRACE(i * 100 + 51);
+        float f = 1.f;
+        const bool need = m1x > mx + PP_RESCALE_THRESHOLD;
+        if (need) {
+          f = ex2_approx(mx - m1x);
+          mx = m1x;
+          l *= f;
+        }
+        if (__any_sync(0xffffffffu, need)) {                     // rare: rescale this warp's 32 rows of O_t in place
+#pragma unroll 1
+          for (int c = 0; c < 96; c += 8) {
+            uint32_t o[8];
+            tmem_ld8<0>(o_addr + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+            tmem_st8<0>(o_addr + c, o);
+          }
+          tmem_st_wait();
+        }
+        l += pp_exp_block<PP_VALID1 / 16, PP_VALID1 % 16>(s_addr, sl2, -mx);
+        STRACE(i * 100 + 52);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        STRACE(i * 100 + 53);                                    // P(t,1) published
+      }
+      {
+        // ------------------------------------------------------------ epilogue: O_t / l -> bf16
+        const float inv = 1.f / l;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * VA_S + 1 + t * 128 + row) * p.ld_out + h * VA_D);
+        mbar_wait(&o_full[t], i & 1);
+        STRACE(i * 100 + 60);                                    // O_t complete
+        tc_fence_after();
+        uint32_t o[96];
+        tmem_ld32<0>(o_addr, o);
+        tmem_ld32<32>(o_addr + 32, o);
+        tmem_ld32<64>(o_addr + 64, o);
+        tmem_ld_wait();
+        STRACE(i * 100 + 61);                                    // O_t in registers
+        tc_fence_before();
+        mbar_arrive(&o_free[t]);
+#pragma unroll
+        for (int c = 0; c < 11; ++c) {                           // 88 valid d columns = 11 x 16 bytes
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * c + 0]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+          v.y = pack_bf16(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+          v.z = pack_bf16(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+          v.w = pack_bf16(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+          dst[c] = v;
+        }
+        STRACE(i * 100 + 62);                                    // stores issued
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 va_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (fn) return fn;
@@ -482,6 +1023,23 @@ static PFN_cuTensorMapEncodeTiled_v12000 va_encode_fn() {
 
 using namespace tgb;
 
+#ifdef TGB_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int tgb_debug_attn_trace(long long* out_host, int* n_host) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out_host, g_attn_trace, sizeof(long long) * TR_ROLES * TR_CAP * 2) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(n_host, g_attn_trace_n, sizeof(int) * TR_ROLES) != cudaSuccess) return -1;
+  return TR_CAP;
+}
+#endif
+
+static int g_vit_attention_variant = 0;   // 0 = ping-pong kernel (default), 1 = one-shot kernel (cross-check)
+
+extern "C" int tgb_vit_attention_set_variant(int variant) {
+  TGB_CHECK_ARG(variant == 0 || variant == 1, "vit_attention_set_variant: 0 (ping-pong) or 1 (one-shot)");
+  g_vit_attention_variant = variant;
+  return TGB_OK;
+}
+
 extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int frames,
                                       float scale, tgb_stream_t stream) {
   int st = check_device();
@@ -496,21 +1054,26 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
     return TGB_ECUDA;
   }
-  CUtensorMap map;
+  CUtensorMap map, map144, map128;
   cuuint64_t dims[3] = {VA_D, 3 * VA_H, (cuuint64_t)frames * VA_S};
   cuuint64_t strides[2] = {VA_D * 2, (cuuint64_t)ld_qkv * 2};
-  cuuint32_t box[3] = {64, 1, VA_BOX_ROWS};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("vit_attention: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-    return TGB_ECUDA;
+  CUtensorMap* maps[3] = {&map, &map144, &map128};
+  const cuuint32_t box_rows[3] = {VA_BOX_ROWS, PP_KEYS0, 128};
+  for (int i = 0; i < 3; ++i) {
+    cuuint32_t box[3] = {64, 1, box_rows[i]};
+    CUresult r = fn(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("vit_attention: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+      return TGB_ECUDA;
+    }
   }
   static bool configured = false;
   if (!configured) {
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM_TOTAL));
+    TGB_CUDA(cudaFuncSetAttribute(vit_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_TOTAL));
     configured = true;
   }
   VitAttnParams p;
@@ -522,7 +1085,10 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   p.num_items = frames * VA_H;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
-  vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM_TOTAL, (cudaStream_t)stream>>>(map, p);
+  if (g_vit_attention_variant == 1)
+    vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM_TOTAL, (cudaStream_t)stream>>>(map, p);
+  else
+    vit_attention_pp_kernel<<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, p);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

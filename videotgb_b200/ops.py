@@ -368,6 +368,11 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor])
     return out
 
 
+def vit_attention_set_variant(variant: int) -> None:
+    """Test knob: 0 = ping-pong kernel (default), 1 = one-shot kernel."""
+    check(_lib.load().tgb_vit_attention_set_variant(int(variant)))
+
+
 def vit_attention(qkv: torch.Tensor, frames: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """tcgen05 self-attention for the EVA-ViT-g shape: qkv bf16 [frames*257, 4224] -> ctx bf16 [frames*257, 1408]."""
     _need(qkv, torch.bfloat16, "qkv", contiguous=False)
