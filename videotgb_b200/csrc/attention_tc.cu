@@ -510,7 +510,10 @@ constexpr int PP_SMEM_Q = 0;
 constexpr int PP_SMEM_K = 4 * PP_Q_BYTES;
 constexpr int PP_SMEM_V = PP_SMEM_K + 2 * VA_KBLK_BYTES;
 constexpr int PP_SMEM_BAR = PP_SMEM_V + 2 * VA_KBLK_BYTES;     // 204800
-constexpr int PP_SMEM_TOTAL = PP_SMEM_BAR + 256 + 1024;        // + alignment slack
+constexpr int PP_SMEM_CLS = PP_SMEM_BAR + 256;                 // float [2 warps][272] CLS-row scores / probabilities
+constexpr int PP_SMEM_STAGE = PP_SMEM_CLS + 2 * 272 * 4 + 128; // bf16 [128][88] output tile staged for the TMA store (128-B aligned)
+constexpr int PP_STAGE_BYTES = 128 * VA_D * 2;                 // 22528
+constexpr int PP_SMEM_TOTAL = PP_SMEM_STAGE + PP_STAGE_BYTES + 1024;   // + alignment slack
 constexpr int PP_BLK0_BYTES = PP_KEYS0 * 128;                  // one d block of key block 0
 constexpr int PP_BLK1_BYTES = (272 - PP_KEYS0) * 128;
 
@@ -619,7 +622,9 @@ __device__ __forceinline__ uint32_t va_tile_off(int r, int chunk) {
 
 __device__ __forceinline__ void cls_row_item(const VitAttnParams& p, int w, uint32_t ph, uint32_t sK, uint32_t sV,
                                              uint64_t* k_full, uint64_t* k_free, uint64_t* v_full, uint64_t* v_free,
-                                             int lane) {          // the four barrier arguments are [2]: one per key block
+                                             float* sc_s, int lane) {   // the four barrier arguments are [2]: one per key block
+  // Loops are ROLLED (scores and probabilities go through the 272-entry shared array sc_s): the routine runs once per
+  // item on one warp, so straight-line code would be fetched cold every time.
   const int b = w / VA_H, h = w - b * VA_H;
   const long long row0 = (long long)b * VA_S;
   const int g = lane >> 2, t = lane & 3;
@@ -636,65 +641,69 @@ __device__ __forceinline__ void cls_row_item(const VitAttnParams& p, int w, uint
   const int lrow = lane & 7, lmat = lane >> 3;
   mbar_wait(&k_full[0], ph);
   mbar_wait(&k_full[1], ph);
-  float sc[17][2];
-  // groups of up to 4 key tiles: the ldmatrix loads of a k-step are issued together, then the (independent) MMAs
+  // ---- S^T = K q^T, two 16-key tiles per iteration (16 of them; the 17th tile is peeled), scores of column 0 -> sc_s
+  auto qk_tile = [&](int mt, float (&c)[4]) {
+    const int key = mt * 16 + (lmat & 1) * 8 + lrow;            // matrices: (keys lo, d lo) (keys hi, d lo) (keys lo, d hi) (keys hi, d hi)
+    uint32_t a[6][4];
 #pragma unroll
-  for (int mg = 0; mg < 17; mg += 4) {
-    float c[4][4];
+    for (int ks = 0; ks < 6; ++ks) va_ldsm_x4(sK + va_tile_off(key, 2 * ks + (lmat >> 1)), a[ks]);
+    c[0] = c[1] = c[2] = c[3] = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.f; }
-#pragma unroll
-    for (int ks = 0; ks < 6; ++ks) {
-      uint32_t a[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (mg + u < 17) {
-          const int key = (mg + u) * 16 + (lmat & 1) * 8 + lrow;   // matrices: (keys lo, d lo) (keys hi, d lo) (keys lo, d hi) (keys hi, d hi)
-          va_ldsm_x4(sK + va_tile_off(key, 2 * ks + (lmat >> 1)), a[u]);
-        }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (mg + u < 17) va_mma_16816(c[u], a[u], qb[ks][0], qb[ks][1]);
+    for (int ks = 0; ks < 6; ++ks) va_mma_16816(c, a[ks], qb[ks][0], qb[ks][1]);
+  };
+#pragma unroll 1
+  for (int mt = 0; mt < 16; mt += 2) {
+    float c0[4], c1[4];
+    qk_tile(mt, c0);
+    qk_tile(mt + 1, c1);
+    if (t == 0) {
+      sc_s[mt * 16 + g] = c0[0]; sc_s[mt * 16 + 8 + g] = c0[2];
+      sc_s[mt * 16 + 16 + g] = c1[0]; sc_s[mt * 16 + 24 + g] = c1[2];
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (mg + u < 17) { sc[mg + u][0] = c[u][0]; sc[mg + u][1] = c[u][2]; }
+  }
+  {
+    float c0[4];
+    qk_tile(16, c0);
+    if (t == 0) { sc_s[256 + g] = c0[0]; sc_s[264 + g] = c0[2]; }
   }
   __syncwarp();
   if (lane == 0) { mbar_arrive(&k_free[0]); mbar_arrive(&k_free[1]); }   // done reading K (second arrival: tcgen05.commit)
-  // softmax over the 257 valid keys; lanes with t == 0 own key mt*16 + g (sc[mt][0]) and mt*16 + 8 + g (sc[mt][1])
+  // ---- softmax over the 257 valid keys, 9 per lane (the last lane group only key 256)
+  float x[9];
   float m = -INFINITY;
 #pragma unroll
-  for (int mt = 0; mt < 17; ++mt) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const bool valid = t == 0 && (mt * 16 + e * 8 + g) < VA_S;
-      sc[mt][e] = valid ? sc[mt][e] * p.scale_log2 : -INFINITY;
-      m = fmaxf(m, sc[mt][e]);
-    }
+  for (int it = 0; it < 9; ++it) {
+    const int j = it * 32 + lane;
+    x[it] = (j < VA_S) ? sc_s[j] * p.scale_log2 : -INFINITY;
+    m = fmaxf(m, x[it]);
   }
   m = warp_max(m);
   float l = 0.f;
-  uint32_t pk[17];                                               // bf16x2 (p[key g], p[key g + 8]) of k-step mt
+  __nv_bfloat16* p_s = reinterpret_cast<__nv_bfloat16*>(sc_s);   // probabilities as bf16 [272] over the same storage
+  float pr[9];
 #pragma unroll
-  for (int mt = 0; mt < 17; ++mt) {
-    const float p0 = ex2_approx(sc[mt][0] - m), p1 = ex2_approx(sc[mt][1] - m);     // exp2(-inf) = 0
-    l += p0 + p1;
-    pk[mt] = pack_bf16(p0, p1);
+  for (int it = 0; it < 9; ++it) {
+    pr[it] = (it * 32 + lane < 272) ? ex2_approx(x[it] - m) : 0.f;      // exp2(-inf) = 0 for the masked keys
+    l += pr[it];
   }
   l = warp_sum(l);
+  __syncwarp();                                                  // every lane has read its scores before p overwrites them
+#pragma unroll
+  for (int it = 0; it < 9; ++it)
+    if (it * 32 + lane < 272) p_s[it * 32 + lane] = __float2bfloat16(pr[it]);
+  __syncwarp();
   mbar_wait(&v_full[0], ph);
   mbar_wait(&v_full[1], ph);
+  // ---- O^T = V^T p
   float o[6][4];
 #pragma unroll
   for (int mt = 0; mt < 6; ++mt) { o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f; }
-#pragma unroll
+  const uint32_t* p32 = reinterpret_cast<const uint32_t*>(p_s);
+#pragma unroll 1
   for (int kk = 0; kk < 17; ++kk) {
     // B fragment of p for keys [16kk, 16kk+16): b0 = keys (2t, 2t+1), b1 = keys (8+2t, 9+2t), column n = g
-    const uint32_t x0 = __shfl_sync(0xffffffffu, pk[kk], 8 * t);        // owner of key 2t   (low half) and 8+2t (high half)
-    const uint32_t x1 = __shfl_sync(0xffffffffu, pk[kk], 8 * t + 4);    // owner of key 2t+1 and 9+2t
-    const uint32_t b0 = (g == 0) ? __byte_perm(x0, x1, 0x5410) : 0u;
-    const uint32_t b1 = (g == 0) ? __byte_perm(x0, x1, 0x7632) : 0u;
+    const uint32_t b0 = (g == 0) ? p32[kk * 8 + t] : 0u;
+    const uint32_t b1 = (g == 0) ? p32[kk * 8 + 4 + t] : 0u;
     const int key = kk * 16 + (lmat >> 1) * 8 + lrow;            // matrices: (keys lo, d lo) (keys lo, d hi) (keys hi, d lo) (keys hi, d hi)
     uint32_t a[6][4];
 #pragma unroll
@@ -718,7 +727,7 @@ __device__ __forceinline__ void cls_row_item(const VitAttnParams& p, int w, uint
 
 __global__ void __launch_bounds__(VA_THREADS, 1)
 vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __grid_constant__ CUtensorMap tmap128,
-                        const VitAttnParams p) {
+                        const __grid_constant__ CUtensorMap tmap_out, const VitAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + PP_SMEM_Q;
@@ -735,7 +744,10 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
   uint64_t* p_full = bars + 14;    // [2]
   uint64_t* o_full = bars + 16;    // [2] one completion per item
   uint64_t* o_free = bars + 18;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* stage_free = bars + 20; // the output staging tile has been read by its TMA store (one completion per use)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  float* cls_scores = reinterpret_cast<float*>(smem + PP_SMEM_CLS);
+  uint8_t* stage = smem + PP_SMEM_STAGE;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -743,6 +755,8 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmap144);
     tma_prefetch_desc(&tmap128);
+    tma_prefetch_desc(&tmap_out);
+    mbar_init(stage_free, 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1); mbar_init(&q_free[t], 1);
       mbar_init(&k_full[t], 1); mbar_init(&k_free[t], 2);      // tcgen05.commit + the CLS warp of the item
@@ -888,7 +902,7 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
       if ((i & 1) == (warp - 2)) {
         if (lane == 0) TRACE(warp, i * 100 + 30);
-        cls_row_item(p, w, i & 1, sK32, sV32, k_full, k_free, v_full, v_free, lane);
+        cls_row_item(p, w, i & 1, sK32, sV32, k_full, k_free, v_full, v_free, cls_scores + (warp - 2) * 272, lane);
         if (lane == 0) TRACE(warp, i * 100 + 31);
       } else {
         // keep in step with the barrier phases of the items the other warp handles (a parity wait is only
@@ -919,10 +933,16 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
 #else
 #define STRACE(tag) do { } while (0)
 #endif
+    bool store_pending = false;                  // (thread 0 of the warpgroup) a TMA store of the staging tile is in flight
     int i = 0;
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
       const int b = w / VA_H, h = w - b * VA_H;
       float mx, l;
+      if (store_pending) {                       // hand the staging tile on while this warpgroup would wait for S anyway
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(stage_free);
+        store_pending = false;
+      }
       {
         // ------------------------------------------------------------ key block 0: keys [0,144), all valid
         mbar_wait(&s_full[t], 0);
@@ -971,9 +991,11 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         STRACE(i * 100 + 53);                                    // P(t,1) published
       }
       {
-        // ------------------------------------------------------------ epilogue: O_t / l -> bf16
+        // ------------------------------------------------------------ epilogue: O_t / l -> bf16 -> staging tile -> TMA store
+        // Per-row 16-byte global stores touch 32 cache lines per instruction and kept the LSU (and with it the tensor
+        // memory traffic of the other warpgroup) busy for ~3k cycles; instead each thread writes its row into a dense
+        // [128][88] shared tile (conflict-free: 176-byte rows) and one thread issues an asynchronous bulk tensor store.
         const float inv = 1.f / l;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * VA_S + 1 + t * 128 + row) * p.ld_out + h * VA_D);
         mbar_wait(&o_full[t], i & 1);
         STRACE(i * 100 + 60);                                    // O_t complete
         tc_fence_after();
@@ -985,6 +1007,9 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         STRACE(i * 100 + 61);                                    // O_t in registers
         tc_fence_before();
         mbar_arrive(&o_free[t]);
+        const int use = 2 * i + t;                               // uses of the staging tile alternate between the warpgroups
+        mbar_wait(stage_free, (use & 1) ^ 1);                    // use - 1 has been read out
+        uint4* srow = reinterpret_cast<uint4*>(stage + row * (VA_D * 2));
 #pragma unroll
         for (int c = 0; c < 11; ++c) {                           // 88 valid d columns = 11 x 16 bytes
           uint4 v;
@@ -992,10 +1017,23 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
           v.y = pack_bf16(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
           v.z = pack_bf16(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
           v.w = pack_bf16(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-          dst[c] = v;
+          srow[c] = v;
+        }
+        fence_proxy_async();                                     // generic-proxy writes -> visible to the TMA (async proxy)
+        named_bar_sync(1 + t, 128);
+        if (quarter == 0 && lane == 0) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stage)), "r"(0), "r"(h),
+                         "r"(b * VA_S + 1 + t * 128) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          store_pending = true;
         }
         STRACE(i * 100 + 62);                                    // stores issued
       }
+    }
+    if (store_pending) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the store has fully completed before the CTA may exit
+      mbar_arrive(stage_free);
     }
   }
 
@@ -1070,6 +1108,19 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
       return TGB_ECUDA;
     }
   }
+  CUtensorMap map_out;                                            // [rows][16 heads][88] view of `out`, dense 128 x 88 box
+  {
+    cuuint64_t odims[3] = {VA_D, VA_H, (cuuint64_t)frames * VA_S};
+    cuuint64_t ostrides[2] = {VA_D * 2, (cuuint64_t)ld_out * 2};
+    cuuint32_t obox[3] = {VA_D, 1, 128};
+    CUresult r = fn(&map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, odims, ostrides, obox, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("vit_attention: cuTensorMapEncodeTiled (output) failed (CUresult %d)", (int)r);
+      return TGB_ECUDA;
+    }
+  }
   static bool configured = false;
   if (!configured) {
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM_TOTAL));
@@ -1088,7 +1139,7 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   if (g_vit_attention_variant == 1)
     vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM_TOTAL, (cudaStream_t)stream>>>(map, p);
   else
-    vit_attention_pp_kernel<<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, p);
+    vit_attention_pp_kernel<<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, map_out, p);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }
