@@ -620,11 +620,26 @@ __device__ __forceinline__ uint32_t va_tile_off(int r, int chunk) {
   return (uint32_t)((chunk >> 3) * VA_KBLK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((((chunk & 7) ^ (r & 7))) << 4));
 }
 
-__device__ __forceinline__ void cls_row_item(const VitAttnParams& p, int w, uint32_t ph, uint32_t sK, uint32_t sV,
-                                             uint64_t* k_full, uint64_t* k_free, uint64_t* v_full, uint64_t* v_free,
-                                             float* sc_s, int lane) {   // the four barrier arguments are [2]: one per key block
-  // Loops are ROLLED (scores and probabilities go through the 272-entry shared array sc_s): the routine runs once per
-  // item on one warp, so straight-line code would be fetched cold every time.
+// mma without `volatile`: a pure function of its operands, so independent accumulator chains may be interleaved
+__device__ __forceinline__ void va_mma_16816_nv(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// The CLS query row of one item is split between two warps BY KEY BLOCK (warp BLK handles keys of block BLK and only
+// touches that block's K / V buffers, so each block is released to the TMA producer as early as possible); the two
+// partial results (own max m, row sum l, unnormalised O) are merged by the block-0 warp through `xch`.
+// sc_s: warp-private float[144] (scores, then bf16 probabilities over the same storage); xch: float[2][100].
+// Loops are rolled: the routine runs once per item per warp and straight-line code would be fetched cold every time.
+template <int BLK>
+__device__ __forceinline__ void cls_row_block(const VitAttnParams& p, int w, int i, uint32_t sK, uint32_t sV,
+                                              uint64_t* k_full, uint64_t* k_free, uint64_t* v_full, uint64_t* v_free,
+                                              float* sc_s, float* xch, int lane) {
+  constexpr int NT = BLK == 0 ? PP_KEYS0 / 16 : (272 - PP_KEYS0) / 16;     // 16-key tiles: 9 / 8
+  constexpr int KEY0 = BLK * PP_KEYS0;
+  constexpr int NVALID = BLK == 0 ? PP_KEYS0 : PP_VALID1;                  // 144 / 113
+  const uint32_t ph = i & 1;
   const int b = w / VA_H, h = w - b * VA_H;
   const long long row0 = (long long)b * VA_S;
   const int g = lane >> 2, t = lane & 3;
@@ -639,87 +654,107 @@ __device__ __forceinline__ void cls_row_item(const VitAttnParams& p, int w, uint
     }
   }
   const int lrow = lane & 7, lmat = lane >> 3;
-  mbar_wait(&k_full[0], ph);
-  mbar_wait(&k_full[1], ph);
-  // ---- S^T = K q^T, two 16-key tiles per iteration (16 of them; the 17th tile is peeled), scores of column 0 -> sc_s
-  auto qk_tile = [&](int mt, float (&c)[4]) {
-    const int key = mt * 16 + (lmat & 1) * 8 + lrow;            // matrices: (keys lo, d lo) (keys hi, d lo) (keys lo, d hi) (keys hi, d hi)
-    uint32_t a[6][4];
+  mbar_wait(&k_full[BLK], ph);
+  // ---- S^T = K q^T: two key tiles per iteration, two accumulators per tile (even / odd k-steps) = 4 independent chains
+  auto qk_pair = [&](int mt, bool second) {
+    uint32_t a0[6][4], a1[6][4];
+    const int key = KEY0 + mt * 16 + (lmat & 1) * 8 + lrow;     // matrices: (keys lo, d lo) (keys hi, d lo) (keys lo, d hi) (keys hi, d hi)
 #pragma unroll
-    for (int ks = 0; ks < 6; ++ks) va_ldsm_x4(sK + va_tile_off(key, 2 * ks + (lmat >> 1)), a[ks]);
-    c[0] = c[1] = c[2] = c[3] = 0.f;
+    for (int ks = 0; ks < 6; ++ks) va_ldsm_x4(sK + va_tile_off(key, 2 * ks + (lmat >> 1)), a0[ks]);
+    if (second) {
 #pragma unroll
-    for (int ks = 0; ks < 6; ++ks) va_mma_16816(c, a[ks], qb[ks][0], qb[ks][1]);
+      for (int ks = 0; ks < 6; ++ks) va_ldsm_x4(sK + va_tile_off(key + 16, 2 * ks + (lmat >> 1)), a1[ks]);
+    }
+    float c0e[4] = {0.f, 0.f, 0.f, 0.f}, c0o[4] = {0.f, 0.f, 0.f, 0.f}, c1e[4] = {0.f, 0.f, 0.f, 0.f}, c1o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 6; ks += 2) {
+      va_mma_16816_nv(c0e, a0[ks], qb[ks][0], qb[ks][1]);
+      va_mma_16816_nv(c0o, a0[ks + 1], qb[ks + 1][0], qb[ks + 1][1]);
+      if (second) {
+        va_mma_16816_nv(c1e, a1[ks], qb[ks][0], qb[ks][1]);
+        va_mma_16816_nv(c1o, a1[ks + 1], qb[ks + 1][0], qb[ks + 1][1]);
+      }
+    }
+    if (t == 0) {
+      sc_s[mt * 16 + g] = c0e[0] + c0o[0];
+      sc_s[mt * 16 + 8 + g] = c0e[2] + c0o[2];
+      if (second) {
+        sc_s[mt * 16 + 16 + g] = c1e[0] + c1o[0];
+        sc_s[mt * 16 + 24 + g] = c1e[2] + c1o[2];
+      }
+    }
   };
 #pragma unroll 1
-  for (int mt = 0; mt < 16; mt += 2) {
-    float c0[4], c1[4];
-    qk_tile(mt, c0);
-    qk_tile(mt + 1, c1);
-    if (t == 0) {
-      sc_s[mt * 16 + g] = c0[0]; sc_s[mt * 16 + 8 + g] = c0[2];
-      sc_s[mt * 16 + 16 + g] = c1[0]; sc_s[mt * 16 + 24 + g] = c1[2];
-    }
-  }
-  {
-    float c0[4];
-    qk_tile(16, c0);
-    if (t == 0) { sc_s[256 + g] = c0[0]; sc_s[264 + g] = c0[2]; }
-  }
+  for (int mt = 0; mt + 1 < NT; mt += 2) qk_pair(mt, true);
+  if (NT & 1) qk_pair(NT - 1, false);
   __syncwarp();
-  if (lane == 0) { mbar_arrive(&k_free[0]); mbar_arrive(&k_free[1]); }   // done reading K (second arrival: tcgen05.commit)
-  // ---- softmax over the 257 valid keys, 9 per lane (the last lane group only key 256)
-  float x[9];
+  if (lane == 0) mbar_arrive(&k_free[BLK]);                      // done reading this K block (second arrival: tcgen05.commit)
+  // ---- local softmax over this block's valid keys, 5 per lane
+  float x[5];
   float m = -INFINITY;
 #pragma unroll
-  for (int it = 0; it < 9; ++it) {
+  for (int it = 0; it < 5; ++it) {
     const int j = it * 32 + lane;
-    x[it] = (j < VA_S) ? sc_s[j] * p.scale_log2 : -INFINITY;
+    x[it] = (j < NVALID) ? sc_s[j] * p.scale_log2 : -INFINITY;
     m = fmaxf(m, x[it]);
   }
   m = warp_max(m);
   float l = 0.f;
-  __nv_bfloat16* p_s = reinterpret_cast<__nv_bfloat16*>(sc_s);   // probabilities as bf16 [272] over the same storage
-  float pr[9];
 #pragma unroll
-  for (int it = 0; it < 9; ++it) {
-    pr[it] = (it * 32 + lane < 272) ? ex2_approx(x[it] - m) : 0.f;      // exp2(-inf) = 0 for the masked keys
-    l += pr[it];
+  for (int it = 0; it < 5; ++it) {
+    x[it] = ex2_approx(x[it] - m);                               // exp2(-inf) = 0 for masked keys
+    l += x[it];
   }
   l = warp_sum(l);
   __syncwarp();                                                  // every lane has read its scores before p overwrites them
+  __nv_bfloat16* p_s = reinterpret_cast<__nv_bfloat16*>(sc_s);
 #pragma unroll
-  for (int it = 0; it < 9; ++it)
-    if (it * 32 + lane < 272) p_s[it * 32 + lane] = __float2bfloat16(pr[it]);
+  for (int it = 0; it < 5; ++it)
+    if (it * 32 + lane < NT * 16) p_s[it * 32 + lane] = __float2bfloat16(x[it]);
   __syncwarp();
-  mbar_wait(&v_full[0], ph);
-  mbar_wait(&v_full[1], ph);
-  // ---- O^T = V^T p
+  mbar_wait(&v_full[BLK], ph);
+  // ---- O^T = V^T p over this block's keys
   float o[6][4];
 #pragma unroll
   for (int mt = 0; mt < 6; ++mt) { o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f; }
   const uint32_t* p32 = reinterpret_cast<const uint32_t*>(p_s);
 #pragma unroll 1
-  for (int kk = 0; kk < 17; ++kk) {
+  for (int kk = 0; kk < NT; ++kk) {
     // B fragment of p for keys [16kk, 16kk+16): b0 = keys (2t, 2t+1), b1 = keys (8+2t, 9+2t), column n = g
     const uint32_t b0 = (g == 0) ? p32[kk * 8 + t] : 0u;
     const uint32_t b1 = (g == 0) ? p32[kk * 8 + 4 + t] : 0u;
-    const int key = kk * 16 + (lmat >> 1) * 8 + lrow;            // matrices: (keys lo, d lo) (keys lo, d hi) (keys hi, d lo) (keys hi, d hi)
+    const int key = KEY0 + kk * 16 + (lmat >> 1) * 8 + lrow;     // matrices: (keys lo, d lo) (keys lo, d hi) (keys hi, d lo) (keys hi, d hi)
     uint32_t a[6][4];
 #pragma unroll
     for (int mt = 0; mt < 6; ++mt) va_ldsm_x4_t(sV + va_tile_off(key, 2 * mt + (lmat & 1)), a[mt]);
 #pragma unroll
-    for (int mt = 0; mt < 6; ++mt) va_mma_16816(o[mt], a[mt], b0, b1);
+    for (int mt = 0; mt < 6; ++mt) va_mma_16816_nv(o[mt], a[mt], b0, b1);
   }
   __syncwarp();
-  if (lane == 0) { mbar_arrive(&v_free[0]); mbar_arrive(&v_free[1]); }   // done reading V
-  if (t == 0) {
-    const float inv = 1.f / l;
-    __nv_bfloat16* dst = p.out + row0 * p.ld_out + h * VA_D;
+  if (lane == 0) mbar_arrive(&v_free[BLK]);                      // done reading this V block
+  // ---- merge: block-1 warp publishes (O, m, l); block-0 warp combines and stores
+  float* xb = xch + (i & 1) * 100;
+  if (BLK == 1) {
+    if (t == 0) {
 #pragma unroll
-    for (int mt = 0; mt < 6; ++mt) {
-      dst[mt * 16 + g] = __float2bfloat16(o[mt][0] * inv);
-      if (mt < 5) dst[mt * 16 + 8 + g] = __float2bfloat16(o[mt][2] * inv);
+      for (int mt = 0; mt < 6; ++mt) { xb[mt * 16 + g] = o[mt][0]; xb[mt * 16 + 8 + g] = o[mt][2]; }
+    }
+    if (lane == 0) { xb[96] = m; xb[97] = l; }
+    __syncwarp();
+    named_bar_sync(3, 64);
+  } else {
+    named_bar_sync(3, 64);
+    const float m1 = xb[96], l1 = xb[97];
+    const float mm = fmaxf(m, m1);
+    const float f0 = ex2_approx(m - mm), f1 = ex2_approx(m1 - mm);
+    const float inv = 1.f / (l * f0 + l1 * f1);
+    if (t == 0) {
+      __nv_bfloat16* dst = p.out + row0 * p.ld_out + h * VA_D;
+#pragma unroll
+      for (int mt = 0; mt < 6; ++mt) {
+        dst[mt * 16 + g] = __float2bfloat16((o[mt][0] * f0 + xb[mt * 16 + g] * f1) * inv);
+        if (mt < 5) dst[mt * 16 + 8 + g] = __float2bfloat16((o[mt][2] * f0 + xb[mt * 16 + 8 + g] * f1) * inv);
+      }
     }
   }
   __syncwarp();
@@ -895,23 +930,17 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
     }
     __syncwarp();
   } else if (warp < 4) {
-    // ================================================================ CLS query rows: warp 2 even items, warp 3 odd items
+    // ================================================================ CLS query row: warp 2 key block 0, warp 3 key block 1
     const uint32_t sK32 = smem_u32(sK), sV32 = smem_u32(sV);
+    float* sc_s = cls_scores + (warp - 2) * 144;
+    float* xch = cls_scores + 2 * 144;
     TRACE_DECL
     int i = 0;
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
-      if ((i & 1) == (warp - 2)) {
-        if (lane == 0) TRACE(warp, i * 100 + 30);
-        cls_row_item(p, w, i & 1, sK32, sV32, k_full, k_free, v_full, v_free, cls_scores + (warp - 2) * 272, lane);
-        if (lane == 0) TRACE(warp, i * 100 + 31);
-      } else {
-        // keep in step with the barrier phases of the items the other warp handles (a parity wait is only
-        // meaningful for the current or the previous phase)
-        mbar_wait(&k_full[0], i & 1);
-        mbar_wait(&k_full[1], i & 1);
-        mbar_wait(&v_full[0], i & 1);
-        mbar_wait(&v_full[1], i & 1);
-      }
+      if (lane == 0) TRACE(warp, i * 100 + 30);
+      if (warp == 2) cls_row_block<0>(p, w, i, sK32, sV32, k_full, k_free, v_full, v_free, sc_s, xch, lane);
+      else cls_row_block<1>(p, w, i, sK32, sV32, k_full, k_free, v_full, v_free, sc_s, xch, lane);
+      if (lane == 0) TRACE(warp, i * 100 + 31);
     }
   } else {
     // ================================================================ softmax warpgroups: one thread per query row
