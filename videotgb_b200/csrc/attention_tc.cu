@@ -780,7 +780,8 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
   uint64_t* o_full = bars + 16;    // [2] one completion per item
   uint64_t* o_free = bars + 18;    // [2]
   uint64_t* stage_free = bars + 20; // the output staging tile has been read by its TMA store (one completion per use)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* stage_ready = bars + 21; // ... has been written by a softmax warpgroup (128 arrivals per use)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   float* cls_scores = reinterpret_cast<float*>(smem + PP_SMEM_CLS);
   uint8_t* stage = smem + PP_SMEM_STAGE;
 
@@ -792,6 +793,7 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
     tma_prefetch_desc(&tmap128);
     tma_prefetch_desc(&tmap_out);
     mbar_init(stage_free, 1);
+    mbar_init(stage_ready, 128);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1); mbar_init(&q_free[t], 1);
       mbar_init(&k_full[t], 1); mbar_init(&k_free[t], 2);      // tcgen05.commit + the CLS warp of the item
@@ -812,6 +814,20 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
     // Loads are issued in the order the previous item releases their buffers: K0, Q0, V0, K1, Q1, V1.
     if (lane == 0) {
       TRACE_DECL
+      // Output tiles: a softmax warpgroup stages its bf16 [128][88] tile in shared memory (use n = 2*item + tile of the
+      // single staging buffer); this thread turns it into one asynchronous bulk tensor store and hands the buffer back.
+      // The stores sit at points of the load schedule where this thread has slack.
+      auto store_tile = [&](int ws, int is, int t) {
+        const int use = 2 * is + t;
+        mbar_wait(stage_ready, use & 1);
+        const int bs = ws / VA_H, hs = ws - bs * VA_H;
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stage)), "r"(0), "r"(hs),
+                       "r"(bs * VA_S + 1 + t * 128) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(stage_free);
+      };
       int i = 0;
       for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
         const int b = w / VA_H, h = w - b * VA_H;
@@ -843,10 +859,18 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         TRACE(0, i * 100 + 5);                                   // K block 1 load issued
         load_kv(sK, &k_full[1], 1, VA_H + h);
         load_q(1);
+        if (i > 0) store_tile(w - (int)gridDim.x, i - 1, 0);     // previous item's tile 0 (staged around now)
         mbar_wait(&v_free[1], ph ^ 1);
         TRACE(0, i * 100 + 6);                                   // V block 1 load issued
         load_kv(sV, &v_full[1], 1, 2 * VA_H + h);
+        if (i > 0) store_tile(w - (int)gridDim.x, i - 1, 1);
       }
+      if (i > 0) {                                               // the last item's tiles
+        const int wl = blockIdx.x + (i - 1) * (int)gridDim.x;
+        store_tile(wl, i - 1, 0);
+        store_tile(wl, i - 1, 1);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store has fully completed before the CTA may exit
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -962,16 +986,9 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
 #else
 #define STRACE(tag) do { } while (0)
 #endif
-    bool store_pending = false;                  // (thread 0 of the warpgroup) a TMA store of the staging tile is in flight
     int i = 0;
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
-      const int b = w / VA_H, h = w - b * VA_H;
       float mx, l;
-      if (store_pending) {                       // hand the staging tile on while this warpgroup would wait for S anyway
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(stage_free);
-        store_pending = false;
-      }
       {
         // ------------------------------------------------------------ key block 0: keys [0,144), all valid
         mbar_wait(&s_full[t], 0);
@@ -1023,7 +1040,8 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         // ------------------------------------------------------------ epilogue: O_t / l -> bf16 -> staging tile -> TMA store
         // Per-row 16-byte global stores touch 32 cache lines per instruction and kept the LSU (and with it the tensor
         // memory traffic of the other warpgroup) busy for ~3k cycles; instead each thread writes its row into a dense
-        // [128][88] shared tile (conflict-free: 176-byte rows) and one thread issues an asynchronous bulk tensor store.
+        // [128][88] shared tile (conflict-free: 176-byte rows) and the TMA producer thread issues an asynchronous bulk
+        // tensor store (waiting for the store to drain inside this warpgroup would sit on the critical chain).
         const float inv = 1.f / l;
         mbar_wait(&o_full[t], i & 1);
         STRACE(i * 100 + 60);                                    // O_t complete
@@ -1049,20 +1067,9 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
           srow[c] = v;
         }
         fence_proxy_async();                                     // generic-proxy writes -> visible to the TMA (async proxy)
-        named_bar_sync(1 + t, 128);
-        if (quarter == 0 && lane == 0) {
-          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stage)), "r"(0), "r"(h),
-                         "r"(b * VA_S + 1 + t * 128) : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          store_pending = true;
-        }
+        mbar_arrive(stage_ready);                                // the TMA producer thread issues the bulk store
         STRACE(i * 100 + 62);                                    // stores issued
       }
-    }
-    if (store_pending) {
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the store has fully completed before the CTA may exit
-      mbar_arrive(stage_free);
     }
   }
 
