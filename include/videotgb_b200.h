@@ -51,6 +51,14 @@ TGB_API int tgb_sm_count(void);
 TGB_API int tgb_normalize_frames_u8(const uint8_t* frames_thwc, float* out_tchw, int T, int H, int W,
                             const float* mean3_host, const float* std3_host, tgb_stream_t stream);
 
+/* ---------------------------------------------------------------- N3  resize of decoded frames -------
+ * ResizeVideo -> ToUint8 -> ToTHWC (src/gadgets/functional_video.py:33-40, src/gadgets/transforms.py:33-57,213-238;
+ * composed at eval/utils/builder_utils.py:117-124): bilinear, align_corners=False, no antialias, to S x S regardless of
+ * the aspect ratio, then truncation to uint8.  u8 [T,H0,W0,3] (decoded RGB) -> u8 [T,S,S,3], bit-exact with
+ * F.interpolate's CPU arithmetic followed by .to(torch.uint8).  S % 4 == 0.                                 */
+TGB_API int tgb_resize_bilinear_u8(const uint8_t* frames_thwc, uint8_t* out_thwc, int T, int H0, int W0, int S,
+                           tgb_stream_t stream);
+
 /* ---------------------------------------------------------------- A7  Gumbel span draw ----------------
  * src/models/LSTP_SF_blip2_module.py:424-428: F.gumbel_softmax(cat(start,end), tau, dim=1).argmax(dim=1)
  * with the Gumbel noise made an explicit input.  logits, gumbel: f32 [R, L] (R = 2B rows).  index: i64 [R].
@@ -182,6 +190,17 @@ TGB_API int tgb_cast_f32_bf16(const float* x, int64_t ldx, void* out, int64_t ld
 /* out f32 [G, R, N] -> mean over groups of `width` consecutive leading rows: in [G*width, R*N] -> [G, R*N]
  * (eval/utils/model.py:186-190 mean pooling of a video's frames) */
 TGB_API int tgb_group_mean_f32(const float* x, float* out, int G, int width, int64_t inner, tgb_stream_t stream);
+
+/* ---------------------------------------------------------------- N4  LLM hand-off --------------------
+ * src/models/LSTP_SF_blip2_module.py:482-495: inputs_embeds = cat([language_model_inputs, embed(question)], 1),
+ * attention_mask = cat([ones, question_attention_mask], 1).  visual f32 [B,Nv,H] (the projected query tokens),
+ * table f32 [vocab,H] (the unchanged LLM's input embedding), ids / qmask i64 [B,Tq] ->
+ * embeds f32 [B,Nv+Tq,H], mask i64 [B,Nv+Tq].  Byte copies (bit-exact).  H % 4 == 0.                        */
+TGB_API int tgb_llm_inputs_f32(const float* visual, const float* table, const int64_t* ids, const int64_t* qmask,
+                               int64_t vocab, int B, int Nv, int Tq, int H, float* embeds, int64_t* mask,
+                               tgb_stream_t stream);
+/* :503-504  outputs[outputs == from] = to, in place on i64 [n] (generated id 0 -> 2 for LLaMA tokenizers). */
+TGB_API int tgb_replace_ids(int64_t* ids, int64_t n, int64_t from, int64_t to, tgb_stream_t stream);
 
 #ifdef __cplusplus
 }

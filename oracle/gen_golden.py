@@ -9,6 +9,7 @@ What it pins:
   pseudo_span_kat.json -- N2: the monotone-stack pseudo-label statements (:193-224), the span cross-entropy
                           statements (:241-253) and rouge_n (my_metrics.py:131-179), executed from the reference source.
   gumbel.npz           -- A7: F.gumbel_softmax(...).argmax with a fixed torch seed, plus the explicit noise.
+  resize.npz           -- N3: the reference ResizeVideo/ToUint8/ToTHWC(/ToTensorVideo/NormalizeVideo) chain on decoded frames.
   transform.npz        -- A0: reference ToTensorVideo/NormalizeVideo on random u8 frames.
   vit_small.npz ...    -- A10-A16, A1-A6: the reference classes (through reference_shim) loaded with the
                           seeded synthetic state dicts, fp32, small inputs.  Outputs stored as fp16-safe fp32
@@ -196,6 +197,23 @@ def gen_transform():
                         clip_u8=chain.contiguous().numpy())
 
 
+def gen_resize():
+    """N3: the reference transform chain on decoded (integer-valued) frames, as eval/utils/builder_utils.py:88-107,117-124
+    feeds it: u8 [T,H,W,3] -> permute(3,0,1,2).float() -> ResizeVideo -> ToUint8 -> ToTHWC (-> ToTensorVideo -> NormalizeVideo)."""
+    from src.gadgets import transforms as T
+    rng = np.random.default_rng(21)
+    out = {}
+    for tag, (t, h, w, s) in dict(down=(2, 45, 80, 32), up=(2, 20, 28, 32), mixed=(1, 64, 24, 32), same=(1, 32, 32, 32)).items():
+        u8 = rng.integers(0, 256, size=(t, h, w, 3), dtype=np.uint8)
+        u8[0, : h // 2] = 200                                    # flat region: truncation is sensitive to the last fp32 bit
+        clip = torch.from_numpy(u8).permute(3, 0, 1, 2).float()
+        r = T.ToTHWC()(T.ToUint8()(T.ResizeVideo(s)(clip))).contiguous()
+        full = T.NormalizeVideo((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))(
+            T.ToTensorVideo()(r)).permute(1, 0, 2, 3).contiguous()
+        out[f"{tag}_in"], out[f"{tag}_u8"], out[f"{tag}_norm"] = u8, r.numpy(), full.numpy()
+    np.savez_compressed(os.path.join(GOLD, "resize.npz"), **out)
+
+
 def _summ(t: torch.Tensor, stride: int = 7):
     t = t.detach().float()
     return dict(shape=list(t.shape), mean=float(t.mean()), std=float(t.std()), absmax=float(t.abs().max())), \
@@ -289,7 +307,7 @@ def gen_models():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     reference_shim.install()
-    which = sys.argv[1:] or ["select", "pseudo_span", "gumbel", "transform", "models"]
+    which = sys.argv[1:] or ["select", "pseudo_span", "gumbel", "transform", "resize", "models"]
     for w in which:
         globals()["gen_" + w]()
         print("generated", w)

@@ -118,6 +118,26 @@ def test_spans_to_indices_random_vs_oracle():
         assert torch.equal(got, want), (t, b, lof, n, k, mapping, inclusive, host_ints)
 
 
+# ------------------------------------------------------------------------------------------------ N3
+def test_resize_bilinear_bit_exact():
+    z = np.load(os.path.join(GOLDEN, "resize.npz"))
+    for tag in ("down", "up", "mixed", "same"):
+        got = ops.resize_bilinear_u8(torch.from_numpy(z[f"{tag}_in"]).to(DEV), 32).cpu().numpy()
+        assert np.array_equal(got, z[f"{tag}_u8"]), tag
+    rng = np.random.default_rng(4)
+    for t, h, w, s in [(3, 360, 640, 224), (2, 240, 320, 224), (1, 1080, 1920, 224), (2, 224, 224, 224), (2, 100, 60, 224),
+                       (1, 225, 223, 224), (4, 2, 2, 8)]:
+        u8 = rng.integers(0, 256, size=(t, h, w, 3), dtype=np.uint8)
+        u8[0, :, : w // 2] = 200                               # flat region
+        got = ops.resize_bilinear_u8(torch.from_numpy(u8).to(DEV), s).cpu().numpy()
+        assert np.array_equal(got, transform_ref.resize_bilinear_u8(u8, s)), (t, h, w, s)
+    # the whole reference chain behind the host mirror (decoded frames -> normalised fp32 TCHW)
+    from videotgb_b200.transforms import DataConfig, VideoNormalizer
+    vn = VideoNormalizer(DataConfig(target_size=32))
+    got = vn(torch.from_numpy(z["down_in"]).to(DEV)).cpu().numpy()
+    assert np.array_equal(got, z["down_norm"])
+
+
 # ------------------------------------------------------------------------------------------------ N2
 def test_pseudo_span_and_span_ce_reference_kat():
     with open(os.path.join(GOLDEN, "pseudo_span_kat.json")) as f:
@@ -372,3 +392,21 @@ def test_cast_and_group_mean():
     got = ops.group_mean(y.to(DEV), 3, 4).cpu()
     want = torch.stack([y[i * 4:(i + 1) * 4].mean(0) for i in range(3)])
     assert (got - want).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ N4
+def test_llm_handoff_bit_exact():
+    g = torch.Generator().manual_seed(12)
+    for b, nv, tq, h, vocab in [(3, 128, 16, 2048, 5000), (1, 32, 1, 4096, 100), (2, 0, 7, 64, 50), (2, 5, 0, 64, 50)]:
+        visual = torch.randn(b, nv, h, generator=g)
+        table = torch.randn(vocab, h, generator=g)
+        ids = torch.randint(0, vocab, (b, tq), generator=g)
+        qmask = (torch.rand(b, tq, generator=g) > 0.3).long()
+        want_e = torch.cat([visual, torch.nn.functional.embedding(ids, table)], dim=1)       # the reference expressions
+        want_m = torch.cat([torch.ones(visual.shape[:-1], dtype=torch.long), qmask], dim=1)
+        e, m = ops.llm_inputs(visual.to(DEV), table.to(DEV), ids.to(DEV), qmask.to(DEV))
+        assert torch.equal(e.cpu(), want_e) and torch.equal(m.cpu(), want_m), (b, nv, tq, h)
+    out = torch.randint(0, 4, (5, 33), generator=g)
+    want = out.clone()
+    want[want == 0] = 2
+    assert torch.equal(ops.replace_ids_(out.to(DEV), 0, 2).cpu(), want)

@@ -101,6 +101,23 @@ def test_transform_bit_exact():
     assert np.array_equal(transform_ref.resize_to_uint8(z["clip"], 16), z["clip_u8"])
 
 
+def test_resize_restatement_vs_reference_chain_and_live_interpolate():
+    z = np.load(os.path.join(GOLDEN, "resize.npz"))
+    for tag in ("down", "up", "mixed", "same"):
+        got = transform_ref.resize_bilinear_u8(z[f"{tag}_in"], 32)
+        assert np.array_equal(got, z[f"{tag}_u8"]), tag
+        assert np.array_equal(transform_ref.normalize_u8_thwc(got), z[f"{tag}_norm"]), tag
+    # the ATen arithmetic the restatement encodes, checked live at the sizes real videos come in
+    rng = np.random.default_rng(3)
+    for h, w in [(360, 640), (240, 320), (480, 854), (225, 223), (2, 2)]:
+        u8 = rng.integers(0, 256, size=(2, h, w, 3), dtype=np.uint8)
+        u8[0] = 200
+        clip = torch.from_numpy(u8).permute(3, 0, 1, 2).float()
+        want = torch.nn.functional.interpolate(clip, size=(224, 224), mode="bilinear", align_corners=False)
+        want = want.to(torch.uint8).permute(1, 2, 3, 0).numpy()
+        assert np.array_equal(transform_ref.resize_bilinear_u8(u8, 224), want), (h, w)
+
+
 def test_vit2_and_heads(gold):
     meta, arr = gold
     cfg = syn.VisionCfg(layers=2)

@@ -22,6 +22,7 @@ SIGNATURES = {
     "tgb_device_check": ([], c_int),
     "tgb_sm_count": ([], c_int),
     "tgb_normalize_frames_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
+    "tgb_resize_bilinear_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp], c_int),
     "tgb_gumbel_argmax": ([c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_vp], c_int),
     "tgb_spans_to_indices": ([c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "tgb_pseudo_span": ([c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp], c_int),
@@ -46,6 +47,8 @@ SIGNATURES = {
     "tgb_linear_small_f32": ([c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp], c_int),
     "tgb_vit_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_vp], c_int),
     "tgb_vit_attention_set_variant": ([c_int], c_int),
+    "tgb_llm_inputs_f32": ([c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
+    "tgb_replace_ids": ([c_vp, c_i64, c_i64, c_i64, c_vp], c_int),
     "tgb_cast_f32_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp], c_int),
     "tgb_group_mean_f32": ([c_vp, c_vp, c_int, c_int, c_i64, c_vp], c_int),
 }

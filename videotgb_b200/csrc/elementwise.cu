@@ -86,6 +86,42 @@ __global__ void __launch_bounds__(256) group_mean_kernel(const float* __restrict
   }
 }
 
+
+// N4: LLM hand-off.  One pass builds what the reference makes with an embedding lookup and two
+// torch.cat calls (src/models/LSTP_SF_blip2_module.py:482-495): inputs_embeds[b] = [visual tokens of video b | word
+// embeddings of its question], attention_mask[b] = [ones | question mask].  Pure copies (bit-exact); one warp per row.
+__global__ void __launch_bounds__(256) llm_inputs_kernel(const float* __restrict__ visual, const float* __restrict__ table,
+                                                         const long long* __restrict__ ids, const long long* __restrict__ qmask,
+                                                         long long vocab, int B, int Nv, int Tq, int nvec,
+                                                         float* __restrict__ embeds, long long* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * (Nv + Tq);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const long long b = r / (Nv + Tq);
+    const int j = static_cast<int>(r - b * (Nv + Tq));
+    const float4* src;
+    long long m = 1;
+    if (j < Nv) {
+      src = reinterpret_cast<const float4*>(visual) + (b * Nv + j) * nvec;
+    } else {
+      long long id = ids[b * Tq + (j - Nv)];
+      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);      // host validated; clamp keeps a bad id from faulting
+      src = reinterpret_cast<const float4*>(table) + id * nvec;
+      m = qmask[b * Tq + (j - Nv)];
+    }
+    float4* dst = reinterpret_cast<float4*>(embeds) + r * nvec;
+    for (int c = lane; c < nvec; c += 32) __stcs(dst + c, __ldg(src + c));
+    if (lane == 0) mask[r] = m;
+  }
+}
+
+// outputs[outputs == from] = to   (LSTP_SF_blip2_module.py:503-504: generated id 0 -> 2 for LLaMA tokenizers)
+__global__ void replace_ids_kernel(long long* __restrict__ ids, long long n, long long from, long long to) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (ids[i] == from) ids[i] = to;
+}
+
 }  // namespace tgb
 
 using namespace tgb;
@@ -146,6 +182,38 @@ extern "C" int tgb_group_mean_f32(const float* x, float* out, int G, int width, 
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   group_mean_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, G, width, inner);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
+extern "C" int tgb_llm_inputs_f32(const float* visual, const float* table, const int64_t* ids, const int64_t* qmask,
+                                  int64_t vocab, int B, int Nv, int Tq, int H, float* embeds, int64_t* mask,
+                                  tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(visual && table && ids && qmask && embeds && mask, "llm_inputs: null pointer");
+  TGB_CHECK_ARG(B >= 0 && Nv >= 0 && Tq >= 0 && H > 0 && H % 4 == 0 && vocab > 0, "llm_inputs: bad shape B=%d Nv=%d Tq=%d H=%d", B, Nv, Tq, H);
+  TGB_CHECK_ARG(((uintptr_t)visual % 16) == 0 && ((uintptr_t)table % 16) == 0 && ((uintptr_t)embeds % 16) == 0, "llm_inputs: misaligned");
+  const long long rows = (long long)B * (Nv + Tq);
+  if (rows == 0) return TGB_OK;
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  llm_inputs_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(visual, table, (const long long*)ids, (const long long*)qmask,
+                                                                   vocab, B, Nv, Tq, H / 4, embeds, (long long*)mask);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
+extern "C" int tgb_replace_ids(int64_t* ids, int64_t n, int64_t from, int64_t to, tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(ids && n >= 0, "replace_ids: bad arguments");
+  if (n == 0) return TGB_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  replace_ids_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((long long*)ids, n, from, to);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

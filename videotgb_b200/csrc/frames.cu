@@ -266,6 +266,61 @@ __global__ void __launch_bounds__(128) patchify_u8_pair_kernel(const uint8_t* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// N3: ResizeVideo -> ToUint8 on decoded frames.  u8 [T,H0,W0,3] -> u8 [T,S,S,3], bilinear with
+// align_corners=False, no antialias, non-aspect-preserving (src/gadgets/functional_video.py:33-40), then truncation to
+// uint8 (transforms.py:213-220).  Truncation makes flat regions sensitive to the last fp32 bit (200*w0 + 200*w1 may
+// round to 199.99998), so the kernel follows ATen's CPU arithmetic operation for operation -- source index through one
+// fma, horizontal pass first, each pass fma(x0, w0, round(x1*w1)) -- all with explicit _rn intrinsics.
+// One thread = 4 consecutive output pixels of one row (12 output bytes = three aligned words).
+// ---------------------------------------------------------------------------------------------------------
+struct BilinearTap { int i0, i1; float w0, w1; };
+
+__device__ __forceinline__ BilinearTap bilinear_tap(int o, int in_size, int out_size, float scale) {
+  BilinearTap t;
+  if (in_size == out_size) { t.i0 = t.i1 = o; t.w0 = 1.f; t.w1 = 0.f; return t; }
+  float real = __fmaf_rn(scale, __fadd_rn((float)o, 0.5f), -0.5f);
+  real = real < 0.f ? 0.f : real;
+  int i0 = (int)real;                                 // real >= 0: truncation == floor
+  i0 = i0 < in_size - 1 ? i0 : in_size - 1;
+  float l1 = __fsub_rn(real, (float)i0);
+  l1 = fminf(fmaxf(l1, 0.f), 1.f);
+  t.i0 = i0;
+  t.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  t.w1 = l1;
+  t.w0 = __fsub_rn(1.f, l1);
+  return t;
+}
+
+__global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                 int H0, int W0, int S, float scale_h, float scale_w) {
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x;       // quad of output columns
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int t = blockIdx.z;
+  if (xq * 4 >= S || y >= S) return;
+  const BilinearTap ty = bilinear_tap(y, H0, S, scale_h);
+  const uint8_t* r0 = src + ((long long)t * H0 + ty.i0) * W0 * 3;
+  const uint8_t* r1 = src + ((long long)t * H0 + ty.i1) * W0 * 3;
+  uint8_t o[12];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const BilinearTap tx = bilinear_tap(xq * 4 + q, W0, S, scale_w);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float s00 = (float)__ldg(r0 + tx.i0 * 3 + c), s01 = (float)__ldg(r0 + tx.i1 * 3 + c);
+      const float s10 = (float)__ldg(r1 + tx.i0 * 3 + c), s11 = (float)__ldg(r1 + tx.i1 * 3 + c);
+      const float top = __fmaf_rn(s00, tx.w0, __fmul_rn(s01, tx.w1));
+      const float bot = __fmaf_rn(s10, tx.w0, __fmul_rn(s11, tx.w1));
+      const float v = __fmaf_rn(top, ty.w0, __fmul_rn(bot, ty.w1));
+      o[q * 3 + c] = (uint8_t)(int)v;                      // v in [0,255]: truncation toward zero like .to(torch.uint8)
+    }
+  }
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst + (((long long)t * S + y) * S + xq * 4) * 3);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    d[k] = (uint32_t)o[4 * k] | ((uint32_t)o[4 * k + 1] << 8) | ((uint32_t)o[4 * k + 2] << 16) | ((uint32_t)o[4 * k + 3] << 24);
+}
+
 // Gather: dst[(b*k + i)] = src[b, idx[b,i]] as 16-byte words; blockIdx.y = output frame, grid-stride over words.
 __global__ void __launch_bounds__(256) gather_frames_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx,
                                                             uint4* __restrict__ dst, int N, int k, long long words) {
@@ -464,5 +519,22 @@ extern "C" int tgb_fill_cls_rows(float* hidden, const float* cls, const float* p
 extern "C" int tgb_patchify_set_variant(int variant) {
   TGB_CHECK_ARG(variant == 0 || variant == 1, "patchify_set_variant: 0 (choose) or 1 (generic kernel)");
   g_patchify_variant = variant;
+  return TGB_OK;
+}
+
+extern "C" int tgb_resize_bilinear_u8(const uint8_t* frames_thwc, uint8_t* out_thwc, int T, int H0, int W0, int S,
+                                      tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(frames_thwc && out_thwc, "resize: null pointer");
+  TGB_CHECK_ARG(T >= 0 && H0 > 0 && W0 > 0 && S > 0 && S % 4 == 0, "resize: bad shape T=%d H0=%d W0=%d S=%d (S %% 4 == 0)", T, H0, W0, S);
+  TGB_CHECK_ARG(T <= 65535 && ((uintptr_t)out_thwc % 4) == 0, "resize: at most 65535 frames per call, 4-byte aligned output");
+  if (T == 0) return TGB_OK;
+  // ATen area_pixel_compute_scale (align_corners=False, no scale_factor): (float)input_size / output_size
+  volatile float sh = (float)H0 / (float)S, sw = (float)W0 / (float)S;
+  dim3 block(64, 4);
+  dim3 grid((S / 4 + 63) / 64, (S + 3) / 4, T);
+  resize_bilinear_u8_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(frames_thwc, out_thwc, H0, W0, S, sh, sw);
+  TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

@@ -15,6 +15,8 @@ Forward / inference only (eval-mode semantics: every dropout is the identity); t
 """
 from __future__ import annotations
 
+import os
+
 import math
 from types import SimpleNamespace
 from typing import Optional
@@ -144,7 +146,7 @@ def _model_output(cls_name: str, **kw):
 class Blip2VisionModel(_KernelModule):
     main_input_name = "pixel_values"
 
-    def __init__(self, config=None, max_frames_per_pass: int = 256):
+    def __init__(self, config=None, max_frames_per_pass: int = 512):
         super().__init__()
         self.config = config if config is not None else SimpleNamespace()
         d = self.hidden = _cfg(config, "hidden_size", 1408)
@@ -158,7 +160,7 @@ class Blip2VisionModel(_KernelModule):
         if self.head_dim * self.heads != d:
             raise ValueError(f"embed_dim must be divisible by num_heads (got `embed_dim`: {d} and `num_heads`: {self.heads}).")
         self.tokens = (self.image // self.patch) ** 2 + 1
-        self.max_frames_per_pass = max_frames_per_pass
+        self.max_frames_per_pass = int(os.environ.get("TGB_FRAMES_PER_PASS", max_frames_per_pass))   # tuning knob
         self.use_tc_attention = True
         self.embeddings = _Holder()
         self.embeddings.class_embedding = nn.Parameter(torch.randn(1, 1, d) * 0.02)

@@ -84,6 +84,19 @@ def normalize_frames_u8(frames_thwc: torch.Tensor, mean=CLIP_MEAN, std=CLIP_STD)
     return out
 
 
+def resize_bilinear_u8(frames_thwc: torch.Tensor, size: int) -> torch.Tensor:
+    """u8 [T,H0,W0,3] decoded frames -> u8 [T,size,size,3] (bilinear, align_corners=False, truncation)."""
+    f = _need(frames_thwc, torch.uint8, "frames")
+    if f.dim() != 4 or f.shape[3] != 3:
+        raise _lib.TgbError("frames must be [T,H0,W0,3]")
+    t, h0, w0, _ = f.shape
+    out = torch.empty((t, size, size, 3), dtype=torch.uint8, device=f.device)
+    for lo in range(0, t, 65535):
+        n = min(65535, t - lo)
+        check(_lib.load().tgb_resize_bilinear_u8(_p(f[lo:]), _p(out[lo:]), n, h0, w0, int(size), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ A7-A9
 def gumbel_argmax(logits: torch.Tensor, gumbel: torch.Tensor, tau: float = 0.5) -> torch.Tensor:
     lg = _need(logits, torch.float32, "logits")
@@ -389,3 +402,26 @@ def vit_attention(qkv: torch.Tensor, frames: int, scale: float, out: Optional[to
         e1.record()
         _PROFILE.append(("attention", (frames, 16, 257, 257, 88), e0, e1))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ N4
+def llm_inputs(visual: torch.Tensor, table: torch.Tensor, ids: torch.Tensor, qmask: torch.Tensor):
+    """visual f32 [B,Nv,H], table f32 [V,H], ids/qmask i64 [B,Tq] -> (inputs_embeds f32 [B,Nv+Tq,H], attention_mask i64)."""
+    v = _need(visual, torch.float32, "visual")
+    tb = _need(table, torch.float32, "table")
+    i = _need(ids, torch.int64, "ids")
+    qm = _need(qmask, torch.int64, "qmask")
+    if v.dim() != 3 or tb.dim() != 2 or tb.shape[1] != v.shape[2] or i.shape != qm.shape or i.dim() != 2 or i.shape[0] != v.shape[0]:
+        raise _lib.TgbError("visual [B,Nv,H], table [V,H], ids/qmask [B,Tq] expected")
+    b, nv, h = v.shape
+    tq = i.shape[1]
+    emb = torch.empty((b, nv + tq, h), dtype=torch.float32, device=v.device)
+    mask = torch.empty((b, nv + tq), dtype=torch.int64, device=v.device)
+    check(_lib.load().tgb_llm_inputs_f32(_p(v), _p(tb), _p(i), _p(qm), tb.shape[0], b, nv, tq, h, _p(emb), _p(mask), _stream()))
+    return emb, mask
+
+
+def replace_ids_(ids: torch.Tensor, src: int, dst: int) -> torch.Tensor:
+    i = _need(ids, torch.int64, "ids")
+    check(_lib.load().tgb_replace_ids(_p(i), i.numel(), int(src), int(dst), _stream()))
+    return ids

@@ -121,6 +121,22 @@ class VideoTGBEncoder(nn.Module):
             pooled = torch.cat(parts, 0)
         return m.language_projection(pooled)
 
+    def llm_inputs(self, language_model_inputs: torch.Tensor, batch, embedding_weight: torch.Tensor):
+        """SURVEY.md section 8f N4, LSTP_SF_blip2_module.py:482-495: `(inputs_embeds, attention_mask)` for the unchanged
+        language model's `generate`: visual tokens followed by the question's word embeddings
+        (`embedding_weight` = `language_model.get_input_embeddings().weight`)."""
+        if embedding_weight.dtype != torch.float32:
+            raise ValueError("the hand-off kernel copies fp32 embeddings (the reference keeps the LLM embedding in fp32)")
+        if int(batch["question"].min()) < 0 or int(batch["question"].max()) >= embedding_weight.shape[0]:
+            raise IndexError("index out of range in self")       # what nn.Embedding raises
+        return ops.llm_inputs(language_model_inputs.contiguous(), embedding_weight.contiguous(), batch["question"].contiguous(),
+                              batch["question_attention_mask"].to(torch.int64).contiguous())
+
+    @staticmethod
+    def fix_generated_ids(outputs: torch.Tensor, architecture: str = "LLaMAForCausalLM") -> torch.Tensor:
+        """LSTP_SF_blip2_module.py:503-504: `outputs[outputs==0] = 2` for LLaMA text configs (in place)."""
+        return ops.replace_ids_(outputs, 0, 2) if architecture == "LLaMAForCausalLM" else outputs
+
     def tokens_from_u8(self, sampled_u8: torch.Tensor, batch_size: int, batch=None, assemble: str = "concat"):
         """Same as `tokens` for u8 THWC frames: normalise (A0) is fused into the patchify kernel."""
         m = self.model

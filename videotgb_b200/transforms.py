@@ -2,7 +2,7 @@
 
 The reference composes ResizeVideo -> ToUint8 -> ToTHWC -> ToTensorVideo -> NormalizeVideo on the CPU dataloader
 (src/data/videoinstruct_datamodule.py:125-132, src/gadgets/transforms.py).  `VideoNormalizer` runs the
-ToTensorVideo+NormalizeVideo part (u8 THWC -> fp32 TCHW, bit-exact) on the GPU; `processor_name`, `nframe` and
+whole chain on the GPU (decoded u8 THWC at native resolution -> fp32 TCHW at target_size, bit-exact); `processor_name`, `nframe` and
 `target_size` keep their reference meaning (configs/data/videoinstruct.yaml:5-9).
 """
 from __future__ import annotations
@@ -29,10 +29,13 @@ class VideoNormalizer:
     def __init__(self, config: DataConfig = DataConfig()):
         self.config = config
 
+    def resize(self, frames_u8_thwc: torch.Tensor) -> torch.Tensor:
+        """ResizeVideo -> ToUint8 -> ToTHWC: decoded u8 [T,H0,W0,3] -> u8 [T,S,S,3], S = target_size."""
+        s = self.config.target_size
+        if frames_u8_thwc.shape[1] == s and frames_u8_thwc.shape[2] == s:
+            return frames_u8_thwc                        # the interpolation is the identity at equal sizes
+        return ops.resize_bilinear_u8(frames_u8_thwc.contiguous(), s)
+
     def __call__(self, frames_u8_thwc: torch.Tensor) -> torch.Tensor:
-        """u8 [T,H,W,3] on the GPU -> fp32 [T,3,H,W]."""
-        t, h, w, _ = frames_u8_thwc.shape
-        if h != self.config.target_size or w != self.config.target_size:
-            raise ValueError(f"frames must already be {self.config.target_size}x{self.config.target_size}; the bilinear "
-                             "ResizeVideo stage is a 'next' row (SURVEY.md section 8f N3)")
-        return ops.normalize_frames_u8(frames_u8_thwc, self.mean, self.std)
+        """Decoded u8 [T,H0,W0,3] on the GPU -> fp32 [T,3,S,S]: the whole reference transform chain."""
+        return ops.normalize_frames_u8(self.resize(frames_u8_thwc), self.mean, self.std)
