@@ -62,3 +62,49 @@ def shard_videos(num_videos: int, rank: int, world: int):
     per = (num_videos + world - 1) // world
     lo = min(num_videos, rank * per)
     return lo, min(num_videos, lo + per)
+
+
+# ------------------------------------------------------------------------------------------------ config 4
+# One long video whose candidate frames / flow are sharded BY FRAME (contiguous ranges, rank r owns frames
+# [r*T_local, (r+1)*T_local)): SURVEY.md section 8e.  Two exchange steps, both tiny next to the per-frame compute:
+#   1. all-gather of the per-frame flow embeddings [B, T_local, 768] fp32 (3 KiB per frame) -- after it every rank runs
+#      the small RoPE-BERT encoder replicated on identical inputs, so logits, the span draw (the Gumbel noise is
+#      broadcast from rank 0) and the selected indices are identical everywhere with no further communication;
+#   2. all-gather of the Q-Former tokens of the selected frames each rank owns, padded to `nframe` rows.
+def all_gather_frame_rows(y_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """[B, T_local, D] per rank (same T_local everywhere) -> [B, W*T_local, D] in global frame order."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return y_local
+    b, tl, d = y_local.shape
+    buf = torch.empty((world * b, tl, d), dtype=y_local.dtype, device=y_local.device)     # rank-major concatenation
+    dist.all_gather_into_tensor(buf, y_local.contiguous(), group=group)
+    return buf.view(world, b, tl, d).permute(1, 0, 2, 3).reshape(b, world * tl, d)
+
+
+def owned_selection(indices: torch.Tensor, rank: int, t_local: int):
+    """Sorted global frame indices [k] (replicated) -> (local indices this rank owns, position of the first one in the
+    selection, per-rank counts list).  Shards are contiguous, so each rank owns a contiguous run of the sorted list."""
+    idx = indices.reshape(-1).tolist()                     # one host sync per video (the reference syncs per comparison)
+    owner = [i // t_local for i in idx]
+    mine = [i - rank * t_local for i, o in zip(idx, owner) if o == rank]
+    first = next((p for p, o in enumerate(owner) if o == rank), len(idx))
+    world = max(owner) + 1 if owner else 1
+    counts = [sum(1 for o in owner if o == r) for r in range(world)]
+    return mine, first, counts
+
+
+def all_gather_selected_tokens(tokens_local: torch.Tensor, counts, nframe: int,
+                               group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """tokens_local [n_r, Q, D] (this rank's selected frames, in order; n_r = counts[rank]) -> [nframe, Q, D] on every
+    rank, ordered by global frame index.  Every rank contributes a zero-padded [nframe, Q, D] slab."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return tokens_local
+    q, d = tokens_local.shape[1:]
+    slab = torch.zeros((nframe, q, d), dtype=tokens_local.dtype, device=tokens_local.device)
+    slab[: tokens_local.shape[0]] = tokens_local
+    buf = torch.empty((world * nframe, q, d), dtype=slab.dtype, device=slab.device)
+    dist.all_gather_into_tensor(buf, slab, group=group)
+    counts = list(counts) + [0] * (world - len(counts))
+    return torch.cat([buf[r * nframe: r * nframe + counts[r]] for r in range(world) if counts[r] > 0], dim=0)

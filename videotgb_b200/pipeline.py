@@ -175,6 +175,51 @@ class VideoTGBEncoder(nn.Module):
         return out
 
     @torch.no_grad()
+    def encode_sharded_u8(self, batch, group=None, mode: str = "fusion", variant: str = "eval", gumbel=None, generator=None,
+                          return_aux: bool = False):
+        """BASELINE config 4: ONE long video whose candidates are sharded by frame over `group` (rank r holds frames and
+        flow [r*T_local, (r+1)*T_local) in `frames_u8` [1,T_local,H,W,3] and `of` [1,T_local,2,H,W]; `of_mask`,
+        `of_lengths`, the question and `nframe` describe the whole video).  Every rank returns the same
+        `language_model_inputs` [1, nframe*32, H_llm] the unsharded `encode_u8` produces."""
+        import torch.distributed as dist
+        from . import distributed as D
+        if self.instruct:
+            raise NotImplementedError("frame-sharded long videos are wired for the BLIP-2 Q-Former (config 4)")
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        nframe = batch["nframe"]
+        px = batch["frames_u8"]
+        if px.shape[0] != 1:
+            raise ValueError("encode_sharded_u8 handles one long video; shard whole videos with shard_videos() otherwise")
+        t_local = px.shape[1]
+        of_feat, of_logits = self.temporal_encoder(
+            encoder_embeds=batch["of"], attention_mask=batch["of_mask"], encoder_hidden_states=batch["sampler_question"],
+            encoder_attention_mask=batch.get("sampler_question_attention_mask"), mode=mode, flow_group=group)
+        start_logits, end_logits = of_logits.split(1, dim=-1)
+        if gumbel is None:                                  # identical noise everywhere: drawn on rank 0, broadcast
+            lg = torch.cat([start_logits.reshape(1, -1), end_logits.reshape(1, -1)], 0)
+            gumbel = [selection.gumbel_noise_like(lg, generator) for _ in range(2)]
+            for g in gumbel:
+                dist.broadcast(g, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        cs, ce = selection.draw_spans(start_logits, end_logits, 2, 0.5, gumbel, None)
+        idx = selection.select_indices(cs, ce, batch["of_lengths"], t_local * world, nframe, variant)
+        mine, _, counts = D.owned_selection(idx[0], rank, t_local)
+        m = self.model
+        if mine:
+            local_idx = torch.tensor([mine], dtype=torch.int64, device=px.device)
+            sampled = ops.gather_frames(px.contiguous(), local_idx)
+            image_embeddings = m.vision_model.forward_u8(sampled)
+            query_tokens = m.query_tokens.expand(image_embeddings.shape[0], -1, -1)
+            query_output = m.qformer(query_embeds=query_tokens, encoder_hidden_states=image_embeddings)[0]
+        else:
+            query_output = torch.zeros((0, m.query_tokens.shape[1], self.model.qformer.hidden), dtype=torch.float32, device=px.device)
+        tokens = D.all_gather_selected_tokens(query_output.to(torch.float32).contiguous(), counts, nframe, group)
+        y = m.language_projection(tokens)
+        out = y.reshape(1, -1, y.shape[-1])
+        if return_aux:
+            return out, SimpleNamespace(indices=idx, start_logits=start_logits, end_logits=end_logits, counts=counts)
+        return out
+
+    @torch.no_grad()
     def encode_u8(self, batch, mode: str = "fusion", variant: str = "eval", assemble: str = "concat", gumbel=None,
                   generator=None, return_aux: bool = False):
         """Same path starting from DECODED u8 frames `frames_u8` [B,N,H,W,3] (what the dataloader holds before the

@@ -133,25 +133,34 @@ class RopeBertModel(_KernelModule):
         return pk
 
     # A1
-    def embed_flow(self, of: torch.Tensor, of_mask: torch.Tensor):
-        """-> (f32, bf16) [B, Lof+2, 768]  (TemporalOFEmbedding.forward, xropebert.py:103-129)."""
+    def embed_flow(self, of: torch.Tensor, of_mask: torch.Tensor, flow_group=None):
+        """-> (f32, bf16) [B, Lof+2, 768]  (TemporalOFEmbedding.forward, xropebert.py:103-129).
+
+        `flow_group`: the flow is sharded by frame over this process group (`of` holds this rank's contiguous slice,
+        `of_mask` covers the whole video); the per-frame embeddings are all-gathered before bos/eos/LayerNorm."""
         pk = self._pack()
         b, l, c, h, w = of.shape
         if c != 2 or h != w:
             raise ValueError("flow must be [B, L, 2, S, S]")
-        if l + 2 > pk.fpos.shape[0]:
-            raise ValueError(f"{l} flow frames need {l + 2} positions > max_position_embeddings={pk.fpos.shape[0]} "
+        l_total = of_mask.shape[1] - 2 if flow_group is not None else l
+        if l_total + 2 > pk.fpos.shape[0]:
+            raise ValueError(f"{l_total} flow frames need {l_total + 2} positions > max_position_embeddings={pk.fpos.shape[0]} "
                              "(the reference indexes out of range here; build the config with a larger table)")
         z = ops.of_patch_reduce(of.to(torch.float32).contiguous().view(b * l, c, h, w), pk.fcw, self.flow_patch)
-        y = ops.gemm(z, pk.conv_w, pk.conv_b, ops.EPI_F32)
+        y = ops.gemm(z, pk.conv_w, pk.conv_b, ops.EPI_F32).view(b, l, -1)
+        if flow_group is not None:
+            from .distributed import all_gather_frame_rows
+            y = all_gather_frame_rows(y, flow_group)
+            if y.shape[1] != l_total:
+                raise ValueError(f"sharded flow covers {y.shape[1]} frames but of_mask describes {l_total}")
         ends = (of_mask.sum(dim=1) - 1).to(torch.int32).contiguous()
-        return ops.sampler_assemble(y.view(b, l, -1), pk.bos, pk.eos, pk.fpos, ends, pk.te_ln[0], pk.te_ln[1], 1e-5)
+        return ops.sampler_assemble(y.contiguous(), pk.bos, pk.eos, pk.fpos, ends, pk.te_ln[0], pk.te_ln[1], 1e-5)
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, head_mask=None, inputs_embeds=None,
                 encoder_embeds: Optional[torch.Tensor] = None, encoder_hidden_states: Optional[torch.Tensor] = None,
                 encoder_attention_mask: Optional[torch.Tensor] = None, past_key_values=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, return_dict=None, is_decoder=False,
-                mode: str = "multi_modal"):
+                mode: str = "multi_modal", flow_group=None):
         if input_ids is not None and inputs_embeds is not None:
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
         if encoder_embeds is None:
@@ -172,10 +181,14 @@ class RopeBertModel(_KernelModule):
         pk = self._pack()
         d, h, hd = self.hidden, self.heads, self.head_dim
         b, l = encoder_embeds.shape[:2]
+        if flow_group is not None:
+            if attention_mask is None:
+                raise ValueError("a frame-sharded flow needs the attention_mask of the whole video")
+            l = attention_mask.shape[1] - 2
         s = l + 2
         if attention_mask is None:
             attention_mask = torch.ones((b, s), dtype=torch.long, device=encoder_embeds.device)
-        x_f32, x_bf16 = self.embed_flow(encoder_embeds, attention_mask)
+        x_f32, x_bf16 = self.embed_flow(encoder_embeds, attention_mask, flow_group)
         x_f32, x_bf16 = x_f32.view(-1, d), x_bf16.view(-1, d)
         ids = encoder_hidden_states.to(torch.int64).contiguous()
         tq = ids.shape[1]
