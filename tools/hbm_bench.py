@@ -52,6 +52,10 @@ def main():
     ms = timeit(lambda: ops.patchify_u8(u8, 14, 592))
     ops.patchify_set_variant(0)
     report("patchify_kernel<u8> (generic fallback: residual-corrected normalise)", f * (150528 + 256 * 592 * 2), ms, f"{f} frames")
+    native = torch.randint(0, 256, (512, 360, 640, 3), dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: ops.resize_bilinear_u8(native, 224))
+    report("resize_bilinear_u8_kernel (360x640 -> 224x224, u8)", 512 * (360 * 640 * 3 + 150528), ms, "512 decoded frames")
+    del native
     px = torch.randn(1024, 3, 224, 224, device=dev)
     ms = timeit(lambda: ops.patchify(px, 14, 592))
     report("patchify_kernel<f32> (im2col -> bf16)", 1024 * (602112 + 256 * 592 * 2), ms, "1024 frames")

@@ -185,6 +185,8 @@ class VideoTGBEncoder(nn.Module):
         from . import distributed as D
         if self.instruct:
             raise NotImplementedError("frame-sharded long videos are wired for the BLIP-2 Q-Former (config 4)")
+        if group is None:
+            group = dist.group.WORLD
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         nframe = batch["nframe"]
         px = batch["frames_u8"]
@@ -199,7 +201,7 @@ class VideoTGBEncoder(nn.Module):
             lg = torch.cat([start_logits.reshape(1, -1), end_logits.reshape(1, -1)], 0)
             gumbel = [selection.gumbel_noise_like(lg, generator) for _ in range(2)]
             for g in gumbel:
-                dist.broadcast(g, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                dist.broadcast(g, src=dist.get_global_rank(group, 0), group=group)
         cs, ce = selection.draw_spans(start_logits, end_logits, 2, 0.5, gumbel, None)
         idx = selection.select_indices(cs, ce, batch["of_lengths"], t_local * world, nframe, variant)
         mine, _, counts = D.owned_selection(idx[0], rank, t_local)
