@@ -191,8 +191,9 @@ extern "C" int tgb_llm_inputs_f32(const float* visual, const float* table, const
                                   tgb_stream_t stream) {
   int st = check_device();
   if (st != TGB_OK) return st;
-  TGB_CHECK_ARG(visual && table && ids && qmask && embeds && mask, "llm_inputs: null pointer");
   TGB_CHECK_ARG(B >= 0 && Nv >= 0 && Tq >= 0 && H > 0 && H % 4 == 0 && vocab > 0, "llm_inputs: bad shape B=%d Nv=%d Tq=%d H=%d", B, Nv, Tq, H);
+  if ((long long)B * (Nv + Tq) == 0) return TGB_OK;
+  TGB_CHECK_ARG((visual || Nv == 0) && ((table && ids && qmask) || Tq == 0) && embeds && mask, "llm_inputs: null pointer");
   TGB_CHECK_ARG(((uintptr_t)visual % 16) == 0 && ((uintptr_t)table % 16) == 0 && ((uintptr_t)embeds % 16) == 0, "llm_inputs: misaligned");
   const long long rows = (long long)B * (Nv + Tq);
   if (rows == 0) return TGB_OK;
