@@ -126,7 +126,7 @@ def test_resize_bilinear_bit_exact():
         assert np.array_equal(got, z[f"{tag}_u8"]), tag
     rng = np.random.default_rng(4)
     for t, h, w, s in [(3, 360, 640, 224), (2, 240, 320, 224), (1, 1080, 1920, 224), (2, 224, 224, 224), (2, 100, 60, 224),
-                       (1, 225, 223, 224), (4, 2, 2, 8)]:
+                       (1, 225, 223, 224), (4, 2, 2, 8), (2, 481, 854, 224), (1, 2160, 3840, 224)]:
         u8 = rng.integers(0, 256, size=(t, h, w, 3), dtype=np.uint8)
         u8[0, :, : w // 2] = 200                               # flat region
         got = ops.resize_bilinear_u8(torch.from_numpy(u8).to(DEV), s).cpu().numpy()

@@ -307,8 +307,11 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* 
     const BilinearTap tx = bilinear_tap(xq * 4 + q, W0, S, scale_w);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float s00 = (float)__ldg(r0 + tx.i0 * 3 + c), s01 = (float)__ldg(r0 + tx.i1 * 3 + c);
-      const float s10 = (float)__ldg(r1 + tx.i0 * 3 + c), s11 = (float)__ldg(r1 + tx.i1 * 3 + c);
+      // byte -> float through the 2^23 mantissa trick (I2F would run on the quarter-rate XU pipe, which bound this kernel)
+      const float s00 = __uint_as_float(0x4B000000u | __ldg(r0 + tx.i0 * 3 + c)) - 8388608.0f;
+      const float s01 = __uint_as_float(0x4B000000u | __ldg(r0 + tx.i1 * 3 + c)) - 8388608.0f;
+      const float s10 = __uint_as_float(0x4B000000u | __ldg(r1 + tx.i0 * 3 + c)) - 8388608.0f;
+      const float s11 = __uint_as_float(0x4B000000u | __ldg(r1 + tx.i1 * 3 + c)) - 8388608.0f;
       const float top = __fmaf_rn(s00, tx.w0, __fmul_rn(s01, tx.w1));
       const float bot = __fmaf_rn(s10, tx.w0, __fmul_rn(s11, tx.w1));
       const float v = __fmaf_rn(top, ty.w0, __fmul_rn(bot, ty.w1));
@@ -532,6 +535,9 @@ extern "C" int tgb_resize_bilinear_u8(const uint8_t* frames_thwc, uint8_t* out_t
   if (T == 0) return TGB_OK;
   // ATen area_pixel_compute_scale (align_corners=False, no scale_factor): (float)input_size / output_size
   volatile float sh = (float)H0 / (float)S, sw = (float)W0 / (float)S;
+  // (A row-staged variant -- source rows copied to shared memory with 16-byte loads, taps precomputed per CTA -- was
+  //  measured slower, 2.2 vs 3.3 TB/s: the kernel is instruction-issue bound at ~42 instructions per output byte, not
+  //  load bound; profiles/r1_hbm_kernels.jsonl.)
   dim3 block(64, 4);
   dim3 grid((S / 4 + 63) / 64, (S + 3) / 4, T);
   resize_bilinear_u8_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(frames_thwc, out_thwc, H0, W0, S, sh, sw);
