@@ -202,6 +202,35 @@ TGB_API int tgb_llm_inputs_f32(const float* visual, const float* table, const in
 /* :503-504  outputs[outputs == from] = to, in place on i64 [n] (generated id 0 -> 2 for LLaMA tokenizers). */
 TGB_API int tgb_replace_ids(int64_t* ids, int64_t n, int64_t from, int64_t to, tgb_stream_t stream);
 
+/* ---------------------------------------------------------------- N1  RAFT optical-flow extractor -----
+ * src/models/components/xraft.py:102-158 and raft_utils/{extractor,corr,update}.py.  Activations are NHWC pixel rows
+ * [N*H*W, C]; every nn.Conv2d is tgb_im2col_nhwc_bf16 + tgb_gemm_bf16 (weights reordered to [Cout, (ky,kx,c)]).          */
+/* out bf16 [N*Ho*Wo, ldo]: column (ky*kw + kx)*C + c = x[(n, oy*sh-ph+ky, ox*sw-pw+kx), c] (0 outside), rest zero.
+ * x: bf16 pixel rows of pitch ldx >= C.  ldo % 8 == 0.                                                        */
+TGB_API int tgb_im2col_nhwc_bf16(const void* x, int64_t ldx, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                                 int ph, int pw, void* out, int64_t ldo, tgb_stream_t stream);
+/* nn.InstanceNorm2d(affine=False) (+ ReLU) over H*W per (n, c) (extractor.py:27-31,125-126): x f32 [N, HW, C].     */
+TGB_API int tgb_instance_norm_nhwc(const float* x, int N, int HW, int C, float eps, int relu, float* out_f32,
+                                   void* out_bf16, tgb_stream_t stream);
+/* out = act(scale * x (+ y)) on [M,N] with row pitches; act 0 identity / 1 relu / 2 sigmoid / 3 tanh.               */
+TGB_API int tgb_act_f32(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t M, int N, int mode, float scale,
+                        float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, tgb_stream_t stream);
+/* SepConvGRU gates (update.py:42-59); zr f32 [M, 2C] = [z_pre | r_pre].  rh = sigmoid(r_pre) * h (bf16, pitch ld);
+ * h <- (1 - sigmoid(z_pre)) h + sigmoid(z_pre) tanh(q_pre) in place (f32) plus a bf16 copy (pitch ld).              */
+TGB_API int tgb_gru_rh(const float* zr, const float* h, int64_t M, int C, void* rh_bf16, int64_t ld, tgb_stream_t stream);
+TGB_API int tgb_gru_update(const float* zr, const float* q, float* h, int64_t M, int C, void* h_bf16, int64_t ld,
+                           tgb_stream_t stream);
+/* CorrBlock (corr.py:12-60): 2x2 average pooling of [R, h, w] and the 4-level 9x9 bilinear lookup around grid + flow
+ * -> bf16 [N*h*w, ldo] (324 columns, zero padded), x taking the first window index as in the reference.            */
+TGB_API int tgb_corr_pool(const float* in, float* out, int64_t R, int h, int w, tgb_stream_t stream);
+TGB_API int tgb_corr_lookup(const float* l0, const float* l1, const float* l2, const float* l3, const float* flow, int N,
+                            int h, int w, void* out_bf16, int64_t ldo, tgb_stream_t stream);
+/* Convex 8x upsampling (xraft.py:88-99): mask f32 [N*h*w, ldm>=576], flow f32 [N*h*w, 2] -> f32 [N,2,8h,8w].        */
+TGB_API int tgb_raft_upsample(const float* mask, int64_t ldm, const float* flow, int N, int h, int w, float* out,
+                              tgb_stream_t stream);
+/* 2*(img/255) - 1 (xraft.py:106-107): f32 [N,C,H*W] -> bf16 pixel rows [N*H*W, ldo].                               */
+TGB_API int tgb_raft_prep_image(const float* img_nchw, int N, int C, int HW, void* out_bf16, int64_t ldo, tgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

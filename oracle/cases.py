@@ -32,3 +32,13 @@ def sampler_inputs():
     qmask = torch.ones(b, tq, dtype=torch.long)
     qmask[1, 6:] = 0
     return of, of_mask, of_len, qids, qmask
+
+
+def raft_pair(n: int = 2, h: int = 128, w: int = 160, seed: int = 31):
+    """A frame pair on the 0..255 scale: smooth random texture and a shifted, slightly noisy copy."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.nn.functional.interpolate(torch.rand(n, 3, h // 8, w // 8, generator=g), size=(h, w), mode="bicubic",
+                                           align_corners=False).clamp(0, 1)
+    img1 = base * 255.0
+    img2 = (torch.roll(base, shifts=(2, -3), dims=(2, 3)) + 0.02 * torch.randn(n, 3, h, w, generator=g)).clamp(0, 1) * 255.0
+    return img1.contiguous(), img2.contiguous()

@@ -10,6 +10,7 @@ What it pins:
                           statements (:241-253) and rouge_n (my_metrics.py:131-179), executed from the reference source.
   gumbel.npz           -- A7: F.gumbel_softmax(...).argmax with a fixed torch seed, plus the explicit noise.
   resize.npz           -- N3: the reference ResizeVideo/ToUint8/ToTHWC(/ToTensorVideo/NormalizeVideo) chain on decoded frames.
+  raft.npz             -- N1: the reference RAFT class on a seeded frame pair (flow_up subsampled, fnet feature sample).
   transform.npz        -- A0: reference ToTensorVideo/NormalizeVideo on random u8 frames.
   vit_small.npz ...    -- A10-A16, A1-A6: the reference classes (through reference_shim) loaded with the
                           seeded synthetic state dicts, fp32, small inputs.  Outputs stored as fp16-safe fp32
@@ -214,6 +215,23 @@ def gen_resize():
     np.savez_compressed(os.path.join(GOLD, "resize.npz"), **out)
 
 
+def gen_raft():
+    """N1: the reference RAFT class (xraft.py) with the seeded synthetic state dict, eval mode, 20 iterations."""
+    from src.models.components.xraft import RAFT
+    from oracle import cases
+    m = RAFT().eval()
+    sd = syn.raft_state_dict()
+    ref_sd = m.state_dict()
+    assert set(ref_sd) == set(sd) and all(ref_sd[k].shape == sd[k].shape for k in sd)
+    m.load_state_dict(sd)
+    img1, img2 = cases.raft_pair()
+    with torch.no_grad():
+        flow = m(img1, img2, iters=20, test_mode=True)
+        fmap1, _ = m.fnet([2 * (img1 / 255.0) - 1.0, 2 * (img2 / 255.0) - 1.0])
+    np.savez_compressed(os.path.join(GOLD, "raft.npz"), flow=flow[:, :, ::4, ::4].numpy(), flow_absmax=float(flow.abs().max()),
+                        flow_std=float(flow.std()), fmap1=fmap1[:, ::8, ::2, ::2].numpy())
+
+
 def _summ(t: torch.Tensor, stride: int = 7):
     t = t.detach().float()
     return dict(shape=list(t.shape), mean=float(t.mean()), std=float(t.std()), absmax=float(t.abs().max())), \
@@ -307,7 +325,7 @@ def gen_models():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     reference_shim.install()
-    which = sys.argv[1:] or ["select", "pseudo_span", "gumbel", "transform", "resize", "models"]
+    which = sys.argv[1:] or ["select", "pseudo_span", "gumbel", "transform", "resize", "raft", "models"]
     for w in which:
         globals()["gen_" + w]()
         print("generated", w)

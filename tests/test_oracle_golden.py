@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import cases, select_ref, torch_ref, transform_ref
+from oracle import cases, raft_ref, select_ref, torch_ref, transform_ref
 from videotgb_b200 import synthetic as syn
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -116,6 +116,17 @@ def test_resize_restatement_vs_reference_chain_and_live_interpolate():
         want = torch.nn.functional.interpolate(clip, size=(224, 224), mode="bilinear", align_corners=False)
         want = want.to(torch.uint8).permute(1, 2, 3, 0).numpy()
         assert np.array_equal(transform_ref.resize_bilinear_u8(u8, 224), want), (h, w)
+
+
+def test_raft_restatement_vs_reference_class():
+    z = np.load(os.path.join(GOLDEN, "raft.npz"))
+    sd = syn.raft_state_dict()
+    img1, img2 = cases.raft_pair()
+    with torch.no_grad():
+        flow, aux = raft_ref.raft_forward(sd, img1, img2, iters=20, return_aux=True)
+    assert abs(float(flow.abs().max()) - float(z["flow_absmax"])) <= 1e-3 * float(z["flow_absmax"])
+    assert np.abs(flow[:, :, ::4, ::4].numpy() - z["flow"]).max() <= 2e-3 * float(z["flow_absmax"])     # fp32 reassociation only
+    assert np.abs(aux["fmap1"][:, ::8, ::2, ::2].numpy() - z["fmap1"]).max() <= 1e-4 * np.abs(z["fmap1"]).max()
 
 
 def test_vit2_and_heads(gold):

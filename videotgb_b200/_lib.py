@@ -49,6 +49,15 @@ SIGNATURES = {
     "tgb_vit_attention_set_variant": ([c_int], c_int),
     "tgb_llm_inputs_f32": ([c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_replace_ids": ([c_vp, c_i64, c_i64, c_i64, c_vp], c_int),
+    "tgb_im2col_nhwc_bf16": ([c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp], c_int),
+    "tgb_instance_norm_nhwc": ([c_vp, c_int, c_int, c_int, c_f32, c_int, c_vp, c_vp, c_vp], c_int),
+    "tgb_act_f32": ([c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp], c_int),
+    "tgb_gru_rh": ([c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp], c_int),
+    "tgb_gru_update": ([c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp], c_int),
+    "tgb_corr_pool": ([c_vp, c_vp, c_i64, c_int, c_int, c_vp], c_int),
+    "tgb_corr_lookup": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_vp], c_int),
+    "tgb_raft_upsample": ([c_vp, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp], c_int),
+    "tgb_raft_prep_image": ([c_vp, c_int, c_int, c_int, c_vp, c_i64, c_vp], c_int),
     "tgb_cast_f32_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp], c_int),
     "tgb_group_mean_f32": ([c_vp, c_vp, c_int, c_int, c_i64, c_vp], c_int),
 }

@@ -425,3 +425,96 @@ def replace_ids_(ids: torch.Tensor, src: int, dst: int) -> torch.Tensor:
     i = _need(ids, torch.int64, "ids")
     check(_lib.load().tgb_replace_ids(_p(i), i.numel(), int(src), int(dst), _stream()))
     return ids
+
+
+# ------------------------------------------------------------------------------------------------ N1 (RAFT)
+def _ld(t: torch.Tensor) -> int:
+    """Row pitch (elements) of a 2-D view whose last dimension is contiguous."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.TgbError("expected a 2-D tensor with a contiguous last dimension")
+    return t.stride(0)
+
+
+def im2col_nhwc(x: torch.Tensor, n: int, h: int, w: int, c: int, kh: int, kw: int, stride=(1, 1), padding=(0, 0),
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 pixel rows [n*h*w, >=c] -> bf16 [n*ho*wo, roundup8(kh*kw*c)]."""
+    _need(x, torch.bfloat16, "x", contiguous=False)
+    ho = (h + 2 * padding[0] - kh) // stride[0] + 1
+    wo = (w + 2 * padding[1] - kw) // stride[1] + 1
+    kpad = (kh * kw * c + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((n * ho * wo, kpad), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().tgb_im2col_nhwc_bf16(_p(x), _ld(x), n, h, w, c, kh, kw, stride[0], stride[1], padding[0], padding[1],
+                                           _p(out), _ld(out), _stream()))
+    return out
+
+
+def instance_norm_nhwc(x: torch.Tensor, n: int, hw: int, relu: bool, want_f32: bool, want_bf16: bool, eps: float = 1e-5):
+    x = _need(x, torch.float32, "x")
+    c = x.shape[-1]
+    of = torch.empty_like(x) if want_f32 else None
+    ob = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    check(_lib.load().tgb_instance_norm_nhwc(_p(x), n, hw, c, float(eps), int(relu), _p(of), _p(ob), _stream()))
+    return of, ob
+
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = range(4)
+
+
+def act(x: torch.Tensor, mode: int, y: Optional[torch.Tensor] = None, scale: float = 1.0, out_f32: Optional[torch.Tensor] = None,
+        out_bf16: Optional[torch.Tensor] = None, want_f32: bool = False, want_bf16: bool = False):
+    """act(scale*x (+ y)) on 2-D fp32 views (row pitches allowed) -> (f32 or None, bf16 or None)."""
+    _need(x, torch.float32, "x", contiguous=False)
+    m, n = x.shape
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    if out_bf16 is None and want_bf16:
+        out_bf16 = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().tgb_act_f32(_p(x), _ld(x), _p(y), _ld(y) if y is not None else 0, m, n, int(mode), float(scale),
+                                  _p(out_f32), _ld(out_f32) if out_f32 is not None else 0,
+                                  _p(out_bf16), _ld(out_bf16) if out_bf16 is not None else 0, _stream()))
+    return out_f32, out_bf16
+
+
+def gru_rh(zr: torch.Tensor, h: torch.Tensor, rh_out: torch.Tensor) -> None:
+    _need(zr, torch.float32, "zr"); _need(h, torch.float32, "h"); _need(rh_out, torch.bfloat16, "rh", contiguous=False)
+    check(_lib.load().tgb_gru_rh(_p(zr), _p(h), h.shape[0], h.shape[1], _p(rh_out), _ld(rh_out), _stream()))
+
+
+def gru_update(zr: torch.Tensor, q: torch.Tensor, h: torch.Tensor, h_bf16_out: torch.Tensor) -> None:
+    _need(zr, torch.float32, "zr"); _need(q, torch.float32, "q"); _need(h, torch.float32, "h")
+    _need(h_bf16_out, torch.bfloat16, "h_bf16", contiguous=False)
+    check(_lib.load().tgb_gru_update(_p(zr), _p(q), _p(h), h.shape[0], h.shape[1], _p(h_bf16_out), _ld(h_bf16_out), _stream()))
+
+
+def corr_pool(x: torch.Tensor) -> torch.Tensor:
+    x = _need(x, torch.float32, "corr")
+    r, h, w = x.shape
+    out = torch.empty((r, h // 2, w // 2), dtype=torch.float32, device=x.device)
+    check(_lib.load().tgb_corr_pool(_p(x), _p(out), r, h, w, _stream()))
+    return out
+
+
+def corr_lookup(pyr, flow: torch.Tensor, n: int, h: int, w: int, out: torch.Tensor) -> torch.Tensor:
+    for t in pyr:
+        _need(t, torch.float32, "pyramid level")
+    _need(flow, torch.float32, "flow")
+    _need(out, torch.bfloat16, "out", contiguous=False)
+    check(_lib.load().tgb_corr_lookup(_p(pyr[0]), _p(pyr[1]), _p(pyr[2]), _p(pyr[3]), _p(flow), n, h, w, _p(out), _ld(out), _stream()))
+    return out
+
+
+def raft_upsample(mask: torch.Tensor, flow: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    _need(mask, torch.float32, "mask", contiguous=False)
+    _need(flow, torch.float32, "flow")
+    out = torch.empty((n, 2, 8 * h, 8 * w), dtype=torch.float32, device=mask.device)
+    check(_lib.load().tgb_raft_upsample(_p(mask), _ld(mask), _p(flow), n, h, w, _p(out), _stream()))
+    return out
+
+
+def raft_prep_image(img: torch.Tensor, ldo: int = 8) -> torch.Tensor:
+    img = _need(img, torch.float32, "image")
+    n, c, h, w = img.shape
+    out = torch.zeros((n * h * w, ldo), dtype=torch.bfloat16, device=img.device)
+    check(_lib.load().tgb_raft_prep_image(_p(img), n, c, h * w, _p(out), ldo, _stream()))
+    return out

@@ -205,3 +205,61 @@ def synthetic_flow(b: int, lof: int, size: int = 224, seed: int = 1234) -> torch
     of = torch.randn(b, lof, 2, size, size, generator=g)
     mag = of.pow(2).sum(2).sqrt().amax(dim=(1, 2, 3), keepdim=True).unsqueeze(2)
     return of / mag
+
+
+def raft_state_dict(seed: int = 1234, device="cpu") -> dict:
+    """`RAFT` keys (src/models/components/xraft.py:52-72; raft_utils/extractor.py, update.py): fnet (instance norm: no
+    parameters), cnet (batch norm with non-trivial running statistics), update_block.  Conv weights ~ N(0, 2/fan_out)
+    (the reference's kaiming_normal_ init) so that activations stay O(1) through 20 recurrent iterations."""
+    sd = _SD("raft.", seed, device)
+
+    def conv(name, cout, cin, kh, kw):
+        sd.w(name + ".weight", cout, cin, kh, kw, std=(2.0 / (cout * kh * kw)) ** 0.5)
+        sd.w(name + ".bias", cout, std=0.05)
+
+    def bn(name, c):
+        sd.w(name + ".weight", c, std=0.1, mean=1.0)
+        sd.w(name + ".bias", c, std=0.1)
+        sd.w(name + ".running_mean", c, std=0.1)
+        sd[name + ".running_var"] = _draw("raft." + name + ".running_var", (c,), seed, 0.2, 0.0, device).abs() + 0.6
+        sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.int64, device=device)
+
+    for enc, out_dim, batch_norm in (("fnet.", 256, False), ("cnet.", 256, True)):
+        conv(enc + "conv1", 64, 3, 7, 7)
+        if batch_norm:
+            bn(enc + "norm1", 64)
+        cin = 64
+        for li, dim in ((1, 64), (2, 96), (3, 128)):
+            for bi in (0, 1):
+                p = f"{enc}layer{li}.{bi}."
+                conv(p + "conv1", dim, cin if bi == 0 else dim, 3, 3)
+                conv(p + "conv2", dim, dim, 3, 3)
+                if batch_norm:
+                    bn(p + "norm1", dim)
+                    bn(p + "norm2", dim)
+                if bi == 0 and li > 1:
+                    conv(p + "downsample.0", dim, cin, 1, 1)
+                    if batch_norm:
+                        bn(p + "norm3", dim)
+                        for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+                            sd[p + "downsample.1." + k] = sd[p + "norm3." + k]       # the same module under two names
+            cin = dim
+        conv(enc + "conv2", out_dim, 128, 1, 1)
+    u = "update_block."
+    conv(u + "encoder.convc1", 256, 324, 1, 1)
+    conv(u + "encoder.convc2", 192, 256, 3, 3)
+    conv(u + "encoder.convf1", 128, 2, 7, 7)
+    conv(u + "encoder.convf2", 64, 128, 3, 3)
+    conv(u + "encoder.conv", 126, 256, 3, 3)
+    for g in "zrq":
+        conv(u + f"gru.conv{g}1", 128, 384, 1, 5)
+        conv(u + f"gru.conv{g}2", 128, 384, 5, 1)
+    conv(u + "flow_head.conv1", 256, 128, 3, 3)
+    conv(u + "flow_head.conv2", 2, 256, 3, 3)
+    # a random-init update operator is not contractive (a trained one is): damp the flow head so that 20 iterations stay
+    # in a regime where rounding differences do not grow chaotically (|flow| ~ 40 px on a 128x160 pair)
+    sd[u + "flow_head.conv2.weight"] = sd[u + "flow_head.conv2.weight"] * 0.01
+    sd[u + "flow_head.conv2.bias"] = sd[u + "flow_head.conv2.bias"] * 0.01
+    conv(u + "mask.0", 256, 128, 3, 3)
+    conv(u + "mask.2", 576, 256, 1, 1)
+    return dict(sd)
