@@ -123,8 +123,10 @@ TGB_API int tgb_fill_cls_rows(float* hidden, const float* cls, const float* pos0
  *   TGB_EPI_F32_RESID   out f32  = acc + bias + resid[m,n]   (resid f32, leading dim ldr; may alias out)
  *   TGB_EPI_F32_ROWBIAS out f32 row (m/period)*(period+skip)+skip+m%period = acc + rowbias[m%period, n]
  *                       (patch-embed: bias+position_embedding folded into rowbias, CLS row skipped)
+ *   TGB_EPI_BF16_RELU   out bf16 = relu(acc + bias)                               (RAFT convolutions)
  * N % 8 == 0.  bn: 0 = choose, else force the N tile (256/176/128/64).                                      */
-enum { TGB_EPI_BF16 = 0, TGB_EPI_BF16_GELU = 1, TGB_EPI_F32 = 2, TGB_EPI_F32_RESID = 3, TGB_EPI_F32_ROWBIAS = 4 };
+enum { TGB_EPI_BF16 = 0, TGB_EPI_BF16_GELU = 1, TGB_EPI_F32 = 2, TGB_EPI_F32_RESID = 3, TGB_EPI_F32_ROWBIAS = 4,
+       TGB_EPI_BF16_RELU = 5 };
 TGB_API int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
                   const float* bias, const float* resid, int64_t ldr, const float* rowbias, int period, int skip,
                   void* out, int64_t ldo, int bn, tgb_stream_t stream);
@@ -209,9 +211,10 @@ TGB_API int tgb_replace_ids(int64_t* ids, int64_t n, int64_t from, int64_t to, t
  * x: bf16 pixel rows of pitch ldx >= C.  ldo % 8 == 0.                                                        */
 TGB_API int tgb_im2col_nhwc_bf16(const void* x, int64_t ldx, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
                                  int ph, int pw, void* out, int64_t ldo, tgb_stream_t stream);
-/* nn.InstanceNorm2d(affine=False) (+ ReLU) over H*W per (n, c) (extractor.py:27-31,125-126): x f32 [N, HW, C].     */
-TGB_API int tgb_instance_norm_nhwc(const float* x, int N, int HW, int C, float eps, int relu, float* out_f32,
-                                   void* out_bf16, tgb_stream_t stream);
+/* nn.InstanceNorm2d(affine=False) (+ ReLU) over H*W per (n, c) (extractor.py:27-31,125-126): x f32 [N, HW, C].
+ * workspace: f32 [N * 16 * C * 2] scratch for the split statistics (the library never allocates).                   */
+TGB_API int tgb_instance_norm_nhwc(const float* x, int N, int HW, int C, float eps, int relu, float* workspace,
+                                   float* out_f32, void* out_bf16, tgb_stream_t stream);
 /* out = act(scale * x (+ y)) on [M,N] with row pitches; act 0 identity / 1 relu / 2 sigmoid / 3 tanh.               */
 TGB_API int tgb_act_f32(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t M, int N, int mode, float scale,
                         float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, tgb_stream_t stream);

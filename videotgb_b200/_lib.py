@@ -50,7 +50,7 @@ SIGNATURES = {
     "tgb_llm_inputs_f32": ([c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_replace_ids": ([c_vp, c_i64, c_i64, c_i64, c_vp], c_int),
     "tgb_im2col_nhwc_bf16": ([c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp], c_int),
-    "tgb_instance_norm_nhwc": ([c_vp, c_int, c_int, c_int, c_f32, c_int, c_vp, c_vp, c_vp], c_int),
+    "tgb_instance_norm_nhwc": ([c_vp, c_int, c_int, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_vp], c_int),
     "tgb_act_f32": ([c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp], c_int),
     "tgb_gru_rh": ([c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp], c_int),
     "tgb_gru_update": ([c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp], c_int),

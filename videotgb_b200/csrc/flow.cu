@@ -10,18 +10,51 @@ namespace tgb {
 // im2col: out[(n,oy,ox), (ky*kw + kx)*C + c] = x[(n, oy*sh - ph + ky, ox*sw - pw + kx), c]  (0 outside the image),
 // columns [kh*kw*C, ldo) zero.  VEC path: C % 8 == 0 -> one 16-byte copy per 8 channels.
 // ---------------------------------------------------------------------------------------------------------
-template <bool VEC>
+// Vector path: one thread owns (output pixel, 8-channel chunk) and walks the kh*kw taps, so the integer divisions are
+// paid once per thread instead of once per 16 bytes; consecutive lanes write consecutive 16-byte chunks of a tap segment.
+__global__ void __launch_bounds__(256) im2col_nhwc_vec_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int H, int W,
+                                                              int C, int kh, int kw, int sh, int sw, int ph, int pw, int Ho,
+                                                              int Wo, long long rows, __nv_bfloat16* __restrict__ out,
+                                                              long long ldo) {
+  const int c8 = C >> 3;
+  const int K = kh * kw * C;
+  const long long total = rows * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c8;
+    const int c = (int)(i - r * c8) << 3;
+    const int ox = (int)(r % Wo);
+    const long long t = r / Wo;
+    const int oy = (int)(t % Ho);
+    const long long n = t / Ho;
+    const int iy0 = oy * sh - ph, ix0 = ox * sw - pw;
+    __nv_bfloat16* o = out + r * ldo + c;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int iy = iy0 + ky;
+      const bool yok = iy >= 0 && iy < H;
+      const __nv_bfloat16* srow = x + ((n * H + iy) * W) * ldx + c;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int ix = ix0 + kx;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (yok && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const uint4*>(srow + (long long)ix * ldx));
+        *reinterpret_cast<uint4*>(o + (ky * kw + kx) * C) = v;
+      }
+    }
+    if (c == 0)                                                 // zero the K padding of this row (at most 7 columns... up to ldo)
+      for (int k = K; k < (int)ldo; ++k) out[r * ldo + k] = __float2bfloat16(0.f);
+  }
+}
+
+// Scalar path (C = 2 / 3 input channels): one thread per output element.
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int H, int W,
                                                           int C, int kh, int kw, int sh, int sw, int ph, int pw, int Ho,
                                                           int Wo, long long rows, __nv_bfloat16* __restrict__ out,
                                                           long long ldo) {
   const int K = kh * kw * C;
-  const int units = VEC ? (int)(ldo >> 3) : (int)ldo;            // work units per output row
+  const int units = (int)ldo;
   const long long total = rows * units;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / units;
-    const int u = (int)(i - r * units);
-    const int col = VEC ? u * 8 : u;
+    const int col = (int)(i - r * units);
     const int ox = (int)(r % Wo);
     const long long t = r / Wo;
     const int oy = (int)(t % Ho);
@@ -36,62 +69,89 @@ __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const __nv_bfloat16* _
       ix = ox * sw - pw + kx;
       ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
     }
-    const __nv_bfloat16* src = x + ((n * H + iy) * W + ix) * ldx + c;
-    if (VEC) {
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (ok) v = *reinterpret_cast<const uint4*>(src);
-      *reinterpret_cast<uint4*>(out + r * ldo + col) = v;
-    } else {
-      out[r * ldo + col] = ok ? *src : __float2bfloat16(0.f);
-    }
+    out[r * ldo + col] = ok ? x[((n * H + iy) * W + ix) * ldx + c] : __float2bfloat16(0.f);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // InstanceNorm2d (affine=False, eps) over H*W per (n, c) on fp32 NHWC, optional ReLU; fp32 and/or bf16 outputs.
-// One CTA per (n, 32-channel group): 8 pixel lanes x 32 channels; two passes (statistics, apply).
+// Two kernels: (1) per (n, 32-channel group, pixel split) a two-pass (mean, M2) over the split's pixels -> partials in
+// a caller-provided workspace; (2) a fully parallel apply that merges the partials (Chan's formula) per channel.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) instnorm_nhwc_kernel(const float* __restrict__ x, int HW, int C, float eps, int relu,
-                                                            float* __restrict__ of, __nv_bfloat16* __restrict__ ob) {
-  __shared__ float s_sum[8][32], s_sq[8][32], s_mean[32], s_rstd[32];
-  const int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
+constexpr int IN_SPLITS = 16;
+
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __restrict__ x, int HW, int C,
+                                                             float* __restrict__ ws) {      // ws [N][IN_SPLITS][C][2]
+  __shared__ float s_a[8][32], s_mean[32];
+  const int n = blockIdx.y, split = blockIdx.z, cl = threadIdx.x & 31, c = blockIdx.x * 32 + cl, pl = threadIdx.x >> 5;
+  const int per = (HW + IN_SPLITS - 1) / IN_SPLITS;
+  const int p0 = split * per, p1 = min(HW, p0 + per);
+  const int cnt = max(p1 - p0, 0);
   const bool cok = c < C;
   const float* xb = x + (long long)n * HW * C;
   float s = 0.f;
   if (cok)
-    for (int p = pl; p < HW; p += 8) s += xb[(long long)p * C + c];
-  s_sum[pl][threadIdx.x & 31] = s;
+    for (int p = p0 + pl; p < p1; p += 8) s += xb[(long long)p * C + c];
+  s_a[pl][cl] = s;
   __syncthreads();
   if (threadIdx.x < 32) {
     float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += s_sum[k][threadIdx.x];
-    s_mean[threadIdx.x] = t / (float)HW;
+    for (int k = 0; k < 8; ++k) t += s_a[k][threadIdx.x];
+    s_mean[threadIdx.x] = cnt > 0 ? t / (float)cnt : 0.f;
   }
   __syncthreads();
-  const float mean = s_mean[threadIdx.x & 31];
+  const float mean = s_mean[cl];
   float q = 0.f;
   if (cok)
-    for (int p = pl; p < HW; p += 8) {
+    for (int p = p0 + pl; p < p1; p += 8) {
       const float d = xb[(long long)p * C + c] - mean;
       q += d * d;
     }
-  s_sq[pl][threadIdx.x & 31] = q;
   __syncthreads();
-  if (threadIdx.x < 32) {
+  s_a[pl][cl] = q;
+  __syncthreads();
+  if (threadIdx.x < 32 && cok) {
     float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += s_sq[k][threadIdx.x];
-    s_rstd[threadIdx.x] = rsqrtf(t / (float)HW + eps);           // biased variance, as F.instance_norm
+    for (int k = 0; k < 8; ++k) t += s_a[k][threadIdx.x];
+    float* w = ws + (((long long)n * IN_SPLITS + split) * C + c) * 2;
+    w[0] = mean;
+    w[1] = t;                                                    // M2 of this split
   }
-  __syncthreads();
-  const float rstd = s_rstd[threadIdx.x & 31];
-  if (cok)
-    for (int p = pl; p < HW; p += 8) {
-      const long long o = ((long long)n * HW + p) * C + c;
-      float v = (xb[(long long)p * C + c] - mean) * rstd;
+}
+
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ ws, int HW,
+                                                             int C, float eps, int relu, long long total,
+                                                             float* __restrict__ of, __nv_bfloat16* __restrict__ ob) {
+  // grid-stride over (n, pixel-block of 8, channel): the per-channel statistics are merged once per thread and reused
+  const int per = (HW + IN_SPLITS - 1) / IN_SPLITS;
+  const int pblocks = (HW + 7) / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int pb = (int)(t % pblocks);
+    const long long n = t / pblocks;
+    float mean = 0.f, m2 = 0.f, cnt = 0.f;
+#pragma unroll
+    for (int sidx = 0; sidx < IN_SPLITS; ++sidx) {
+      const int p0 = sidx * per;
+      const float nb = (float)max(min(HW, p0 + per) - p0, 0);
+      if (nb > 0.f) {
+        const float* w = ws + ((n * IN_SPLITS + sidx) * C + c) * 2;
+        const float delta = w[0] - mean, tot = cnt + nb;
+        mean += delta * nb / tot;
+        m2 += w[1] + delta * delta * cnt * nb / tot;
+        cnt = tot;
+      }
+    }
+    const float rstd = rsqrtf(m2 / (float)HW + eps);            // biased variance, as F.instance_norm
+    for (int p = pb * 8; p < min(HW, pb * 8 + 8); ++p) {
+      const long long o = (n * HW + p) * C + c;
+      float v = (x[o] - mean) * rstd;
       if (relu) v = fmaxf(v, 0.f);
       if (of) of[o] = v;
       if (ob) ob[o] = __float2bfloat16(v);
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -102,6 +162,32 @@ __device__ __forceinline__ float act_apply(float v, int mode) {
   if (mode == 2) return 1.f / (1.f + __expf(-v));
   if (mode == 3) return tanhf(v);
   return v;
+}
+
+// 4-wide variant for N % 4 == 0 with 16-byte aligned rows (every hot use)
+__global__ void __launch_bounds__(256) act4_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y,
+                                                   long long ldy, long long M, int N4, int mode, float scale,
+                                                   float* __restrict__ of, long long ldf, __nv_bfloat16* __restrict__ ob,
+                                                   long long ldb) {
+  const long long total = M * N4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / N4;
+    const int c = (int)(i - r * N4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    if (y) {
+      const float4 u = *reinterpret_cast<const float4*>(y + r * ldy + c);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    v.x = act_apply(v.x, mode); v.y = act_apply(v.y, mode); v.z = act_apply(v.z, mode); v.w = act_apply(v.w, mode);
+    if (of) *reinterpret_cast<float4*>(of + r * ldf + c) = v;
+    if (ob) {
+      uint2 pk;
+      pk.x = pack_bf16(v.x, v.y);
+      pk.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(ob + r * ldb + c) = pk;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y,
@@ -277,21 +363,24 @@ extern "C" int tgb_im2col_nhwc_bf16(const void* x, int64_t ldx, int N, int H, in
   auto xb = (const __nv_bfloat16*)x;
   auto ob = (__nv_bfloat16*)out;
   if (vec)
-    im2col_nhwc_kernel<true><<<ew_grid(rows * (ldo / 8)), 256, 0, (cudaStream_t)stream>>>(xb, ldx, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, rows, ob, ldo);
+    im2col_nhwc_vec_kernel<<<ew_grid(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>(xb, ldx, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, rows, ob, ldo);
   else
-    im2col_nhwc_kernel<false><<<ew_grid(rows * ldo), 256, 0, (cudaStream_t)stream>>>(xb, ldx, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, rows, ob, ldo);
+    im2col_nhwc_kernel<<<ew_grid(rows * ldo), 256, 0, (cudaStream_t)stream>>>(xb, ldx, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, rows, ob, ldo);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }
 
-extern "C" int tgb_instance_norm_nhwc(const float* x, int N, int HW, int C, float eps, int relu, float* out_f32,
-                                      void* out_bf16, tgb_stream_t stream) {
+extern "C" int tgb_instance_norm_nhwc(const float* x, int N, int HW, int C, float eps, int relu, float* workspace,
+                                      float* out_f32, void* out_bf16, tgb_stream_t stream) {
   int st = check_device();
   if (st != TGB_OK) return st;
-  TGB_CHECK_ARG(x && (out_f32 || out_bf16) && N >= 0 && HW > 0 && C > 0 && N <= 65535, "instance_norm: bad arguments");
+  TGB_CHECK_ARG(x && workspace && (out_f32 || out_bf16) && N >= 0 && HW > 0 && C > 0 && N <= 65535, "instance_norm: bad arguments");
   if (N == 0) return TGB_OK;
-  dim3 grid((C + 31) / 32, N);
-  instnorm_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, HW, C, eps, relu, out_f32, (__nv_bfloat16*)out_bf16);
+  dim3 grid((C + 31) / 32, N, IN_SPLITS);
+  instnorm_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, HW, C, workspace);
+  const long long total = (long long)N * ((HW + 7) / 8) * C;
+  instnorm_apply_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, workspace, HW, C, eps, relu, total, out_f32,
+                                                                        (__nv_bfloat16*)out_bf16);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }
@@ -302,8 +391,16 @@ extern "C" int tgb_act_f32(const float* x, int64_t ldx, const float* y, int64_t 
   if (st != TGB_OK) return st;
   TGB_CHECK_ARG(x && (out_f32 || out_bf16) && M >= 0 && N > 0 && mode >= 0 && mode <= 3, "act: bad arguments");
   if (M == 0) return TGB_OK;
-  act_kernel<<<ew_grid(M * N), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, N, mode, scale, out_f32, ld_f32,
-                                                              (__nv_bfloat16*)out_bf16, ld_bf16);
+  const bool v4 = N % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)x % 16) == 0 &&
+                  (!y || (ldy % 4 == 0 && ((uintptr_t)y % 16) == 0)) &&
+                  (!out_f32 || (ld_f32 % 4 == 0 && ((uintptr_t)out_f32 % 16) == 0)) &&
+                  (!out_bf16 || (ld_bf16 % 4 == 0 && ((uintptr_t)out_bf16 % 8) == 0));
+  if (v4)
+    act4_kernel<<<ew_grid(M * (N / 4)), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, N / 4, mode, scale, out_f32, ld_f32,
+                                                                     (__nv_bfloat16*)out_bf16, ld_bf16);
+  else
+    act_kernel<<<ew_grid(M * N), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, N, mode, scale, out_f32, ld_f32,
+                                                                (__nv_bfloat16*)out_bf16, ld_bf16);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

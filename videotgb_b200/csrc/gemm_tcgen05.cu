@@ -70,10 +70,13 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, float4 v, c
   if (EPI == TGB_EPI_BF16_GELU) {
     v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
   }
+  if (EPI == TGB_EPI_BF16_RELU) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  }
   if (EPI == TGB_EPI_F32_RESID) {
     v.x += res.x; v.y += res.y; v.z += res.z; v.w += res.w;
   }
-  if (EPI == TGB_EPI_BF16 || EPI == TGB_EPI_BF16_GELU) {
+  if (EPI == TGB_EPI_BF16 || EPI == TGB_EPI_BF16_GELU || EPI == TGB_EPI_BF16_RELU) {
     uint2 o;
     o.x = pack_bf16(v.x, v.y);
     o.y = pack_bf16(v.z, v.w);
@@ -393,6 +396,7 @@ static int dispatch_epi(const void* A, long long lda, const void* W, long long l
     case TGB_EPI_F32: return launch_gemm<BN, TGB_EPI_F32, CG>(A, lda, W, ldw, p, s);
     case TGB_EPI_F32_RESID: return launch_gemm<BN, TGB_EPI_F32_RESID, CG>(A, lda, W, ldw, p, s);
     case TGB_EPI_F32_ROWBIAS: return launch_gemm<BN, TGB_EPI_F32_ROWBIAS, CG>(A, lda, W, ldw, p, s);
+    case TGB_EPI_BF16_RELU: return launch_gemm<BN, TGB_EPI_BF16_RELU, CG>(A, lda, W, ldw, p, s);
   }
   set_last_error("unknown epilogue %d", p.epi);
   return TGB_EINVAL;

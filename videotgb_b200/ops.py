@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import check
 
-EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_F32_ROWBIAS = range(5)
+EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_F32_ROWBIAS, EPI_BF16_RELU = range(6)
 MAP_SCALED, MAP_RATIO = 0, 1
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -204,7 +204,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     n, kw, ldw = _rows(w, "w")
     if k != kw:
         raise _lib.TgbError(f"gemm: K mismatch {k} vs {kw}")
-    out_dtype = torch.bfloat16 if epilogue in (EPI_BF16, EPI_BF16_GELU) else torch.float32
+    out_dtype = torch.bfloat16 if epilogue in (EPI_BF16, EPI_BF16_GELU, EPI_BF16_RELU) else torch.float32
     if out is None:
         if epilogue == EPI_F32_ROWBIAS:
             raise _lib.TgbError("gemm: the row-bias epilogue writes into a caller-provided buffer")
@@ -454,7 +454,8 @@ def instance_norm_nhwc(x: torch.Tensor, n: int, hw: int, relu: bool, want_f32: b
     c = x.shape[-1]
     of = torch.empty_like(x) if want_f32 else None
     ob = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    check(_lib.load().tgb_instance_norm_nhwc(_p(x), n, hw, c, float(eps), int(relu), _p(of), _p(ob), _stream()))
+    ws = torch.empty((n * 16 * c * 2,), dtype=torch.float32, device=x.device)
+    check(_lib.load().tgb_instance_norm_nhwc(_p(x), n, hw, c, float(eps), int(relu), _p(ws), _p(of), _p(ob), _stream()))
     return of, ob
 
 

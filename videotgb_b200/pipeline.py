@@ -58,14 +58,30 @@ class LanguageProjection(_KernelModule):
 
 class VideoTGBEncoder(nn.Module):
     def __init__(self, vision_config=None, qformer_config=None, sampler_config=None, llm_hidden: int = 2048,
-                 instruct: bool = False):
+                 instruct: bool = False, with_flow_extractor: bool = False):
         super().__init__()
         self.instruct = instruct
         self.model = _Blip2Like(vision_config, qformer_config, llm_hidden, instruct)
         self.temporal_encoder = RopeBertModel(sampler_config)
+        if with_flow_extractor:            # offline inference computes the flow online (eval/utils/model.py:37,75-84)
+            from .raft import RAFT
+            self.of_extractor = RAFT()
         self.token_exchange = None      # optional distributed.TokenAllGather: all-gather of the Q-Former tokens
 
     # ---- stages -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def extract_flow(self, flow_frames) -> torch.Tensor:
+        """SURVEY.md section 8f N1, eval/utils/model.py:75-84: per video `flow_frame` [T,3,H,W] -> RAFT on consecutive
+        pairs (padded to a multiple of 8), last flow repeated -> `of` [B,T,2,H,W] for `temporal_encoder`."""
+        from .raft import InputPadder
+        of = []
+        for flow_frame in flow_frames:
+            padder = InputPadder(flow_frame[0].shape)
+            ff = padder.pad(flow_frame)
+            feats = self.of_extractor(ff[:-1], ff[1:])
+            of.append(torch.cat([feats, feats[-1].unsqueeze(0)], dim=0))
+        return torch.stack(of)
+
     def score(self, batch, mode: str = "fusion"):
         """A1-A6: -> (of_feat, start_logits [B,L,1], end_logits [B,L,1])."""
         of_feat, of_logits = self.temporal_encoder(

@@ -173,15 +173,15 @@ class RAFT(_KernelModule):
 
     # ---- building blocks ---------------------------------------------------------------------------------
     @staticmethod
-    def _conv(x_bf16, n, h, w, c, pc, out=None):
-        """bf16 pixel rows [n*h*w, >=c] -> fp32 [n*ho*wo, cout_pad]; returns (y, ho, wo)."""
+    def _conv(x_bf16, n, h, w, c, pc, out=None, epi=ops.EPI_F32):
+        """bf16 pixel rows [n*h*w, >=c] -> fp32 (or, with the fused-ReLU epilogue, bf16) [n*ho*wo, cout_pad]; -> (y, ho, wo)."""
         ho = (h + 2 * pc.padding[0] - pc.kh) // pc.stride[0] + 1
         wo = (w + 2 * pc.padding[1] - pc.kw) // pc.stride[1] + 1
         if pc.kh == 1 and pc.kw == 1 and pc.stride == (1, 1) and c % 8 == 0:
             a = x_bf16 if x_bf16.shape[1] == c else x_bf16[:, :c]
         else:
             a = ops.im2col_nhwc(x_bf16, n, h, w, c, pc.kh, pc.kw, pc.stride, pc.padding)
-        return ops.gemm(a, pc.w, pc.b, ops.EPI_F32, out=out), ho, wo
+        return ops.gemm(a, pc.w, pc.b, epi, out=out), ho, wo
 
     def _encode(self, e, img_rows, n, h, w, instance: bool):
         """BasicEncoder on bf16 pixel rows [n*h*w, 8] (3 real channels) -> fp32 [n*(h/8)*(w/8), out]."""
@@ -216,13 +216,24 @@ class RAFT(_KernelModule):
             raise NotImplementedError("the B200 RAFT is inference only (test_mode=True returns the final flow_up)")
         if flow_init is not None:
             raise NotImplementedError("flow_init is not used on the VideoTGB path")
-        pk = self._pack()
         n, _, H, W = image1.shape
         if H % 8 or W % 8:
             raise ValueError("image sides must be divisible by 8 (use InputPadder)")
+        if ((H // 8) * (W // 8)) % 8 or H < 128 or W < 128:
+            raise ValueError("the correlation GEMM needs (H/8)*(W/8) % 8 == 0 and the 4-level pyramid H, W >= 128")
+        self._pack()
+        image1, image2 = image1.float().contiguous(), image2.float().contiguous()
+        if self._use_graph(n):                                   # ~800 launches per call: replay a captured CUDA graph
+            return self._graphs.run(("raft", n, H, W, iters), [image1, image2],
+                                    lambda a, b: (self._forward_impl(a, b, iters),))[0]
+        return self._forward_impl(image1, image2, iters)
+
+    def _forward_impl(self, image1, image2, iters):
+        pk = self._pack()
+        n, _, H, W = image1.shape
         dev = image1.device
-        rows1 = ops.raft_prep_image(image1.float().contiguous())
-        rows2 = ops.raft_prep_image(image2.float().contiguous())
+        rows1 = ops.raft_prep_image(image1)
+        rows2 = ops.raft_prep_image(image2)
         fmaps, h, w = self._encode(pk.fnet, torch.cat([rows1, rows2], 0), 2 * n, H, W, instance=True)
         hw = h * w
         # all-pairs correlation / sqrt(dim): one GEMM per pair (fmap1 pre-scaled by 1/16, exact in bf16)
@@ -249,17 +260,12 @@ class RAFT(_KernelModule):
         mask = None
         for _ in range(iters):
             ops.corr_lookup(pyr, flow, n, h, w, corr_feat)
-            # BasicMotionEncoder (update.py:97-113)
-            y, _, _ = self._conv(corr_feat, n, h, w, 328, pk.convc1)
-            _, cb = ops.act(y, ops.ACT_RELU, want_bf16=True)
-            y, _, _ = self._conv(cb, n, h, w, 256, pk.convc2)
-            ops.act(y, ops.ACT_RELU, out_bf16=cor_flo[:, :192])
-            y, _, _ = self._conv(flow_b, n, h, w, 2, pk.convf1)
-            _, fb = ops.act(y, ops.ACT_RELU, want_bf16=True)
-            y, _, _ = self._conv(fb, n, h, w, 128, pk.convf2)
-            ops.act(y, ops.ACT_RELU, out_bf16=cor_flo[:, 192:256])
-            y, _, _ = self._conv(cor_flo, n, h, w, 256, pk.conv)
-            ops.act(y[:, :126], ops.ACT_RELU, out_bf16=hx[:, 256:382])
+            # BasicMotionEncoder (update.py:97-113); ReLU is fused into the GEMM epilogue, outputs land in their concat slots
+            cb, _, _ = self._conv(corr_feat, n, h, w, 328, pk.convc1, epi=ops.EPI_BF16_RELU)
+            self._conv(cb, n, h, w, 256, pk.convc2, out=cor_flo[:, :192], epi=ops.EPI_BF16_RELU)
+            fb, _, _ = self._conv(flow_b, n, h, w, 2, pk.convf1, epi=ops.EPI_BF16_RELU)
+            self._conv(fb, n, h, w, 128, pk.convf2, out=cor_flo[:, 192:256], epi=ops.EPI_BF16_RELU)
+            self._conv(cor_flo, n, h, w, 256, pk.conv, out=hx[:, 256:384], epi=ops.EPI_BF16_RELU)   # 126 real channels + 2 pad
             hx[:, 382:384].copy_(flow_b[:, :2])
             rhx[:, 256:384].copy_(hx[:, 256:384])
             # SepConvGRU (update.py:31-59): horizontal then vertical half
@@ -269,12 +275,10 @@ class RAFT(_KernelModule):
                 q, _, _ = self._conv(rhx, n, h, w, 384, pk.q[s])
                 ops.gru_update(zr, q, net, hx[:, :128])
             nb = hx[:, :128]
-            y, _, _ = self._conv(nb, n, h, w, 128, pk.fh1)
-            _, t = ops.act(y, ops.ACT_RELU, want_bf16=True)
+            t, _, _ = self._conv(nb, n, h, w, 128, pk.fh1, epi=ops.EPI_BF16_RELU)
             delta, _, _ = self._conv(t, n, h, w, 256, pk.fh2)
             ops.act(flow, ops.ACT_NONE, y=delta[:, :2], out_f32=flow, out_bf16=flow_b[:, :2])     # F(t+1) = F(t) + delta
         # the upsampling mask only matters for the last iteration (test_mode returns the final flow_up)
-        y, _, _ = self._conv(hx[:, :128], n, h, w, 128, pk.mask0)
-        _, t = ops.act(y, ops.ACT_RELU, want_bf16=True)
+        t, _, _ = self._conv(hx[:, :128], n, h, w, 128, pk.mask0, epi=ops.EPI_BF16_RELU)
         mask, _, _ = self._conv(t, n, h, w, 256, pk.mask2)
         return ops.raft_upsample(mask, flow, n, h, w)
