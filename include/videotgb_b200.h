@@ -212,7 +212,7 @@ TGB_API int tgb_replace_ids(int64_t* ids, int64_t n, int64_t from, int64_t to, t
 TGB_API int tgb_im2col_nhwc_bf16(const void* x, int64_t ldx, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
                                  int ph, int pw, void* out, int64_t ldo, tgb_stream_t stream);
 /* nn.InstanceNorm2d(affine=False) (+ ReLU) over H*W per (n, c) (extractor.py:27-31,125-126): x f32 [N, HW, C].
- * workspace: f32 [N * 16 * C * 2] scratch for the split statistics (the library never allocates).                   */
+ * workspace: f32 [N * 17 * C * 2] scratch for the split statistics (the library never allocates).  C % 4 == 0.      */
 TGB_API int tgb_instance_norm_nhwc(const float* x, int N, int HW, int C, float eps, int relu, float* workspace,
                                    float* out_f32, void* out_bf16, tgb_stream_t stream);
 /* out = act(scale * x (+ y)) on [M,N] with row pitches; act 0 identity / 1 relu / 2 sigmoid / 3 tanh.               */

@@ -119,17 +119,13 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ ws, int HW,
-                                                             int C, float eps, int relu, long long total,
-                                                             float* __restrict__ of, __nv_bfloat16* __restrict__ ob) {
-  // grid-stride over (n, pixel-block of 8, channel): the per-channel statistics are merged once per thread and reused
+// merge the split partials (Chan's formula) once per (n, c): fin[(n*C + c)*2] = (mean, rstd)
+__global__ void __launch_bounds__(256) instnorm_finalize_kernel(const float* __restrict__ ws, int HW, int C, float eps,
+                                                                long long NC, float* __restrict__ fin) {
   const int per = (HW + IN_SPLITS - 1) / IN_SPLITS;
-  const int pblocks = (HW + 7) / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long t = i / C;
-    const int pb = (int)(t % pblocks);
-    const long long n = t / pblocks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NC; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / C;
+    const int c = (int)(i - n * C);
     float mean = 0.f, m2 = 0.f, cnt = 0.f;
 #pragma unroll
     for (int sidx = 0; sidx < IN_SPLITS; ++sidx) {
@@ -143,13 +139,32 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __rest
         cnt = tot;
       }
     }
-    const float rstd = rsqrtf(m2 / (float)HW + eps);            // biased variance, as F.instance_norm
-    for (int p = pb * 8; p < min(HW, pb * 8 + 8); ++p) {
-      const long long o = (n * HW + p) * C + c;
-      float v = (x[o] - mean) * rstd;
-      if (relu) v = fmaxf(v, 0.f);
-      if (of) of[o] = v;
-      if (ob) ob[o] = __float2bfloat16(v);
+    fin[i * 2] = mean;
+    fin[i * 2 + 1] = rsqrtf(m2 / (float)HW + eps);              // biased variance, as F.instance_norm
+  }
+}
+
+// fully parallel apply: 4 channels per thread, 16-byte accesses
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ fin, int HW,
+                                                             int C, int relu, long long total4, float* __restrict__ of,
+                                                             __nv_bfloat16* __restrict__ ob) {
+  const int c4n = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) << 2;
+    const long long np = i / c4n;                                 // n*HW + p
+    const long long n = np / HW;
+    const float4 v = *reinterpret_cast<const float4*>(x + np * C + c);
+    const float4 s0 = *reinterpret_cast<const float4*>(fin + (n * C + c) * 2);         // mean0 rstd0 mean1 rstd1
+    const float4 s1 = *reinterpret_cast<const float4*>(fin + (n * C + c) * 2 + 4);
+    float4 o;
+    o.x = (v.x - s0.x) * s0.y; o.y = (v.y - s0.z) * s0.w; o.z = (v.z - s1.x) * s1.y; o.w = (v.w - s1.z) * s1.w;
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (of) *reinterpret_cast<float4*>(of + np * C + c) = o;
+    if (ob) {
+      uint2 pk;
+      pk.x = pack_bf16(o.x, o.y);
+      pk.y = pack_bf16(o.z, o.w);
+      *reinterpret_cast<uint2*>(ob + np * C + c) = pk;
     }
   }
 }
@@ -374,13 +389,17 @@ extern "C" int tgb_instance_norm_nhwc(const float* x, int N, int HW, int C, floa
                                       float* out_f32, void* out_bf16, tgb_stream_t stream) {
   int st = check_device();
   if (st != TGB_OK) return st;
-  TGB_CHECK_ARG(x && workspace && (out_f32 || out_bf16) && N >= 0 && HW > 0 && C > 0 && N <= 65535, "instance_norm: bad arguments");
+  TGB_CHECK_ARG(x && workspace && (out_f32 || out_bf16) && N >= 0 && HW > 0 && C > 0 && C % 4 == 0 && N <= 65535,
+                "instance_norm: bad arguments (C %% 4 == 0)");
+  TGB_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)workspace % 16) == 0, "instance_norm: misaligned");
   if (N == 0) return TGB_OK;
+  float* fin = workspace + (size_t)N * IN_SPLITS * C * 2;
   dim3 grid((C + 31) / 32, N, IN_SPLITS);
   instnorm_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, HW, C, workspace);
-  const long long total = (long long)N * ((HW + 7) / 8) * C;
-  instnorm_apply_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, workspace, HW, C, eps, relu, total, out_f32,
-                                                                        (__nv_bfloat16*)out_bf16);
+  instnorm_finalize_kernel<<<ew_grid((long long)N * C), 256, 0, (cudaStream_t)stream>>>(workspace, HW, C, eps, (long long)N * C, fin);
+  const long long total4 = (long long)N * HW * (C / 4);
+  instnorm_apply_kernel<<<ew_grid(total4), 256, 0, (cudaStream_t)stream>>>(x, fin, HW, C, relu, total4, out_f32,
+                                                                         (__nv_bfloat16*)out_bf16);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

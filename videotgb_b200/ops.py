@@ -454,7 +454,7 @@ def instance_norm_nhwc(x: torch.Tensor, n: int, hw: int, relu: bool, want_f32: b
     c = x.shape[-1]
     of = torch.empty_like(x) if want_f32 else None
     ob = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    ws = torch.empty((n * 16 * c * 2,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((n * 17 * c * 2,), dtype=torch.float32, device=x.device)
     check(_lib.load().tgb_instance_norm_nhwc(_p(x), n, hw, c, float(eps), int(relu), _p(ws), _p(of), _p(ob), _stream()))
     return of, ob
 
