@@ -94,3 +94,53 @@ def test_full_oracle_spot_check(full):
         want = torch_ref.project_tokens(hsd, qo, 2)              # [2, 32, 2048]
     got = torch.stack([out[v, s * 32:(s + 1) * 32] for v, s in pick])
     assert_parity(got, want, "full-size tokens vs fp32 oracle")
+
+
+@pytest.mark.parametrize("tt,real", [(16, 16), (32, 20)])
+def test_full_config3_instructblip_long_video(tt, real):
+    """BASELINE config 3 at full size: InstructBLIP-Vicuna path, one 128-frame video (flow frames == candidates), the
+    sampler (mode="multi_modal", 12 layers) selects 32 frames, instruction-conditioned Q-Former (Tt instruction tokens,
+    `real` of them unpadded), H_llm = 4096.  Every selected frame is compared with the fp32 oracle (39-layer ViT)."""
+    from oracle.transform_ref import normalize_u8_thwc
+    from videotgb_b200 import synthetic as syn
+    b, t_frames, tq, k = 1, 128, 16, 32
+    enc = VideoTGBEncoder(NS(), None, NS(fusion_layer=6, encoder_width=768), llm_hidden=4096, instruct=True).to(DEV)
+    vsd, isd = syn.vision_state_dict(), syn.qformer_state_dict(syn.QFormerCfg(instruct=True))
+    ssd, hsd = syn.sampler_state_dict(), syn.head_state_dict(llm_hidden=4096)
+    enc.model.vision_model.load_state_dict(vsd)
+    enc.model.qformer.load_state_dict(isd)
+    enc.temporal_encoder.load_state_dict(ssd)
+    enc.load_state_dict({"model." + kk: v for kk, v in hsd.items()}, strict=False)
+    enc.eval()
+    g = torch.Generator().manual_seed(77 + tt)
+    u8 = torch.randint(0, 256, (b, t_frames, 224, 224, 3), generator=g, dtype=torch.uint8)
+    of = syn.synthetic_flow(b, t_frames, seed=19)
+    of_mask = torch.ones(b, t_frames + 2, dtype=torch.long)
+    qids = torch.randint(1000, 30522, (b, tq), generator=g)
+    tids = torch.randint(1000, 30522, (b, tt), generator=g)
+    tmask = torch.ones(b, tt, dtype=torch.long)
+    tmask[:, real:] = 0
+    gum = [-torch.empty(2 * b, t_frames, 1).exponential_(generator=g).log() for _ in range(2)]
+    batch = dict(frames_u8=u8.to(DEV), of=of.to(DEV), of_mask=of_mask.to(DEV), of_lengths=[t_frames],
+                 sampler_question=qids.to(DEV), sampler_question_attention_mask=torch.ones(b, tq, dtype=torch.long, device=DEV),
+                 qformer_text=tids.to(DEV), qformer_text_attention_mask=tmask.to(DEV), nframe=k)
+    out, aux = enc.encode_u8(batch, mode="multi_modal", gumbel=[x.to(DEV) for x in gum], return_aux=True)
+    assert out.shape == (1, k * 32, 4096) and bool(torch.isfinite(out).all())
+    sl, el = aux.start_logits.cpu(), aux.end_logits.cpu()
+    cs, ce = zip(*[select_ref.gumbel_argmax(sl, el, gg) for gg in gum])
+    want_idx = select_ref.select_batch(list(cs), list(ce), [t_frames], t_frames, k)
+    assert torch.equal(aux.indices.cpu(), want_idx)
+    px = torch.from_numpy(normalize_u8_thwc(u8.view(-1, 224, 224, 3).numpy())).view(b, t_frames, 3, 224, 224)
+    dev = lambda sd: {kk: v.to(DEV) for kk, v in sd.items()}
+    with torch.no_grad():
+        sampled = select_ref.gather_frames(px, want_idx).to(DEV)
+        img, _ = torch_ref.vit_forward(dev(vsd), sampled)
+        qt = hsd["query_tokens"].to(DEV).expand(k, -1, -1)
+        ids = torch.repeat_interleave(tids, k, 0).to(DEV)
+        am = torch.cat([torch.ones(k, 32, dtype=torch.long), torch.repeat_interleave(tmask, k, 0)], 1).to(DEV)
+        qo = torch_ref.qformer_forward(dev(isd), qt, img, None, input_ids=ids, attention_mask=am, instruct=True)[:, :32]
+        want = torch_ref.project_tokens(dev(hsd), qo, b)
+        _, rlogits = torch_ref.sampler_forward(dev(ssd), of.to(DEV), of_mask.to(DEV), qids.to(DEV),
+                                               torch.ones(b, tq, dtype=torch.long, device=DEV), mode="multi_modal")
+    assert_parity(out, want, "config 3 tokens vs fp32 oracle")
+    assert_parity(torch.cat([aux.start_logits, aux.end_logits], -1), rlogits, "config 3 multi_modal scores")
