@@ -351,7 +351,9 @@ def run_ours(args):
             traffic = tr.get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
-    epi_names = {0: "bias", 1: "bias+erf-GELU", 2: "bias (fp32 out)", 3: "bias+fp32 residual", 4: "row-bias (patch embed)"}
+    epi_names = {0: "bias", 1: "bias+erf-GELU", 2: "bias (fp32 out)", 3: "bias+fp32 residual", 4: "row-bias (patch embed)",
+                 5: "bias+ReLU", 6: "folded LayerNorm+bias", 7: "folded LayerNorm+bias+erf-GELU",
+                 8: "bias+fp32 residual+bf16 copy+LayerNorm statistics"}
 
     if rank != 0:
         if world > 1:

@@ -126,10 +126,30 @@ TGB_API int tgb_fill_cls_rows(float* hidden, const float* cls, const float* pos0
  *   TGB_EPI_BF16_RELU   out bf16 = relu(acc + bias)                               (RAFT convolutions)
  * N % 8 == 0.  bn: 0 = choose, else force the N tile (256/176/128/64).                                      */
 enum { TGB_EPI_BF16 = 0, TGB_EPI_BF16_GELU = 1, TGB_EPI_F32 = 2, TGB_EPI_F32_RESID = 3, TGB_EPI_F32_ROWBIAS = 4,
-       TGB_EPI_BF16_RELU = 5 };
+       TGB_EPI_BF16_RELU = 5, TGB_EPI_BF16_LN = 6, TGB_EPI_BF16_GELU_LN = 7, TGB_EPI_F32_RESID_STATS = 8 };
 TGB_API int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
                   const float* bias, const float* resid, int64_t ldr, const float* rowbias, int period, int skip,
                   void* out, int64_t ldo, int bn, tgb_stream_t stream);
+
+/* LayerNorm folded into the GEMMs either side of it (the pre-LN blocks of Blip2EncoderLayer, xblip2.py:236-258:
+ * layer_norm1 -> qkv, layer_norm2 -> fc1).  With W' = W * gamma (per input column), colsum[n] = sum_k W'[n,k] and
+ * bias'[n] = sum_k W[n,k] beta[k] + b[n]:   LN(x) W^T + b = rstd_m * (x W'^T - mean_m * colsum) + bias'.
+ *   TGB_EPI_BF16_LN / TGB_EPI_BF16_GELU_LN   consumer: A = bf16 copy of the un-normalised residual rows, W = W',
+ *                       bias = bias', rowstats f32 [M,2] = (mean, rstd) per row, colsum f32 [N]
+ *   TGB_EPI_F32_RESID_STATS                  producer: out f32 = acc + bias + resid (as TGB_EPI_F32_RESID), plus
+ *                       out_bf16 [M, ldo2] = bf16(out) and partial_stats f32 [M, slots, 2] = (sum, sum of squares) of
+ *                       each row over the columns of one slot; slots = tgb_gemm_ln_stats_slots(M, N); every slot is
+ *                       written exactly once per launch (no atomics: results are run-to-run deterministic)
+ * tgb_ln_stats_finalize reduces the slots to rowstats (float64 combine, biased variance, rstd = 1/sqrt(var + eps));
+ * tgb_rowstats_cast_f32 produces rowstats and the bf16 copy for rows that did not come out of a GEMM (first layer).  */
+TGB_API int tgb_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
+                     const float* bias, const float* resid, int64_t ldr, const float* rowstats, const float* colsum,
+                     void* out, int64_t ldo, void* out_bf16, int64_t ldo2, float* partial_stats, tgb_stream_t stream);
+TGB_API int tgb_gemm_ln_stats_slots(int M, int N);
+TGB_API int tgb_ln_stats_finalize(const float* partial_stats, int M, int slots, int N, float eps, float* rowstats,
+                          tgb_stream_t stream);
+TGB_API int tgb_rowstats_cast_f32(const float* x, int64_t ldx, int M, int N, float eps, void* out_bf16, int64_t ldo,
+                          float* rowstats, tgb_stream_t stream);
 
 /* Debug / test knob: 0 = choose per problem (default), 1 = single-CTA 128xBN tiles, 2 = CTA-pair 256xBN tiles.      */
 TGB_API int tgb_gemm_set_cta_group(int cta_group);

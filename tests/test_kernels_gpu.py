@@ -303,6 +303,98 @@ def test_gemm_epilogues(cta_group):
     assert (hidden[:, 0] == 7.0).all()
 
 
+# LayerNorm folded into the GEMMs (tgb_gemm_bf16_ln): producer statistics, finalize, consumer epilogues, and the chain
+# residual-GEMM -> LN -> GEMM against torch's layer_norm in float64.
+@pytest.mark.parametrize("m,n,k", [(777, 1408, 1408), (257 * 2, 1408, 6144), (130, 768, 256), (64, 136, 64)])
+def test_gemm_ln_statistics_producer(m, n, k, cta_group):
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) * 0.03).to(torch.bfloat16)
+    bias = torch.randn(n, generator=g)
+    resid = torch.randn(m, n, generator=g) * 2 + 0.7          # non-zero row mean
+    want = _gemm_ref(a, w, bias) + resid.double()
+    slots = ops.ln_stats_slots(m, n)
+    assert slots > 0 and slots % 4 == 0
+    x = resid.to(DEV)
+    xb = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
+    part = torch.full((m, slots, 2), float("nan"), device=DEV)
+    ops.gemm_ln(a.to(DEV), w.to(DEV), bias.to(DEV), ops.EPI_F32_RESID_STATS, x, resid=x, out_bf16=xb, partial_stats=part)
+    got = x.cpu()
+    assert (got.double() - want).abs().max().item() < 2e-4 * want.abs().max().item()
+    assert torch.equal(xb.cpu(), got.to(torch.bfloat16))      # the copy is the rounded fp32 result
+    assert torch.isfinite(part).all()                          # every slot of every row written
+    ps = part.cpu().double().sum(dim=1)
+    assert (ps[:, 0] - got.double().sum(dim=1)).abs().max().item() < 1e-3
+    assert ((ps[:, 1] - (got.double() ** 2).sum(dim=1)).abs() / (got.double() ** 2).sum(dim=1)).max().item() < 1e-5
+    for eps in (1e-6, 1e-12):
+        stats = torch.empty(m, 2, device=DEV)
+        ops.ln_stats_finalize(part, n, eps, stats)
+        mean = got.double().mean(dim=1)
+        rstd = 1.0 / torch.sqrt(got.double().var(dim=1, unbiased=False) + eps)
+        assert (stats[:, 0].cpu().double() - mean).abs().max().item() < 1e-5
+        assert ((stats[:, 1].cpu().double() - rstd).abs() / rstd).max().item() < 1e-4
+    # a second launch reproduces the statistics bit for bit (no atomics)
+    part2 = torch.empty_like(part)
+    x2 = resid.to(DEV)
+    ops.gemm_ln(a.to(DEV), w.to(DEV), bias.to(DEV), ops.EPI_F32_RESID_STATS, x2, resid=x2, out_bf16=xb, partial_stats=part2)
+    assert torch.equal(part, part2)
+
+
+def test_rowstats_cast():
+    g = torch.Generator().manual_seed(5)
+    for m, n in ((300, 1408), (17, 768), (9, 2048)):
+        x = torch.randn(m, n, generator=g) * 3 + 1.5
+        xb = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+        stats = torch.empty(m, 2, device=DEV)
+        ops.rowstats_cast(x.to(DEV), 1e-6, xb, stats)
+        assert torch.equal(xb.cpu(), x.to(torch.bfloat16))
+        assert (stats[:, 0].cpu() - x.mean(dim=1)).abs().max().item() < 1e-5
+        rstd = 1.0 / torch.sqrt(x.double().var(dim=1, unbiased=False) + 1e-6)
+        assert ((stats[:, 1].cpu().double() - rstd).abs() / rstd).max().item() < 1e-5
+
+
+@pytest.mark.parametrize("gelu", [False, True])
+@pytest.mark.parametrize("m,n,k", [(777, 4224, 1408), (300, 6144, 1408), (70, 264, 128)])
+def test_gemm_ln_consumer_matches_layernorm_then_linear(m, n, k, gelu, cta_group):
+    g = torch.Generator().manual_seed(m + n + k + int(gelu))
+    x = torch.randn(m, k, generator=g) * 1.7 + 0.4
+    x[:, 3] += 25.0                                             # an outlier channel, as in EVA-ViT-g residual streams
+    gamma = 1 + 0.2 * torch.randn(k, generator=g)
+    beta = 0.2 * torch.randn(k, generator=g)
+    w = torch.randn(n, k, generator=g) * 0.03
+    b = torch.randn(n, generator=g)
+    want = torch.nn.functional.layer_norm(x.double(), (k,), gamma.double(), beta.double(), 1e-6) @ w.double().t() + b.double()
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    wf = (w * gamma[None, :]).to(torch.bfloat16)
+    colsum = wf.float().sum(dim=1)
+    bias = w @ beta + b
+    xb = torch.empty(m, k, dtype=torch.bfloat16, device=DEV)
+    stats = torch.empty(m, 2, device=DEV)
+    ops.rowstats_cast(x.to(DEV), 1e-6, xb, stats)
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_ln(xb, wf.to(DEV), bias.to(DEV), ops.EPI_BF16_GELU_LN if gelu else ops.EPI_BF16_LN, out,
+                rowstats=stats, colsum=colsum.to(DEV))
+    # reference with the unfused kernels: the same bf16 operand roundings, so both sit at the same distance from float64
+    ln = ops.layernorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-6)[0]
+    unfused = ops.gemm(ln, w.to(torch.bfloat16).to(DEV), b.to(DEV), ops.EPI_BF16_GELU if gelu else ops.EPI_BF16)
+    e_fused = (out.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    e_unfused = (unfused.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    assert e_fused <= max(2 * e_unfused, 2 ** -7), (e_fused, e_unfused)
+    assert _cos(out.cpu(), want) > 0.9999
+
+
+def test_gemm_ln_rejects_bad_arguments():
+    a = torch.zeros(8, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(8, 64, dtype=torch.bfloat16, device=DEV)
+    out = torch.zeros(8, 8, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w, None, ops.EPI_BF16_LN, out=out)           # the plain entry point refuses the fold epilogues
+    with pytest.raises(RuntimeError):
+        ops.gemm_ln(a, w, torch.zeros(8, device=DEV), ops.EPI_BF16_LN, out, rowstats=torch.zeros(4, 2, device=DEV),
+                    colsum=torch.zeros(8, device=DEV))           # rowstats rows != M
+
+
 def test_gemm_rejects_bad_arguments():
     a = torch.zeros(8, 60, dtype=torch.bfloat16, device=DEV)
     w = torch.zeros(8, 60, dtype=torch.bfloat16, device=DEV)

@@ -71,6 +71,25 @@ def test_vit2_golden_and_oracle(vit2, gold):
         m()
 
 
+def test_vit_layernorm_fold_matches_separate_layernorm(vit2):
+    """layer_norm1/2 are folded into the qkv / fc1 GEMMs by default; the separate-LayerNorm path must agree with it to
+    bf16 rounding noise, and both must sit at the same distance from the fp32 oracle."""
+    sd, m, px, out = vit2
+    assert m.fuse_layernorm and m._pack().fused
+    plain = Blip2VisionModel(NS(num_hidden_layers=2)).to(DEV)
+    plain.fuse_layernorm = False
+    plain.load_state_dict(sd)
+    ref = plain(pixel_values=px).last_hidden_state
+    assert not plain._pack().fused
+    with torch.no_grad():
+        ref32, _ = torch_ref.vit_forward(to_dev(sd), px, layers=2)
+    r_fused, r_plain = relerr(out.last_hidden_state, ref32), relerr(ref, ref32)
+    print(f"vit2 LayerNorm fold: fused-vs-fp32 {r_fused:.3e}  separate-vs-fp32 {r_plain:.3e}  fused-vs-separate "
+          f"{relerr(out.last_hidden_state, ref):.3e}")
+    assert_parity(out.last_hidden_state, ref, "fused vs separate LayerNorm", rel=1e-2, cos=0.9999)
+    assert r_fused <= max(1.5 * r_plain, 5e-3)
+
+
 def test_vit_u8_fast_path(vit2):
     sd, m, _, _ = vit2
     u8 = syn.synthetic_frames_u8(2, seed=11).to(DEV)

@@ -66,21 +66,28 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // Exact-erf GELU (HF ACT2FN["gelu"]):  gelu(x) = x * Phi(x),  Phi(x) = 1 - 0.5*erfc(x/sqrt2).
-// erfc via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7) with the 0.5 folded into the coefficients:
+// erfc via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7) with the -0.5 folded into the coefficients:
 //   h(|x|) = 0.5*erfc(|x|/sqrt2) = t*(a1 + t*(a2 + t*(a3 + t*(a4 + t*a5)))) * exp(-x^2/2) / 2,  t = 1/(1 + p*|x|/sqrt2)
-//   gelu(x) = 0.5*x + |x|*(0.5 - h)        (branch-free; equals x*(1-h) for x >= 0 and x*h for x < 0)
-// 13 FP32 ops + 2 MUFU per element.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x);
-  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
-  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
-  poly = fmaf(poly, t, 0.5f * 1.421413741f);
-  poly = fmaf(poly, t, 0.5f * -0.284496736f);
-  poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  poly *= t;
-  const float e = ex2_approx((x * -0.72134752044448170f) * x);     // exp(-x^2/2)
-  const float h = poly * e;
-  return fmaf(ax, 0.5f - h, 0.5f * x);
+//   gelu(x) = max(x, 0) - |x|*h        (branch-free; equals x*(1-h) for x >= 0 and x*h for x < 0)
+// Evaluated on PAIRS with Blackwell's packed fp32 pipe (FFMA2 / FMUL2): 10 packed FP32 + 4 ALU + 4 MUFU per two
+// elements (the scalar form was 24 FP32 + 4 MUFU); the epilogue's instruction issue is what the GELU GEMM pays for.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  constexpr float K0 = 0.3275911f * 0.70710678118654752f;
+  const float2 d = __ffma2_rn(ax, make_float2(K0, K0), make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  constexpr float A1 = -0.5f * 0.254829592f, A2 = -0.5f * -0.284496736f, A3 = -0.5f * 1.421413741f,
+                  A4 = -0.5f * -1.453152027f, A5 = -0.5f * 1.061405429f;
+  float2 poly = __ffma2_rn(t, make_float2(A5, A5), make_float2(A4, A4));
+  poly = __ffma2_rn(poly, t, make_float2(A3, A3));
+  poly = __ffma2_rn(poly, t, make_float2(A2, A2));
+  poly = __ffma2_rn(poly, t, make_float2(A1, A1));
+  poly = __fmul2_rn(poly, t);
+  constexpr float KE = -0.72134752044448170f;                         // exp(-x^2/2) = 2^(KE * x^2)
+  const float2 arg = __fmul2_rn(__fmul2_rn(x, x), make_float2(KE, KE));
+  const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+  const float2 nh = __fmul2_rn(poly, e);                              // -h
+  return __ffma2_rn(ax, nh, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 
 // ------------------------------------------------------------------ mbarrier

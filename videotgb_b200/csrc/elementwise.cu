@@ -59,6 +59,65 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// LayerNorm fold, first layer: rows that did not come out of a statistics-producing GEMM.  One warp per row; same
+// two-pass statistics as layernorm_kernel; writes the bf16 copy of the raw row and (mean, rstd).
+template <int VEC>
+__global__ void __launch_bounds__(256) rowstats_cast_kernel(const float* __restrict__ x, long long ldx, float eps, int M,
+                                                            int N, __nv_bfloat16* __restrict__ ob, long long ldb,
+                                                            float2* __restrict__ stats) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nvec = N >> 2;
+  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
+       row += (long long)gridDim.x * warps_per_block) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+    float4 v[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = (c < nvec) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / static_cast<float>(N);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+        uint2 pk;
+        pk.x = pack_bf16(v[i].x, v[i].y);
+        pk.y = pack_bf16(v[i].z, v[i].w);
+        reinterpret_cast<uint2*>(ob + row * ldb)[c] = pk;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(N) + eps);
+    if (lane == 0) stats[row] = make_float2(mean, rstd);
+  }
+}
+
+// LayerNorm fold: per-row (sum, sum of squares) slots written by the TGB_EPI_F32_RESID_STATS epilogue -> (mean, rstd).
+// One thread per row, slots summed in index order in float64 (deterministic; the subtraction E[x^2] - mean^2 is exact
+// to fp32 partial-sum accuracy).
+__global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __restrict__ part, int M, int slots, int N,
+                                                                float eps, float2* __restrict__ stats) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  const float2* pr = part + (long long)row * slots;
+  double s = 0.0, q = 0.0;
+  for (int j = 0; j < slots; ++j) {
+    const float2 v = pr[j];
+    s += static_cast<double>(v.x);
+    q += static_cast<double>(v.y);
+  }
+  const double mean = s / N;
+  double var = q / N - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  stats[row] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, long long ldx,
                                                             __nv_bfloat16* __restrict__ out, long long ldo, int M, int nvec) {
   const long long total = (long long)M * nvec;
@@ -125,6 +184,46 @@ __global__ void replace_ids_kernel(long long* __restrict__ ids, long long n, lon
 }  // namespace tgb
 
 using namespace tgb;
+
+extern "C" int tgb_ln_stats_finalize(const float* partial_stats, int M, int slots, int N, float eps, float* rowstats,
+                                     tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(partial_stats && rowstats && M >= 0 && slots > 0 && N > 0, "ln_stats_finalize: bad arguments");
+  TGB_CHECK_ARG(((uintptr_t)partial_stats % 8) == 0 && ((uintptr_t)rowstats % 8) == 0, "ln_stats_finalize: misaligned");
+  if (M == 0) return TGB_OK;
+  ln_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(partial_stats), M, slots, N, eps, reinterpret_cast<float2*>(rowstats));
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
+extern "C" int tgb_rowstats_cast_f32(const float* x, int64_t ldx, int M, int N, float eps, void* out_bf16, int64_t ldo,
+                                     float* rowstats, tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(x && out_bf16 && rowstats, "rowstats_cast: null pointer");
+  TGB_CHECK_ARG(M >= 0 && N > 0 && N % 4 == 0 && N <= 128 * LN_MAX_VEC, "rowstats_cast: N=%d must be a multiple of 4 and <= %d", N, 128 * LN_MAX_VEC);
+  TGB_CHECK_ARG(ldx % 4 == 0 && ldx >= N && ((uintptr_t)x % 16) == 0, "rowstats_cast: misaligned input");
+  TGB_CHECK_ARG(ldo % 4 == 0 && ldo >= N && ((uintptr_t)out_bf16 % 8) == 0 && ((uintptr_t)rowstats % 8) == 0, "rowstats_cast: bad output");
+  if (M == 0) return TGB_OK;
+  const int warps = 8;
+  long long blocks = ((long long)M + warps - 1) / warps;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  const int nvec_lane = (N / 4 + 31) / 32;
+  cudaStream_t s = (cudaStream_t)stream;
+  auto ob = (__nv_bfloat16*)out_bf16;
+  auto rs = reinterpret_cast<float2*>(rowstats);
+#define TGB_RS(V) rowstats_cast_kernel<V><<<(int)blocks, 256, 0, s>>>(x, ldx, eps, M, N, ob, ldo, rs)
+  if (nvec_lane <= 2) TGB_RS(2);
+  else if (nvec_lane <= 6) TGB_RS(6);
+  else if (nvec_lane <= 11) TGB_RS(11);
+  else TGB_RS(16);
+#undef TGB_RS
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
 
 extern "C" int tgb_layernorm_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int M,
                                  int N, void* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32,

@@ -39,6 +39,22 @@ struct GemmParams {
   const float* rowbias;
   void* out;
   long long ldo, ldr;
+  // LayerNorm fold (see tgb_gemm_bf16_ln): consumer side reads rowstats [M,2] = (mean, rstd) and colsum [N]; the
+  // producer side (residual epilogue) also writes a bf16 copy of the new residual rows and per-slot (sum, sum of squares)
+  const float* rowstats;
+  const float* colsum;
+  __nv_bfloat16* out2;
+  long long ldo2;
+  float2* pstats;
+  int nslots;
+};
+
+template <int EPI> struct EpiTraits {
+  static constexpr bool LN = EPI == TGB_EPI_BF16_LN || EPI == TGB_EPI_BF16_GELU_LN;      // consumes row statistics
+  static constexpr bool STATS = EPI == TGB_EPI_F32_RESID_STATS;                          // produces them
+  static constexpr bool RESID = EPI == TGB_EPI_F32_RESID || STATS;
+  static constexpr bool GELU = EPI == TGB_EPI_BF16_GELU || EPI == TGB_EPI_BF16_GELU_LN;
+  static constexpr bool OUT_BF16 = EPI == TGB_EPI_BF16 || EPI == TGB_EPI_BF16_RELU || GELU || LN;
 };
 
 // EW = number of epilogue warps (8 or 16: 2 or 4 per TMEM lane quarter).  16 hides the global-memory latency of the
@@ -64,19 +80,32 @@ struct GemmCfg {
 // Epilogue math on 4 consecutive columns of one output row (transposed mapping: 4 lanes cover a 16-column row chunk,
 // so a warp instruction touches 8 rows x 64 contiguous bytes instead of 32 scattered rows).
 template <int EPI>
-__device__ __forceinline__ void epilogue_store4(const GemmParams& p, float4 v, const float4& bias4, const float4& res,
-                                                long long out_row, int col) {
-  v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-  if (EPI == TGB_EPI_BF16_GELU) {
-    v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+__device__ __forceinline__ float4 epilogue_store4(const GemmParams& p, float4 acc, const float4& bias4, const float4& res,
+                                                  const float4& cs4, float nmean, float rstd, long long out_row, int col) {
+  using T = EpiTraits<EPI>;
+  // packed fp32 pairs (FFMA2 / FADD2): half the FP32-pipe instructions of the scalar form
+  float2 lo = make_float2(acc.x, acc.y), hi = make_float2(acc.z, acc.w);
+  if (T::LN) {       // LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (W beta + b)
+    const float2 m2 = make_float2(nmean, nmean), r2 = make_float2(rstd, rstd);
+    lo = __ffma2_rn(__ffma2_rn(m2, make_float2(cs4.x, cs4.y), lo), r2, make_float2(bias4.x, bias4.y));
+    hi = __ffma2_rn(__ffma2_rn(m2, make_float2(cs4.z, cs4.w), hi), r2, make_float2(bias4.z, bias4.w));
+  } else {
+    lo = __fadd2_rn(lo, make_float2(bias4.x, bias4.y));
+    hi = __fadd2_rn(hi, make_float2(bias4.z, bias4.w));
   }
+  if (T::GELU) {
+    lo = gelu_erf2(lo);
+    hi = gelu_erf2(hi);
+  }
+  if (T::RESID) {
+    lo = __fadd2_rn(lo, make_float2(res.x, res.y));
+    hi = __fadd2_rn(hi, make_float2(res.z, res.w));
+  }
+  float4 v = make_float4(lo.x, lo.y, hi.x, hi.y);
   if (EPI == TGB_EPI_BF16_RELU) {
     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
   }
-  if (EPI == TGB_EPI_F32_RESID) {
-    v.x += res.x; v.y += res.y; v.z += res.z; v.w += res.w;
-  }
-  if (EPI == TGB_EPI_BF16 || EPI == TGB_EPI_BF16_GELU || EPI == TGB_EPI_BF16_RELU) {
+  if (T::OUT_BF16) {
     uint2 o;
     o.x = pack_bf16(v.x, v.y);
     o.y = pack_bf16(v.z, v.w);
@@ -84,6 +113,13 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, float4 v, c
   } else {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + col) = v;
   }
+  if (T::STATS) {
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(p.out2 + out_row * p.ldo2 + col) = o;
+  }
+  return v;
 }
 
 template <int BN, int EPI, int CG, int EW>
@@ -204,6 +240,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     // TMEM hands every thread one ROW (lane == row) of a 16-column chunk.  The chunk is transposed through a padded
     // per-warp shared-memory tile so that the global side is coalesced: thread -> (row = i*8 + lane/4, 4 columns at
     // (lane%4)*4), i.e. 64 contiguous bytes per row and 8 rows per instruction for the residual read and the store.
+    using T = EpiTraits<EPI>;
     const int ew = warp;
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
     const int sub = ew >> 2;                       // which 16-column chunks: sub, sub+NSUB, ...
@@ -240,11 +277,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       float4 rnext[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) rnext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (EPI == TGB_EPI_F32_RESID) {
+      if (T::RESID) {
         const int c = col0 + sub * 16 + tcol;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (rok[i] && c < p.N) rnext[i] = *reinterpret_cast<const float4*>(p.resid + (long long)(row_base + i * 8 + trow) * p.ldr + c);
+      }
+      // LayerNorm fold: (mean, rstd) of this thread's four rows (consumer) / running partial statistics (producer)
+      float rmean[4], rrstd[4], ssum[4], ssq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rmean[i] = 0.f; rrstd[i] = 0.f; ssum[i] = 0.f; ssq[i] = 0.f;
+        if (T::LN && rok[i]) {
+          const float2 st = __ldg(reinterpret_cast<const float2*>(p.rowstats) + (row_base + i * 8 + trow));
+          rmean[i] = -st.x;
+          rrstd[i] = st.y;
+        }
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -258,7 +306,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         float4 rcur[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
-        if (EPI == TGB_EPI_F32_RESID) {
+        if (T::RESID) {
           const int cn = col + NSUB * 16 + tcol;
           const bool more = (j + NSUB < NCHUNK) && (cn < p.N);
 #pragma unroll
@@ -276,15 +324,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const bool cok = c < p.N;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EPI != TGB_EPI_F32_ROWBIAS && p.bias != nullptr && cok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (T::LN && cok) cs4 = __ldg(reinterpret_cast<const float4*>(p.colsum + c));
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 a = *reinterpret_cast<const float4*>(stg + (i * 8 + trow) * STG_PITCH + tcol);
           if (rok[i] && cok) {
             if (EPI == TGB_EPI_F32_ROWBIAS) bias4 = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)rbrow[i] * p.N + c));
-            epilogue_store4<EPI>(p, a, bias4, rcur[i], orow[i], c);
+            const float4 r = epilogue_store4<EPI>(p, a, bias4, rcur[i], cs4, rmean[i], rrstd[i], orow[i], c);
+            if (T::STATS) {
+              ssum[i] += (r.x + r.y) + (r.z + r.w);
+              ssq[i] += fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w);
+            }
           }
         }
         __syncwarp();
+      }
+      if (T::STATS) {
+        // this warp's share of the tile (chunks sub, sub+NSUB, ...) -> one (sum, sum of squares) slot per row; every
+        // slot of every row is written exactly once per launch, in a fixed order: deterministic, no atomics
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 1);
+          ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 1);
+          ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 2);
+          ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 2);
+          if ((lane & 3) == 0 && rok[i])
+            p.pstats[(long long)(row_base + i * 8 + trow) * p.nslots + n_blk * NSUB + sub] = make_float2(ssum[i], ssq[i]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -383,7 +450,8 @@ template <int BN, int EPI, int CG>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmParams& p, cudaStream_t stream) {
   // measured (tools/gemm_ab.py, interleaved medians): 16 warps help the fp32-residual epilogue at short K (proj: 940 vs
   // 799 TF/s); bias / GELU epilogues are marginally better with 8 warps and the extra pipeline stage
-  int ew = g_force_ew ? g_force_ew : (EPI == TGB_EPI_F32_RESID ? 16 : 8);
+  int ew = g_force_ew ? g_force_ew : (EpiTraits<EPI>::RESID ? 16 : 8);
+  if (EpiTraits<EPI>::STATS) ew = 16;          // the statistics slot layout (4 per N tile) is fixed
   if (ew == 16) return launch_gemm_ew<BN, EPI, CG, 16>(A, lda, W, ldw, p, stream);
   return launch_gemm_ew<BN, EPI, CG, 8>(A, lda, W, ldw, p, stream);
 }
@@ -397,6 +465,9 @@ static int dispatch_epi(const void* A, long long lda, const void* W, long long l
     case TGB_EPI_F32_RESID: return launch_gemm<BN, TGB_EPI_F32_RESID, CG>(A, lda, W, ldw, p, s);
     case TGB_EPI_F32_ROWBIAS: return launch_gemm<BN, TGB_EPI_F32_ROWBIAS, CG>(A, lda, W, ldw, p, s);
     case TGB_EPI_BF16_RELU: return launch_gemm<BN, TGB_EPI_BF16_RELU, CG>(A, lda, W, ldw, p, s);
+    case TGB_EPI_BF16_LN: return launch_gemm<BN, TGB_EPI_BF16_LN, CG>(A, lda, W, ldw, p, s);
+    case TGB_EPI_BF16_GELU_LN: return launch_gemm<BN, TGB_EPI_BF16_GELU_LN, CG>(A, lda, W, ldw, p, s);
+    case TGB_EPI_F32_RESID_STATS: return launch_gemm<BN, TGB_EPI_F32_RESID_STATS, CG>(A, lda, W, ldw, p, s);
   }
   set_last_error("unknown epilogue %d", p.epi);
   return TGB_EINVAL;
@@ -463,9 +534,10 @@ extern "C" int tgb_gemm_set_cta_group(int cta_group) {
   return TGB_OK;
 }
 
-extern "C" int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
-                             const float* bias, const float* resid, int64_t ldr, const float* rowbias, int period,
-                             int skip, void* out, int64_t ldo, int bn, tgb_stream_t stream) {
+static int gemm_entry(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
+                      const float* bias, const float* resid, int64_t ldr, const float* rowbias, int period, int skip,
+                      void* out, int64_t ldo, int bn, const float* rowstats, const float* colsum, void* out_bf16,
+                      int64_t ldo2, float* partial_stats, tgb_stream_t stream) {
   int st = check_device();
   if (st != TGB_OK) return st;
   TGB_CHECK_ARG(A && W && out, "gemm: null pointer");
@@ -476,19 +548,60 @@ extern "C" int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
                 "gemm: A, W, out must be 16-byte aligned");
   TGB_CHECK_ARG(ldo % 8 == 0 && ldo >= N, "gemm: ldo must be a multiple of 8 and >= N");
   TGB_CHECK_ARG(bias == nullptr || ((uintptr_t)bias % 16) == 0, "gemm: bias must be 16-byte aligned");
-  if (epilogue == TGB_EPI_F32_RESID)
+  if (epilogue == TGB_EPI_F32_RESID || epilogue == TGB_EPI_F32_RESID_STATS)
     TGB_CHECK_ARG(resid && ldr % 4 == 0 && ldr >= N && ((uintptr_t)resid % 16) == 0, "gemm: bad residual");
   if (epilogue == TGB_EPI_F32_ROWBIAS)
     TGB_CHECK_ARG(rowbias && period > 0 && skip >= 0 && ((uintptr_t)rowbias % 16) == 0, "gemm: bad rowbias");
+  if (epilogue == TGB_EPI_BF16_LN || epilogue == TGB_EPI_BF16_GELU_LN)
+    TGB_CHECK_ARG(rowstats && colsum && ((uintptr_t)rowstats % 8) == 0 && ((uintptr_t)colsum % 16) == 0,
+                  "gemm: the LayerNorm-fold epilogues need rowstats [M,2] and colsum [N]");
+  if (epilogue == TGB_EPI_F32_RESID_STATS)
+    TGB_CHECK_ARG(out_bf16 && partial_stats && ldo2 % 8 == 0 && ldo2 >= N && ((uintptr_t)out_bf16 % 16) == 0 &&
+                      ((uintptr_t)partial_stats % 8) == 0,
+                  "gemm: the statistics epilogue needs out_bf16 (ld %% 8 == 0) and partial_stats");
   int auto_bn, cg;
   choose_tile(M, N, &auto_bn, &cg);
   if (bn == 0) bn = auto_bn;
+  // the statistics slots are (256-column tile, epilogue warp) pairs: keeping that partition independent of M keeps a
+  // row's statistics -- and with them the whole encoder -- bit-identical whatever batch the row is encoded in
+  if (epilogue == TGB_EPI_F32_RESID_STATS) bn = 256;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.epi = epilogue;
   p.num_m_blocks = p.num_n_blocks = p.num_k_blocks = 0;
   p.period = period > 0 ? period : 1; p.skip = skip;
   p.bias = bias; p.resid = resid; p.rowbias = rowbias; p.out = out; p.ldo = ldo; p.ldr = ldr;
+  p.rowstats = rowstats; p.colsum = colsum; p.out2 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo2 = ldo2;
+  p.pstats = reinterpret_cast<float2*>(partial_stats);
+  p.nslots = ((N + bn - 1) / bn) * 4;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (cg == 2) return dispatch_bn<2>(bn, A, lda, W, ldw, p, s);
   return dispatch_bn<1>(bn, A, lda, W, ldw, p, s);
+}
+
+extern "C" int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
+                             const float* bias, const float* resid, int64_t ldr, const float* rowbias, int period,
+                             int skip, void* out, int64_t ldo, int bn, tgb_stream_t stream) {
+  if (epilogue == TGB_EPI_BF16_LN || epilogue == TGB_EPI_BF16_GELU_LN || epilogue == TGB_EPI_F32_RESID_STATS) {
+    set_last_error("gemm: epilogue %d takes the extra operands of tgb_gemm_bf16_ln", epilogue);
+    return TGB_EINVAL;
+  }
+  return gemm_entry(A, lda, W, ldw, M, N, K, epilogue, bias, resid, ldr, rowbias, period, skip, out, ldo, bn, nullptr,
+                    nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int tgb_gemm_ln_stats_slots(int M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  return ((N + 255) / 256) * 4;
+}
+
+extern "C" int tgb_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
+                                const float* bias, const float* resid, int64_t ldr, const float* rowstats,
+                                const float* colsum, void* out, int64_t ldo, void* out_bf16, int64_t ldo2,
+                                float* partial_stats, tgb_stream_t stream) {
+  if (epilogue != TGB_EPI_BF16_LN && epilogue != TGB_EPI_BF16_GELU_LN && epilogue != TGB_EPI_F32_RESID_STATS) {
+    set_last_error("gemm_ln: epilogue must be TGB_EPI_BF16_LN, TGB_EPI_BF16_GELU_LN or TGB_EPI_F32_RESID_STATS");
+    return TGB_EINVAL;
+  }
+  return gemm_entry(A, lda, W, ldw, M, N, K, epilogue, bias, resid, ldr, nullptr, 0, 0, out, ldo, 0, rowstats, colsum,
+                    out_bf16, ldo2, partial_stats, stream);
 }

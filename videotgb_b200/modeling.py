@@ -162,6 +162,9 @@ class Blip2VisionModel(_KernelModule):
         self.tokens = (self.image // self.patch) ** 2 + 1
         self.max_frames_per_pass = int(os.environ.get("TGB_FRAMES_PER_PASS", max_frames_per_pass))   # tuning knob
         self.use_tc_attention = True
+        # layer_norm1 / layer_norm2 folded into the qkv / fc1 GEMMs (statistics from the residual GEMMs' epilogues);
+        # False keeps the separate LayerNorm pass (cross-check; call _invalidate() after changing it)
+        self.fuse_layernorm = os.environ.get("TGB_FUSE_LN", "1") != "0"
         self.embeddings = _Holder()
         self.embeddings.class_embedding = nn.Parameter(torch.randn(1, 1, d) * 0.02)
         self.embeddings.position_embedding = nn.Parameter(torch.randn(1, self.tokens, d) * 0.02)
@@ -199,8 +202,17 @@ class Blip2VisionModel(_KernelModule):
             kpad=kpad, patch_w=pw,
             patch_rowbias=(pos[1:] + self.embeddings.patch_embedding.bias.detach().float()).contiguous(),
             cls=self._f32(self.embeddings.class_embedding.reshape(-1)), pos0=pos[0].contiguous(),
+            fused=bool(self.fuse_layernorm),
             layers=[], post=(self._f32(self.post_layernorm.weight), self._f32(self.post_layernorm.bias)))
         for lyr in self.encoder.layers:
+            if pk.fused:
+                qkv_w, qkv_c1, qkv_b = self._fold_ln(lyr.layer_norm1, lyr.self_attn.qkv)
+                fc1_w, fc1_c1, fc1_b = self._fold_ln(lyr.layer_norm2, lyr.mlp.fc1)
+                pk.layers.append(SimpleNamespace(
+                    qkv_w=qkv_w, qkv_c1=qkv_c1, qkv_b=qkv_b, fc1_w=fc1_w, fc1_c1=fc1_c1, fc1_b=fc1_b,
+                    proj_w=self._bf16(lyr.self_attn.projection.weight), proj_b=self._f32(lyr.self_attn.projection.bias),
+                    fc2_w=self._bf16(lyr.mlp.fc2.weight), fc2_b=self._f32(lyr.mlp.fc2.bias)))
+                continue
             pk.layers.append(SimpleNamespace(
                 ln1=(self._f32(lyr.layer_norm1.weight), self._f32(lyr.layer_norm1.bias)),
                 ln2=(self._f32(lyr.layer_norm2.weight), self._f32(lyr.layer_norm2.bias)),
@@ -210,6 +222,16 @@ class Blip2VisionModel(_KernelModule):
                 fc2_w=self._bf16(lyr.mlp.fc2.weight), fc2_b=self._f32(lyr.mlp.fc2.bias)))
         self._packed = pk
         return pk
+
+    @staticmethod
+    def _fold_ln(ln: "_LayerNorm", lin: "_Linear"):
+        """LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (W beta + b) with W' = W * gamma: the bf16 operand W',
+        its row sums (of the ROUNDED operand, so the mean term cancels exactly what the tensor cores add) and bias'."""
+        w = lin.weight.detach().float()
+        wf = (w * ln.weight.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+        colsum = wf.float().sum(dim=1).contiguous()
+        bias = (w @ ln.bias.detach().float() + lin.bias.detach().float()).contiguous()
+        return wf, colsum, bias
 
     # -- the frame-batched encoder (A10-A13)
     def _encode(self, pk, cols: torch.Tensor, nf: int, last: torch.Tensor, last_bf16: Optional[torch.Tensor]):
@@ -225,13 +247,34 @@ class Blip2VisionModel(_KernelModule):
         hid = torch.empty((m, self.mlp), dtype=torch.bfloat16, device=dev)
         scale = self.head_dim ** -0.5
         tc_attn = self.use_tc_attention and (h, self.head_dim, s) == (16, 88, 257)
-        for lw in pk.layers:
-            ops.layernorm(x, lw.ln1[0], lw.ln1[1], self.eps, out_bf16=ln)
-            ops.gemm(ln, lw.qkv_w, lw.qkv_b, ops.EPI_BF16, out=qkv)
+
+        def attend():
             if tc_attn:      # EVA-ViT-g shape: tcgen05 attention (S in TMEM, P as TMEM operand, V MN-major)
                 ops.vit_attention(qkv, nf, scale, out=ctx)
             else:            # any other ViT shape: generic mma.sync flash kernel
                 ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nf, h, s, s, self.head_dim, scale, out=ctx)
+
+        if pk.fused:
+            # `ln` holds the bf16 copy of the UN-normalised residual rows; the LayerNorms live in the GEMM epilogues:
+            # the residual GEMMs emit that copy plus per-row partial (sum, sum of squares), a tiny kernel turns them into
+            # (mean, rstd), and the qkv / fc1 GEMMs apply rstd * (acc - mean * colsum) + bias'
+            stats = torch.empty((m, 2), dtype=torch.float32, device=dev)
+            part = torch.empty((m, ops.ln_stats_slots(m, d), 2), dtype=torch.float32, device=dev)
+            ops.rowstats_cast(x, self.eps, ln, stats)
+            for lw in pk.layers:
+                ops.gemm_ln(ln, lw.qkv_w, lw.qkv_b, ops.EPI_BF16_LN, qkv, rowstats=stats, colsum=lw.qkv_c1)
+                attend()
+                ops.gemm_ln(ctx, lw.proj_w, lw.proj_b, ops.EPI_F32_RESID_STATS, x, resid=x, out_bf16=ln, partial_stats=part)
+                ops.ln_stats_finalize(part, d, self.eps, stats)
+                ops.gemm_ln(ln, lw.fc1_w, lw.fc1_b, ops.EPI_BF16_GELU_LN, hid, rowstats=stats, colsum=lw.fc1_c1)
+                ops.gemm_ln(hid, lw.fc2_w, lw.fc2_b, ops.EPI_F32_RESID_STATS, x, resid=x, out_bf16=ln, partial_stats=part)
+                ops.ln_stats_finalize(part, d, self.eps, stats)
+            ops.layernorm(x, pk.post[0], pk.post[1], self.eps, out_bf16=last_bf16, out_f32=last)
+            return
+        for lw in pk.layers:
+            ops.layernorm(x, lw.ln1[0], lw.ln1[1], self.eps, out_bf16=ln)
+            ops.gemm(ln, lw.qkv_w, lw.qkv_b, ops.EPI_BF16, out=qkv)
+            attend()
             ops.gemm(ctx, lw.proj_w, lw.proj_b, ops.EPI_F32_RESID, out=x, resid=x)
             ops.layernorm(x, lw.ln2[0], lw.ln2[1], self.eps, out_bf16=ln)
             ops.gemm(ln, lw.fc1_w, lw.fc1_b, ops.EPI_BF16_GELU, out=hid)

@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import check
 
 EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_F32_ROWBIAS, EPI_BF16_RELU = range(6)
+EPI_BF16_LN, EPI_BF16_GELU_LN, EPI_F32_RESID_STATS = 6, 7, 8       # LayerNorm folded into the GEMMs (gemm_ln)
 MAP_SCALED, MAP_RATIO = 0, 1
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -230,6 +231,90 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         e1.record()
         _PROFILE.append(("gemm", (m, n, k, epilogue), e0, e1))
     return out
+
+
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int, out: torch.Tensor,
+            rowstats: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+            resid: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
+            partial_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The LayerNorm-fold GEMMs (include/videotgb_b200.h, tgb_gemm_bf16_ln).
+    EPI_BF16_LN / EPI_BF16_GELU_LN: out bf16 = act(rstd_m * (a @ w.T - mean_m * colsum) + bias), rowstats f32 [M,2].
+    EPI_F32_RESID_STATS: out f32 = a @ w.T + bias + resid, out_bf16 = bf16(out), partial_stats f32 [M, slots, 2]."""
+    _need(a, torch.bfloat16, "a", contiguous=False)
+    _need(w, torch.bfloat16, "w", contiguous=False)
+    m, k, lda = _rows(a, "a")
+    n, kw, ldw = _rows(w, "w")
+    if k != kw:
+        raise _lib.TgbError(f"gemm_ln: K mismatch {k} vs {kw}")
+    producer = epilogue == EPI_F32_RESID_STATS
+    _need(out, torch.float32 if producer else torch.bfloat16, "out", contiguous=False)
+    mo, n_out, ldo = _rows(out, "out")
+    if n_out != n or mo != m:
+        raise _lib.TgbError("gemm_ln: out has the wrong shape")
+    _need(bias, torch.float32, "bias")
+    ldr = ldo2 = 0
+    if producer:
+        _need(resid, torch.float32, "resid", contiguous=False)
+        _, _, ldr = _rows(resid, "resid")
+        _need(out_bf16, torch.bfloat16, "out_bf16", contiguous=False)
+        m2, n2, ldo2 = _rows(out_bf16, "out_bf16")
+        _need(partial_stats, torch.float32, "partial_stats")
+        if (m2, n2) != (m, n) or partial_stats.numel() != m * ln_stats_slots(m, n) * 2:
+            raise _lib.TgbError("gemm_ln: out_bf16 / partial_stats have the wrong shape")
+    else:
+        _need(rowstats, torch.float32, "rowstats")
+        _need(colsum, torch.float32, "colsum")
+        if rowstats.numel() != 2 * m or colsum.numel() != n:
+            raise _lib.TgbError("gemm_ln: rowstats must be [M,2] and colsum [N]")
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.load().tgb_gemm_bf16_ln(_p(a), lda, _p(w), ldw, m, n, k, epilogue, _p(bias), _p(resid), ldr, _p(rowstats),
+                                       _p(colsum), _p(out), ldo, _p(out_bf16), ldo2, _p(partial_stats), _stream()))
+    if _PROFILE is not None:
+        e1.record()
+        _PROFILE.append(("gemm", (m, n, k, epilogue), e0, e1))
+    return out
+
+
+def ln_stats_slots(m: int, n: int) -> int:
+    """Partial-statistics slots per row the EPI_F32_RESID_STATS epilogue writes for an [m, n] output."""
+    return int(_lib.load().tgb_gemm_ln_stats_slots(int(m), int(n)))
+
+
+def ln_stats_finalize(partial_stats: torch.Tensor, n: int, eps: float, rowstats: torch.Tensor) -> torch.Tensor:
+    """partial_stats f32 [M, slots, 2] (sum, sum of squares) -> rowstats f32 [M, 2] (mean, rstd)."""
+    _need(partial_stats, torch.float32, "partial_stats")
+    _need(rowstats, torch.float32, "rowstats")
+    m, slots, two = partial_stats.shape
+    if two != 2 or rowstats.shape != (m, 2):
+        raise _lib.TgbError("ln_stats_finalize: partial_stats must be [M, slots, 2] and rowstats [M, 2]")
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.load().tgb_ln_stats_finalize(_p(partial_stats), m, slots, int(n), float(eps), _p(rowstats), _stream()))
+    if _PROFILE is not None:
+        e1.record()
+        _PROFILE.append(("layernorm", (m, n, "finalize"), e0, e1))
+    return rowstats
+
+
+def rowstats_cast(x: torch.Tensor, eps: float, out_bf16: torch.Tensor, rowstats: torch.Tensor) -> None:
+    """x f32 [M,N] -> bf16 copy + (mean, rstd) per row (LayerNorm fold, rows that did not come out of a GEMM)."""
+    _need(x, torch.float32, "x", contiguous=False)
+    m, n, ldx = _rows(x, "x")
+    _need(out_bf16, torch.bfloat16, "out_bf16", contiguous=False)
+    m2, n2, ldo = _rows(out_bf16, "out_bf16")
+    _need(rowstats, torch.float32, "rowstats")
+    if (m2, n2) != (m, n) or rowstats.shape != (m, 2):
+        raise _lib.TgbError("rowstats_cast: shape mismatch")
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.load().tgb_rowstats_cast_f32(_p(x), ldx, m, n, float(eps), _p(out_bf16), ldo, _p(rowstats), _stream()))
+    if _PROFILE is not None:
+        e1.record()
+        _PROFILE.append(("layernorm", (m, n, "rowstats"), e0, e1))
 
 
 def gemm_set_cta_group(cta_group: int) -> None:
