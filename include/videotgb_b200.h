@@ -124,7 +124,7 @@ TGB_API int tgb_fill_cls_rows(float* hidden, const float* cls, const float* pos0
  *   TGB_EPI_F32_ROWBIAS out f32 row (m/period)*(period+skip)+skip+m%period = acc + rowbias[m%period, n]
  *                       (patch-embed: bias+position_embedding folded into rowbias, CLS row skipped)
  *   TGB_EPI_BF16_RELU   out bf16 = relu(acc + bias)                               (RAFT convolutions)
- * N % 8 == 0.  bn: 0 = choose, else force the N tile (256/176/128/64).                                      */
+ * N % 8 == 0.  bn: 0 = choose, else force the N tile (256/128/64).                                      */
 enum { TGB_EPI_BF16 = 0, TGB_EPI_BF16_GELU = 1, TGB_EPI_F32 = 2, TGB_EPI_F32_RESID = 3, TGB_EPI_F32_ROWBIAS = 4,
        TGB_EPI_BF16_RELU = 5, TGB_EPI_BF16_LN = 6, TGB_EPI_BF16_GELU_LN = 7, TGB_EPI_F32_RESID_STATS = 8 };
 TGB_API int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,

@@ -235,7 +235,7 @@ def _gemm_ref(a, w, bias):
 GEMM_SHAPES = [
     # (M, N, K, bn)
     (128, 256, 64, 256), (128, 256, 128, 256), (256, 512, 256, 256), (300, 264, 200, 256),
-    (257 * 4, 1408, 1408, 0), (257 * 4, 1408, 1408, 176), (257 * 4, 1408, 1408, 128), (257 * 4, 4224, 1408, 0),
+    (257 * 4, 1408, 1408, 0), (257 * 4, 1408, 1408, 128), (257 * 4, 4224, 1408, 0),
     (1000, 6144, 1408, 256), (520, 1408, 6144, 0), (256 * 3, 1408, 592, 0), (96, 768, 768, 64), (4097, 768, 3072, 0),
     (37, 2048, 768, 0), (128, 8, 64, 64),
 ]

@@ -1,4 +1,4 @@
-"""Interleaved A/B of the N-tile width (bn = 256 / 176 / 128) for the two residual GEMMs of a ViT layer."""
+"""Interleaved A/B of the N-tile width (bn = 256 / 128) for the two residual GEMMs of a ViT layer."""
 import os
 import statistics
 import sys
@@ -24,7 +24,7 @@ def main():
     for rnd in range(7):
         for name, m, n, k, epi in SHAPES:
             a, w, bias, out = bufs[name]
-            for bn in (0, 176, 128):
+            for bn in (0, 128):
                 fn = (lambda: ops.gemm(a, w, bias, epi, out=out, resid=out, bn=bn)) if epi == ops.EPI_F32_RESID else \
                      (lambda: ops.gemm(a, w, bias, epi, out=out, bn=bn))
                 try:
@@ -37,7 +37,7 @@ def main():
     for name, m, n, k, epi in SHAPES:
         fl = 2.0 * m * n * k
         print(name, "  ".join(f"bn={bn or 256}: {statistics.median(res[(name, bn)]):.3f} ms {fl / statistics.median(res[(name, bn)]) / 1e9:6.0f} TF"
-                              for bn in (0, 176, 128)))
+                              for bn in (0, 128)))
 
 
 if __name__ == "__main__":

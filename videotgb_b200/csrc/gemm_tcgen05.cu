@@ -21,6 +21,10 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#ifndef TGB_GEMM_X
+#define TGB_GEMM_X 0        // tools/gemm_limits.py builds variants: bit 0 = skip TMA loads (stale operands), bit 1 = skip epilogue
+#endif
+
 namespace tgb {
 
 constexpr int BM = 128;          // rows per CTA
@@ -59,10 +63,12 @@ template <int EPI> struct EpiTraits {
 
 // EW = number of epilogue warps (8 or 16: 2 or 4 per TMEM lane quarter).  16 hides the global-memory latency of the
 // residual read-modify-write; 8 leaves room for one more pipeline stage.
-template <int BN, int CG, int EW>
+// ROWEPI = the bf16 epilogue (lane == row, 64-column pieces staged as a SWIZZLE_128B [32 x 64] bf16 box per warp and
+// written with one bulk tensor store); otherwise the transposing fp32 epilogue (padded [32 x 16] fp32 tile per warp).
+template <int BN, int CG, int EW, bool ROWEPI>
 struct GemmCfg {
   static constexpr int THREADS = 128 + EW * 32;
-  static constexpr int STG_BYTES = EW * 32 * STG_PITCH * 4;
+  static constexpr int STG_BYTES = ROWEPI ? EW * 4096 : EW * 32 * STG_PITCH * 4;
   static constexpr int B_ROWS = BN / CG;                 // W rows staged per CTA
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
@@ -71,7 +77,7 @@ struct GemmCfg {
   static constexpr int BUDGET = 227 * 1024 - 1024 - STG_BYTES - BAR_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES < 8 ? BUDGET / STAGE_BYTES : 8;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES;
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint");
+  static_assert(BN == 256 || BN == 128 || BN == 64, "N tiles are whole 64-column epilogue pieces");
   static_assert(B_ROWS % 8 == 0, "W half tile must be whole swizzle atoms");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must stay 1024-B aligned for SWIZZLE_128B");
   static_assert(2 * BN <= (int)TMEM_COLS, "two accumulators must fit TMEM");
@@ -80,8 +86,8 @@ struct GemmCfg {
 // Epilogue math on 4 consecutive columns of one output row (transposed mapping: 4 lanes cover a 16-column row chunk,
 // so a warp instruction touches 8 rows x 64 contiguous bytes instead of 32 scattered rows).
 template <int EPI>
-__device__ __forceinline__ float4 epilogue_store4(const GemmParams& p, float4 acc, const float4& bias4, const float4& res,
-                                                  const float4& cs4, float nmean, float rstd, long long out_row, int col) {
+__device__ __forceinline__ float4 epilogue_math4(float4 acc, const float4& bias4, const float4& res, const float4& cs4,
+                                                 float nmean, float rstd) {
   using T = EpiTraits<EPI>;
   // packed fp32 pairs (FFMA2 / FADD2): half the FP32-pipe instructions of the scalar form
   float2 lo = make_float2(acc.x, acc.y), hi = make_float2(acc.z, acc.w);
@@ -105,6 +111,14 @@ __device__ __forceinline__ float4 epilogue_store4(const GemmParams& p, float4 ac
   if (EPI == TGB_EPI_BF16_RELU) {
     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
   }
+  return v;
+}
+
+template <int EPI>
+__device__ __forceinline__ float4 epilogue_store4(const GemmParams& p, float4 acc, const float4& bias4, const float4& res,
+                                                  const float4& cs4, float nmean, float rstd, long long out_row, int col) {
+  using T = EpiTraits<EPI>;
+  const float4 v = epilogue_math4<EPI>(acc, bias4, res, cs4, nmean, rstd);
   if (T::OUT_BF16) {
     uint2 o;
     o.x = pack_bf16(v.x, v.y);
@@ -125,8 +139,8 @@ __device__ __forceinline__ float4 epilogue_store4(const GemmParams& p, float4 ac
 template <int BN, int EPI, int CG, int EW>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                         const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG, EW>;
+                         const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
+  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::OUT_BF16>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int STG_BYTES = Cfg::STG_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -186,7 +200,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          if (CG == 1) {
+          if (TGB_GEMM_X & 1) {
+            if (leader) mbar_arrive(&full_bar[stage]);
+          } else if (CG == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, a_row);
             tma_load_2d(sa + Cfg::A_BYTES, &tma_b, &full_bar[stage], kb * BK, b_row);
@@ -235,8 +251,92 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
     }
     __syncwarp();
+  } else if (warp < EW && EpiTraits<EPI>::OUT_BF16) {
+    // ------------------------------------------------------------- bf16 epilogue (EW warps), lane == output row
+    // A warp owns 32 rows (its TMEM lane quarter) x 64-column pieces sub, sub+NSUB, ...  Each lane reads its row piece
+    // with two 32-column tcgen05.ld, applies bias / LayerNorm fold / GELU in packed fp32, rounds to bf16 and writes the
+    // 128-byte row into the warp's SWIZZLE_128B staging box (conflict-free 16-byte units); one elected lane turns the
+    // box into a bulk tensor store, which also clips the M / N tails.  ~2 instructions per element outside the
+    // activation math (the transposing epilogue below needs ~6: per-row addresses, predicates, LDS + STG).
+    using T = EpiTraits<EPI>;
+    const int quarter = warp & 3;
+    const int sub = warp >> 2;
+    constexpr int NSUB = EW / 4;
+    constexpr int CW = 64;
+    constexpr int NPIECE = BN / CW;
+    uint8_t* box = reinterpret_cast<uint8_t*>(staging) + warp * 4096;
+    const uint32_t my_row = smem_u32(box) + lane * 128;
+    const uint32_t sw = lane & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t empty0 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+    const uint32_t empty1 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u;
+    if (lane == 0) tma_prefetch_desc(&tma_c);
+    const bool has_bias = p.bias != nullptr;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile - m_blk * p.num_n_blocks;
+      const int row_base = (m_blk * CG + (int)rank) * BM + quarter * 32;
+      const int col0 = n_blk * BN;
+      float nmean = 0.f, rstd = 0.f;
+      if (T::LN && row_base + lane < p.M) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.rowstats) + (row_base + lane));
+        nmean = -st.x;
+        rstd = st.y;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int j = sub; j < NPIECE; j += NSUB) {
+        const int col = col0 + j * CW;
+        if (col >= p.N) break;                       // warp-uniform
+        if (TGB_GEMM_X & 2) break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32_nomem(t_row + j * CW + h * 32, v);
+          if (h == 0 && lane == 0) bulk_wait_read0();     // the previous store has read the box (overlaps the TMEM load)
+          tmem_ld_wait_dep32(v);
+          if (h == 0) __syncwarp();
+          uint32_t pk[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            // columns >= N are clipped by the tensor store, so their bias may be anything: clamp instead of predicating
+            const int c = min(col + h * 32 + q * 4, p.N - 4);
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+            if (T::LN) cs4 = __ldg(reinterpret_cast<const float4*>(p.colsum + c));
+            const float4 a = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            const float4 r = epilogue_math4<EPI>(a, bias4, bias4, cs4, nmean, rstd);
+            pk[2 * q] = pack_bf16(r.x, r.y);
+            pk[2 * q + 1] = pack_bf16(r.z, r.w);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (((h * 4 + u) ^ sw) << 4)),
+                         "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row_base < p.M) {
+          tma_store_2d(&tma_c, box, col, row_base);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(acc == 0 ? empty0 : empty1);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) bulk_wait0();                     // every store has landed before the CTA may exit
+    __syncwarp();
   } else if (warp < EW) {
-    // ------------------------------------------------------------- epilogue (EW warps)
+    // ------------------------------------------------------------- fp32 epilogue (EW warps), transposing
     // TMEM hands every thread one ROW (lane == row) of a 16-column chunk.  The chunk is transposed through a padded
     // per-warp shared-memory tile so that the global side is coalesced: thread -> (row = i*8 + lane/4, 4 columns at
     // (lane%4)*4), i.e. 64 contiguous bytes per row and 8 rows per instruction for the residual read and the store.
@@ -301,6 +401,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       for (int j = sub; j < NCHUNK; j += NSUB) {
         const int col = col0 + j * 16;
         if (col >= p.N) break;                       // warp-uniform
+        if (TGB_GEMM_X & 2) break;
         uint32_t v[16];
         tmem_ld_32x32b_x16_nomem(t_row + j * 16, v);
         float4 rcur[4];
@@ -406,13 +507,34 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
   return TGB_OK;
 }
 
+// bf16 output [M, N] (leading dim ldo) -> tensor map with the epilogue's [32 rows x 64 columns] SWIZZLE_128B store box
+static int make_tmap_out(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return TGB_ECUDA;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (output) failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+    return TGB_ECUDA;
+  }
+  return TGB_OK;
+}
+
 static int g_force_cg = 0;     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
 static int g_force_ew = 0;     // 0 = choose per epilogue, 8 / 16 = force
 
 template <int BN, int EPI, int CG, int EW>
 static int launch_gemm_ew(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, EW>;
+  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::OUT_BF16>;
   p.num_m_blocks = (p.M + BM * CG - 1) / (BM * CG);
   p.num_n_blocks = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
@@ -421,6 +543,11 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
   if (st != TGB_OK) return st;
   st = make_tmap(&tb, W, p.N, p.K, ldw, Cfg::B_ROWS);
   if (st != TGB_OK) return st;
+  CUtensorMap tc = ta;                                   // unused by the fp32 epilogues
+  if (EpiTraits<EPI>::OUT_BF16) {
+    st = make_tmap_out(&tc, p.out, p.M, p.N, p.ldo);
+    if (st != TGB_OK) return st;
+  }
   auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, EW>;
   static bool configured = false;
   if (!configured) {
@@ -442,7 +569,7 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  TGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   return TGB_OK;
 }
 
@@ -478,18 +605,17 @@ static int dispatch_bn(int bn, const void* A, long long lda, const void* W, long
                        cudaStream_t s) {
   switch (bn) {
     case 256: return dispatch_epi<256, CG>(A, lda, W, ldw, p, s);
-    case 176: return dispatch_epi<176, CG>(A, lda, W, ldw, p, s);
     case 128: return dispatch_epi<128, CG>(A, lda, W, ldw, p, s);
     case 64: return dispatch_epi<64, CG>(A, lda, W, ldw, p, s);
   }
-  set_last_error("gemm: unsupported N tile %d (256/176/128/64)", bn);
+  set_last_error("gemm: unsupported N tile %d (256/128/64)", bn);
   return TGB_EINVAL;
 }
 
 // Tile choice: minimise the MMA time of the busiest SM; narrower tiles pay more operand traffic per flop.
 static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
-  // measured on B200: a tcgen05.mma with N=176 costs as much as N=256 (N is processed in 128-wide passes), so 176
-  // is only reachable by forcing bn; prefer 256, then 128.
+  // measured on B200: a tcgen05.mma with N=176 costs as much as N=256 (N is processed in 128-wide passes), so the
+  // tiles are 256 / 128 / 64 wide; prefer 256, then 128.
   const int cands[4] = {256, 128, 64, 64};
   int best_bn = 256, best_cg = 2;
   double best_cost = -1.0;
@@ -502,7 +628,7 @@ static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
       const long long tiles = nblocks * mblocks;
       const long long slots = sm_count() / cg;
       const long long waves = (tiles + slots - 1) / slots;
-      double eff = bn >= 176 ? 1.0 : (bn == 128 ? 0.9 : 0.75);
+      double eff = bn >= 256 ? 1.0 : (bn == 128 ? 0.9 : 0.75);
       if (cg == 1) eff *= 0.9;
       const double cost = (double)waves * bn / eff;
       if (best_cost < 0 || cost < best_cost * 0.999) { best_cost = cost; best_bn = bn; best_cg = cg; }
