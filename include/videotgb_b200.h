@@ -138,7 +138,7 @@ TGB_API int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw
  *                       bias = bias', rowstats f32 [M,2] = (mean, rstd) per row, colsum f32 [N]
  *   TGB_EPI_F32_RESID_STATS                  producer: out f32 = acc + bias + resid (as TGB_EPI_F32_RESID), plus
  *                       out_bf16 [M, ldo2] = bf16(out) and partial_stats f32 [M, slots, 2] = (sum, sum of squares) of
- *                       each row over the columns of one slot; slots = tgb_gemm_ln_stats_slots(M, N); every slot is
+ *                       each row over the columns of one slot; slots = tgb_gemm_ln_stats_slots(M, N) (two per 256-column tile); every slot is
  *                       written exactly once per launch (no atomics: results are run-to-run deterministic)
  * tgb_ln_stats_finalize reduces the slots to rowstats (float64 combine, biased variance, rstd = 1/sqrt(var + eps));
  * tgb_rowstats_cast_f32 produces rowstats and the bf16 copy for rows that did not come out of a GEMM (first layer).  */
@@ -153,7 +153,7 @@ TGB_API int tgb_rowstats_cast_f32(const float* x, int64_t ldx, int M, int N, flo
 
 /* Debug / test knob: 0 = choose per problem (default), 1 = single-CTA 128xBN tiles, 2 = CTA-pair 256xBN tiles.      */
 TGB_API int tgb_gemm_set_cta_group(int cta_group);
-/* Debug / test knob: epilogue warps per CTA, 0 = choose per epilogue (16 for the residual epilogue, else 8).               */
+/* Debug / test knob: epilogue warps per CTA, 0 = choose (8; the fp32-residual epilogues always run 8).               */
 TGB_API int tgb_gemm_set_epilogue_warps(int warps);
 
 /* ---------------------------------------------------------------- LayerNorm ---------------------------

@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvideotgb_b200.so")
+LIB_PATH = os.environ.get("TGB_LIB") or os.path.join(_HERE, "libvideotgb_b200.so")    # TGB_LIB: experiment builds (tools/)
 
 TGB_OK, TGB_EINVAL, TGB_EARCH, TGB_ECUDA = 0, -1, -2, -3
 

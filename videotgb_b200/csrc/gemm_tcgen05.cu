@@ -21,10 +21,6 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
-#ifndef TGB_GEMM_X
-#define TGB_GEMM_X 0        // tools/gemm_limits.py builds variants: bit 0 = skip TMA loads (stale operands), bit 1 = skip epilogue
-#endif
-
 namespace tgb {
 
 constexpr int BM = 128;          // rows per CTA
@@ -59,21 +55,34 @@ template <int EPI> struct EpiTraits {
   static constexpr bool RESID = EPI == TGB_EPI_F32_RESID || STATS;
   static constexpr bool GELU = EPI == TGB_EPI_BF16_GELU || EPI == TGB_EPI_BF16_GELU_LN;
   static constexpr bool OUT_BF16 = EPI == TGB_EPI_BF16 || EPI == TGB_EPI_BF16_RELU || GELU || LN;
+  static constexpr int FAM = OUT_BF16 ? 1 : (RESID ? 2 : 0);
 };
 
 // EW = number of epilogue warps (8 or 16: 2 or 4 per TMEM lane quarter).  16 hides the global-memory latency of the
 // residual read-modify-write; 8 leaves room for one more pipeline stage.
-// ROWEPI = the bf16 epilogue (lane == row, 64-column pieces staged as a SWIZZLE_128B [32 x 64] bf16 box per warp and
-// written with one bulk tensor store); otherwise the transposing fp32 epilogue (padded [32 x 16] fp32 tile per warp).
-template <int BN, int CG, int EW, bool ROWEPI>
+// Epilogue families (per-warp staging in shared memory):
+//   FAM_T    transposing fp32 epilogue (F32, F32_ROWBIAS): padded [32 x 16] fp32 tile per warp
+//   FAM_BF16 lane == row, 64-column pieces staged as a SWIZZLE_128B [32 x 64] bf16 box, one bulk tensor store each
+//   FAM_RES  lane == row, 16-column pieces: the fp32 residual piece arrives by bulk tensor LOAD into a SWIZZLE_64B
+//            [32 x 16] fp32 box (ring of three: loads run two pieces ahead), is updated in place and leaves by bulk
+//            tensor store, plus a bf16 copy box for the statistics-producing variant
+constexpr int FAM_BF16 = 1, FAM_RES = 2;           // (0 = FAM_T)
+constexpr int RES_BOX_BYTES = 32 * 16 * 4, RES_COPY_BYTES = 32 * 16 * 2;
+// residual boxes per warp: loads run RES_NBOX-1 pieces ahead.  Measured (tools/gemm_ab.py, profiles/r1_gemm_ab_nbox.txt):
+// rings of 2 / 3 / 4 boxes and an extra L2 prefetch of the tile's residual by the TMA producer all land within 2 % of
+// each other -- the residual GEMMs are bound by the power their DRAM traffic takes from the tensor cores, not by latency.
+constexpr int RES_NBOX = 3;
+constexpr int RES_WARP_BYTES = RES_NBOX * RES_BOX_BYTES + 2 * RES_COPY_BYTES;
+
+template <int BN, int CG, int EW, int FAM>
 struct GemmCfg {
   static constexpr int THREADS = 128 + EW * 32;
-  static constexpr int STG_BYTES = ROWEPI ? EW * 4096 : EW * 32 * STG_PITCH * 4;
+  static constexpr int STG_BYTES = FAM == FAM_BF16 ? EW * 4096 : (FAM == FAM_RES ? EW * RES_WARP_BYTES : EW * 32 * STG_PITCH * 4);
   static constexpr int B_ROWS = BN / CG;                 // W rows staged per CTA
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;
   static constexpr int BUDGET = 227 * 1024 - 1024 - STG_BYTES - BAR_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES < 8 ? BUDGET / STAGE_BYTES : 8;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES;
@@ -139,8 +148,9 @@ __device__ __forceinline__ float4 epilogue_store4(const GemmParams& p, float4 ac
 template <int BN, int EPI, int CG, int EW>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                         const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::OUT_BF16>;
+                         const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
+                         const __grid_constant__ CUtensorMap tma_c2, const GemmParams p) {
+  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::FAM>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int STG_BYTES = Cfg::STG_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -151,6 +161,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = full_bar + 24;               // FAM_RES: RES_NBOX residual-box barriers per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -176,6 +187,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], CG * EW);  // lane 0 of every epilogue warp of every CTA of the pair
     }
+    if (EpiTraits<EPI>::FAM == FAM_RES)
+      for (int s = 0; s < RES_NBOX * EW; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == W_ALLOC) tmem_alloc_cg<CG>(tmem_slot, TMEM_COLS);
@@ -200,9 +213,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          if (TGB_GEMM_X & 1) {
-            if (leader) mbar_arrive(&full_bar[stage]);
-          } else if (CG == 1) {
+          if (CG == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, a_row);
             tma_load_2d(sa + Cfg::A_BYTES, &tma_b, &full_bar[stage], kb * BK, b_row);
@@ -291,7 +302,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       for (int j = sub; j < NPIECE; j += NSUB) {
         const int col = col0 + j * CW;
         if (col >= p.N) break;                       // warp-uniform
-        if (TGB_GEMM_X & 2) break;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
@@ -332,6 +342,147 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         else mbar_arrive_cluster(acc == 0 ? empty0 : empty1);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) bulk_wait0();                     // every store has landed before the CTA may exit
+    __syncwarp();
+  } else if (warp < EW && EpiTraits<EPI>::FAM == FAM_RES) {
+    // ------------------------------------------------------------- fp32 residual epilogue (EW warps), lane == output row
+    // out = acc + bias + resid.  A warp owns 32 rows x the 16-column pieces sub, sub+NSUB, ... of its tiles.  The residual
+    // piece is fetched by a bulk tensor load one piece AHEAD (across tile boundaries: it does not depend on the MMA),
+    // each lane adds its accumulator row to it in place in shared memory (SWIZZLE_64B: conflict-free 16-byte units) and
+    // an elected lane sends the box back with a bulk tensor store -- no per-row global addresses, predicates or LSU
+    // wavefronts per row; TMA zero-fills / clips the M and N tails.  The statistics variant also stages the bf16 copy
+    // and accumulates the row's (sum, sum of squares) in registers: the lane owns the row, so no shuffles.
+    using T = EpiTraits<EPI>;
+    const int quarter = warp & 3;
+    const int sub = warp >> 2;
+    constexpr int NSUB = EW / 4;
+    constexpr int NCHUNK = BN / 16;
+    uint8_t* wbase = reinterpret_cast<uint8_t*>(staging) + warp * RES_WARP_BYTES;
+    const uint32_t box0 = smem_u32(wbase);
+    const uint32_t copy0 = box0 + RES_NBOX * RES_BOX_BYTES;
+    const uint32_t sw = (lane >> 1) & 3;
+    uint64_t* my_full = res_full + RES_NBOX * warp;
+    const bool has_bias = p.bias != nullptr;
+    const uint32_t empty0 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+    const uint32_t empty1 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u;
+    if (lane == 0) {
+      tma_prefetch_desc(&tma_c);
+      tma_prefetch_desc(&tma_r);
+      if (T::STATS) tma_prefetch_desc(&tma_c2);
+    }
+    // piece iterator: (tile, j) with j = sub, sub+NSUB, ... while the piece starts inside N
+    auto piece_rows = [&](int tile) { return ((tile / p.num_n_blocks) * CG + (int)rank) * BM + quarter * 32; };
+    auto piece_col = [&](int tile, int j) { return (tile % p.num_n_blocks) * BN + j * 16; };
+    auto next_piece = [&](int& tile, int& j) {       // advance; returns false past the end
+      j += NSUB;
+      if (j >= NCHUNK || piece_col(tile, j) >= p.N) {
+        tile += num_clusters;
+        j = sub;
+      }
+      return tile < num_tiles;
+    };
+    auto issue_load = [&](int tile, int j, int b) {  // lane 0
+      mbar_arrive_expect_tx(&my_full[b], RES_BOX_BYTES);
+      tma_load_2d(wbase + b * RES_BOX_BYTES, &tma_r, &my_full[b], piece_col(tile, j), piece_rows(tile));
+    };
+    int tile = cluster_id, j = sub;
+    // (a piece that starts at or beyond N -- narrow problems, the half-empty last N tile -- is still walked: its load is
+    //  zero-filled and its store clipped, which keeps one accumulator hand-shake per tile for every warp)
+    int acc = 0;
+    uint32_t acc_phase = 0, box_phase = 0;           // box_phase: one parity bit per residual box
+    int n = 0, b = 0;                                // piece counter, its box (n % RES_NBOX)
+    {
+      bool live = tile < num_tiles;
+      // load cursor: runs RES_NBOX-1 pieces ahead of the compute cursor
+      int ltile = tile, lj = j, lb = 0;
+      bool lmore = live;
+      for (int k = 0; k < RES_NBOX - 1 && lmore; ++k) {
+        if (lane == 0) issue_load(ltile, lj, lb);
+        lmore = next_piece(ltile, lj);
+        lb = lb + 1 == RES_NBOX ? 0 : lb + 1;
+      }
+      float2 ssum = make_float2(0.f, 0.f), ssq = make_float2(0.f, 0.f);
+      while (live) {
+        int ntile = tile, nj = j;
+        const bool more = next_piece(ntile, nj);
+        if (lane == 0) bulk_wait_read0();           // the store of piece n-1 has read its box (= the one loaded next)
+        if (lmore) {
+          if (lane == 0) issue_load(ltile, lj, lb);
+          lmore = next_piece(ltile, lj);
+          lb = lb + 1 == RES_NBOX ? 0 : lb + 1;
+        }
+        const int row_base = piece_rows(tile);
+        const int col = piece_col(tile, j);
+        if (j == sub) {                              // first piece of a tile: the accumulator must be complete
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+        }
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        uint32_t v[16];
+        tmem_ld_32x32b_x16_nomem(t_row + j * 16, v);
+        mbar_wait(&my_full[b], (box_phase >> b) & 1u);
+        box_phase ^= 1u << b;
+        tmem_ld_wait_dep(v);
+        const uint32_t my_box = box0 + b * RES_BOX_BYTES + lane * 64;
+        uint32_t pk[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t addr = my_box + ((u ^ sw) << 4);
+          float4 r;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+          const int c = min(col + u * 4, p.N - 4);      // columns >= N are clipped by the store
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+          const float4 a = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]),
+                                       __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+          const float4 o = epilogue_math4<EPI>(a, bias4, r, bias4, 0.f, 0.f);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+          if (T::STATS) {
+            pk[2 * u] = pack_bf16(o.x, o.y);
+            pk[2 * u + 1] = pack_bf16(o.z, o.w);
+            if (col + u * 4 < p.N) {                  // warp-uniform: only real columns enter the statistics
+              const float2 lo = make_float2(o.x, o.y), hi = make_float2(o.z, o.w);
+              ssum = __fadd2_rn(ssum, __fadd2_rn(lo, hi));
+              ssq = __ffma2_rn(lo, lo, __ffma2_rn(hi, hi, ssq));
+            }
+          }
+        }
+        if (T::STATS) {
+          const uint32_t my_copy = copy0 + (n & 1) * RES_COPY_BYTES + lane * 32;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_copy), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_copy + 16), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row_base < p.M) {
+          tma_store_2d(&tma_c, wbase + b * RES_BOX_BYTES, col, row_base);
+          if (T::STATS) tma_store_2d(&tma_c2, wbase + RES_NBOX * RES_BOX_BYTES + (n & 1) * RES_COPY_BYTES, col, row_base);
+        }
+        if (lane == 0) bulk_commit();
+        const bool tile_done = !more || ntile != tile;
+        if (tile_done) {
+          if (T::STATS) {
+            if (row_base + lane < p.M)
+              p.pstats[(long long)(row_base + lane) * p.nslots + (tile % p.num_n_blocks) * NSUB + sub] =
+                  make_float2(ssum.x + ssum.y, ssq.x + ssq.y);
+            ssum = make_float2(0.f, 0.f);
+            ssq = make_float2(0.f, 0.f);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive(&tmem_empty[acc]);
+            else mbar_arrive_cluster(acc == 0 ? empty0 : empty1);
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        tile = ntile;
+        j = nj;
+        live = more;
+        ++n;
+        b = b + 1 == RES_NBOX ? 0 : b + 1;
+      }
     }
     if (lane == 0) bulk_wait0();                     // every store has landed before the CTA may exit
     __syncwarp();
@@ -401,7 +552,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       for (int j = sub; j < NCHUNK; j += NSUB) {
         const int col = col0 + j * 16;
         if (col >= p.N) break;                       // warp-uniform
-        if (TGB_GEMM_X & 2) break;
         uint32_t v[16];
         tmem_ld_32x32b_x16_nomem(t_row + j * 16, v);
         float4 rcur[4];
@@ -528,13 +678,35 @@ static int make_tmap_out(CUtensorMap* map, const void* base, long long rows, lon
   return TGB_OK;
 }
 
+// the fp32 residual epilogue's boxes: [32 rows x 16 columns], fp32 (SWIZZLE_64B) or bf16 copy (32-byte rows, no swizzle)
+static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, bool f32) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return TGB_ECUDA;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {16u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (residual box) failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+    return TGB_ECUDA;
+  }
+  return TGB_OK;
+}
+
 static int g_force_cg = 0;     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
 static int g_force_ew = 0;     // 0 = choose per epilogue, 8 / 16 = force
 
 template <int BN, int EPI, int CG, int EW>
 static int launch_gemm_ew(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::OUT_BF16>;
+  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::FAM>;
   p.num_m_blocks = (p.M + BM * CG - 1) / (BM * CG);
   p.num_n_blocks = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
@@ -543,10 +715,20 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
   if (st != TGB_OK) return st;
   st = make_tmap(&tb, W, p.N, p.K, ldw, Cfg::B_ROWS);
   if (st != TGB_OK) return st;
-  CUtensorMap tc = ta;                                   // unused by the fp32 epilogues
+  CUtensorMap tc = ta, tr = ta, tc2 = ta;      // placeholders where an epilogue family does not use them
   if (EpiTraits<EPI>::OUT_BF16) {
     st = make_tmap_out(&tc, p.out, p.M, p.N, p.ldo);
     if (st != TGB_OK) return st;
+  }
+  if (EpiTraits<EPI>::RESID) {
+    st = make_tmap_box16(&tc, p.out, p.M, p.N, p.ldo, true);
+    if (st != TGB_OK) return st;
+    st = make_tmap_box16(&tr, p.resid, p.M, p.N, p.ldr, true);
+    if (st != TGB_OK) return st;
+    if (EpiTraits<EPI>::STATS) {
+      st = make_tmap_box16(&tc2, p.out2, p.M, p.N, p.ldo2, false);
+      if (st != TGB_OK) return st;
+    }
   }
   auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, EW>;
   static bool configured = false;
@@ -569,16 +751,17 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
+  TGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, tc2, p));
   return TGB_OK;
 }
 
 template <int BN, int EPI, int CG>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmParams& p, cudaStream_t stream) {
-  // measured (tools/gemm_ab.py, interleaved medians): 16 warps help the fp32-residual epilogue at short K (proj: 940 vs
-  // 799 TF/s); bias / GELU epilogues are marginally better with 8 warps and the extra pipeline stage
-  int ew = g_force_ew ? g_force_ew : (EpiTraits<EPI>::RESID ? 16 : 8);
-  if (EpiTraits<EPI>::STATS) ew = 16;          // the statistics slot layout (4 per N tile) is fixed
+  // 8 epilogue warps by default (measured with tools/gemm_ab.py: the bias / GELU epilogues are marginally better with 8
+  // warps and the extra pipeline stage than with 16)
+  int ew = g_force_ew ? g_force_ew : 8;
+  if (EpiTraits<EPI>::RESID) ew = 8;           // two double-buffered residual boxes per warp; the statistics slot layout
+                                               // (2 per 256-column tile) is fixed
   if (ew == 16) return launch_gemm_ew<BN, EPI, CG, 16>(A, lda, W, ldw, p, stream);
   return launch_gemm_ew<BN, EPI, CG, 8>(A, lda, W, ldw, p, stream);
 }
@@ -698,7 +881,7 @@ static int gemm_entry(const void* A, int64_t lda, const void* W, int64_t ldw, in
   p.bias = bias; p.resid = resid; p.rowbias = rowbias; p.out = out; p.ldo = ldo; p.ldr = ldr;
   p.rowstats = rowstats; p.colsum = colsum; p.out2 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo2 = ldo2;
   p.pstats = reinterpret_cast<float2*>(partial_stats);
-  p.nslots = ((N + bn - 1) / bn) * 4;
+  p.nslots = ((N + bn - 1) / bn) * 2;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (cg == 2) return dispatch_bn<2>(bn, A, lda, W, ldw, p, s);
   return dispatch_bn<1>(bn, A, lda, W, ldw, p, s);
@@ -717,7 +900,7 @@ extern "C" int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
 
 extern "C" int tgb_gemm_ln_stats_slots(int M, int N) {
   if (M <= 0 || N <= 0) return 0;
-  return ((N + 255) / 256) * 4;
+  return ((N + 255) / 256) * 2;
 }
 
 extern "C" int tgb_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,

@@ -323,7 +323,7 @@ def gemm_set_cta_group(cta_group: int) -> None:
 
 
 def gemm_set_epilogue_warps(warps: int) -> None:
-    """0 = auto (16 for the residual epilogue, else 8), 8 or 16; test / debug knob."""
+    """0 = auto (8), 8 or 16 (the fp32-residual epilogues always run 8 warps); test / debug knob."""
     check(_lib.load().tgb_gemm_set_epilogue_warps(int(warps)))
 
 
