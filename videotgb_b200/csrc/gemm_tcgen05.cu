@@ -309,6 +309,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           if (h == 0 && lane == 0) bulk_wait_read0();     // the previous store has read the box (overlaps the TMEM load)
           tmem_ld_wait_dep32(v);
           if (h == 0) __syncwarp();
+          if (h == 1 && (j + NSUB >= NPIECE || col + NSUB * CW >= p.N)) {
+            // that was this warp's last read of the accumulator: hand it back to the MMA issuer before the math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 1) mbar_arrive_relaxed(&tmem_empty[acc]);
+              else mbar_arrive_cluster_relaxed(acc == 0 ? empty0 : empty1);
+            }
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -335,11 +344,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           bulk_commit();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 1) mbar_arrive(&tmem_empty[acc]);
-        else mbar_arrive_cluster(acc == 0 ? empty0 : empty1);
+      if (sub * CW + col0 >= p.N || sub >= NPIECE) {   // no piece in this tile (narrow N): still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 1) mbar_arrive_relaxed(&tmem_empty[acc]);
+          else mbar_arrive_cluster_relaxed(acc == 0 ? empty0 : empty1);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -424,6 +435,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         mbar_wait(&my_full[b], (box_phase >> b) & 1u);
         box_phase ^= 1u << b;
         tmem_ld_wait_dep(v);
+        const bool tile_done = !more || ntile != tile;
+        if (tile_done) {     // that was this warp's last read of the accumulator: hand it back before the math and the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive_relaxed(&tmem_empty[acc]);
+            else mbar_arrive_cluster_relaxed(acc == 0 ? empty0 : empty1);
+          }
+        }
         const uint32_t my_box = box0 + b * RES_BOX_BYTES + lane * 64;
         uint32_t pk[8];
 #pragma unroll
@@ -460,7 +480,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           if (T::STATS) tma_store_2d(&tma_c2, wbase + RES_NBOX * RES_BOX_BYTES + (n & 1) * RES_COPY_BYTES, col, row_base);
         }
         if (lane == 0) bulk_commit();
-        const bool tile_done = !more || ntile != tile;
         if (tile_done) {
           if (T::STATS) {
             if (row_base + lane < p.M)
@@ -468,12 +487,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
                   make_float2(ssum.x + ssum.y, ssq.x + ssq.y);
             ssum = make_float2(0.f, 0.f);
             ssq = make_float2(0.f, 0.f);
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CG == 1) mbar_arrive(&tmem_empty[acc]);
-            else mbar_arrive_cluster(acc == 0 ? empty0 : empty1);
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -607,8 +620,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 1) mbar_arrive(&tmem_empty[acc]);
-        else mbar_arrive_cluster(acc == 0 ? empty0 : empty1);
+        if (CG == 1) mbar_arrive_relaxed(&tmem_empty[acc]);
+        else mbar_arrive_cluster_relaxed(acc == 0 ? empty0 : empty1);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
