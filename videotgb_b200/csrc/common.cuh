@@ -131,17 +131,21 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU.
-// The polling loop is kept to three instructions (measured: with the timer read inside it, waiting warps issued 16 % of
-// all instructions of the residual GEMM -- on a power-capped part that is throughput taken from the tensor cores); the
-// clock is only consulted every 4096 wake-ups.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded waits: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU.
+// The polling loop is kept to three instructions (measured: with the timer read inside it, waiting warps issued half of
+// all instructions of the bias GEMM -- on a power-capped part that is throughput taken from the tensor cores); the clock
+// is only consulted every 4096 polls.
+//   mbar_wait        plain try_wait polling: for the latency-critical single-thread roles (TMA producer, MMA issuer)
+//   mbar_wait_parked try_wait with a suspend-time hint (NANOSLEEP.SYNCS until the barrier fires): for whole warps that
+//                    wait a long time (the epilogue warps waiting for an accumulator)
+template <bool PARKED>
+__device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = 0;
   for (;;) {
 #pragma unroll 1
     for (int it = 0; it < 4096; ++it)
-      if (mbar_try_wait_hint(bar, parity, 1000000u)) return;
+      if (PARKED ? mbar_try_wait_hint(bar, parity, 1000000u) : mbar_try_wait(bar, parity)) return;
     uint64_t t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     if (t0 == 0) t0 = t1;
@@ -151,6 +155,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_impl<false>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) { mbar_wait_impl<true>(bar, parity); }
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {

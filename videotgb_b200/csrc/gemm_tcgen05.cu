@@ -145,6 +145,30 @@ __device__ __forceinline__ float4 epilogue_store4(const GemmParams& p, float4 ac
   return v;
 }
 
+// bf16 epilogue, one 32-column half of a lane's 64-column row piece: bias / LayerNorm fold / activation in packed fp32,
+// rounded to 16 bf16x2 registers.  FULL = the whole 64-column piece lies inside N, so the per-column vectors are read at
+// immediate offsets from one base pointer; otherwise every 4-column group clamps its index (columns >= N are clipped by
+// the tensor store, so their bias may be anything).
+template <int EPI, bool FULL>
+__device__ __forceinline__ void bf16_half(const GemmParams& p, const uint32_t (&v)[32], uint32_t (&pk)[16], int c0,
+                                          float nmean, float rstd) {
+  using T = EpiTraits<EPI>;
+  const float4* bp = reinterpret_cast<const float4*>(p.bias + (FULL ? c0 : 0));
+  const float4* cp = reinterpret_cast<const float4*>(p.colsum + (FULL ? c0 : 0));
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = FULL ? q : (min(c0 + q * 4, p.N - 4) >> 2);
+    const float4 bias4 = __ldg(bp + i);
+    float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (T::LN) cs4 = __ldg(cp + i);
+    const float4 a = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+    const float4 r = epilogue_math4<EPI>(a, bias4, bias4, cs4, nmean, rstd);
+    pk[2 * q] = pack_bf16(r.x, r.y);
+    pk[2 * q + 1] = pack_bf16(r.z, r.w);
+  }
+}
+
 template <int BN, int EPI, int CG, int EW>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -283,7 +307,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     const uint32_t empty0 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
     const uint32_t empty1 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u;
     if (lane == 0) tma_prefetch_desc(&tma_c);
-    const bool has_bias = p.bias != nullptr;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
@@ -295,13 +318,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         nmean = -st.x;
         rstd = st.y;
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_parked(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
       for (int j = sub; j < NPIECE; j += NSUB) {
         const int col = col0 + j * CW;
         if (col >= p.N) break;                       // warp-uniform
+        const bool full = col + CW <= p.N;           // warp-uniform
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
@@ -319,19 +343,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
             }
           }
           uint32_t pk[16];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            // columns >= N are clipped by the tensor store, so their bias may be anything: clamp instead of predicating
-            const int c = min(col + h * 32 + q * 4, p.N - 4);
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-            if (T::LN) cs4 = __ldg(reinterpret_cast<const float4*>(p.colsum + c));
-            const float4 a = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-            const float4 r = epilogue_math4<EPI>(a, bias4, bias4, cs4, nmean, rstd);
-            pk[2 * q] = pack_bf16(r.x, r.y);
-            pk[2 * q + 1] = pack_bf16(r.z, r.w);
-          }
+          if (full) bf16_half<EPI, true>(p, v, pk, col + h * 32, nmean, rstd);
+          else bf16_half<EPI, false>(p, v, pk, col + h * 32, nmean, rstd);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (((h * 4 + u) ^ sw) << 4)),
@@ -426,7 +439,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const int row_base = piece_rows(tile);
         const int col = piece_col(tile, j);
         if (j == sub) {                              // first piece of a tile: the accumulator must be complete
-          mbar_wait(&tmem_full[acc], acc_phase);
+          mbar_wait_parked(&tmem_full[acc], acc_phase);
           tc_fence_after();
         }
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -558,7 +571,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           rrstd[i] = st.y;
         }
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_parked(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
@@ -712,6 +725,10 @@ static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, l
   }
   return TGB_OK;
 }
+
+// the bf16 epilogues read their bias unconditionally: a call without one gets this block of zeros
+constexpr int ZERO_BIAS_N = 8192;
+__device__ float g_zero_bias[ZERO_BIAS_N];
 
 static int g_force_cg = 0;     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
