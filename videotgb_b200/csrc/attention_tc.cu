@@ -553,17 +553,24 @@ __device__ __forceinline__ float pp_row_max(uint32_t s_addr) {
 // 16 score columns -> 8 packed bf16 probability registers; staged (fma, ex2, add/pack) so the MUFU pipe is fed back to
 // back.  NV = valid columns of the chunk (the rest produce p = 0).
 template <int NV>
-__device__ __forceinline__ void pp_exp16(uint32_t (&v)[16], float sl2, float negm, float& l0, float& l1, float& l2, float& l3) {
-  float x[16];
+__device__ __forceinline__ void pp_exp16(uint32_t (&v)[16], float sl2, float negm, float2& la, float2& lb) {
+  // packed fp32 (FFMA2 / FADD2): half the FP32-pipe instructions of the scalar form, same roundings and summation order
+  // (la = (l0, l1), lb = (l2, l3) of the four interleaved partial sums)
+  float2 x[8];
+  const float2 s2 = make_float2(sl2, sl2), m2 = make_float2(negm, negm);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = fmaf(__uint_as_float(v[j]), sl2, negm);
+  for (int j = 0; j < 8; ++j) x[j] = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), s2, m2);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = (j < NV) ? ex2_approx(x[j]) : 0.f;
+  for (int j = 0; j < 8; ++j) {
+    x[j].x = (2 * j < NV) ? ex2_approx(x[j].x) : 0.f;
+    x[j].y = (2 * j + 1 < NV) ? ex2_approx(x[j].y) : 0.f;
+  }
 #pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    l0 += x[j]; l1 += x[j + 1]; l2 += x[j + 2]; l3 += x[j + 3];
-    v[j >> 1] = pack_bf16(x[j], x[j + 1]);
-    v[(j >> 1) + 1] = pack_bf16(x[j + 2], x[j + 3]);
+  for (int j = 0; j < 8; j += 2) {
+    la = __fadd2_rn(la, x[j]);
+    lb = __fadd2_rn(lb, x[j + 1]);
+    v[j] = pack_bf16(x[j].x, x[j].y);
+    v[j + 1] = pack_bf16(x[j + 1].x, x[j + 1].y);
   }
 }
 
@@ -574,24 +581,24 @@ __device__ __forceinline__ void pp_exp16(uint32_t (&v)[16], float sl2, float neg
 // current chunk is processed.  Returns the row sum.
 template <int NFULL, int TAIL>
 __device__ __forceinline__ float pp_exp_block(uint32_t s_addr, float sl2, float negm) {
-  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
   uint32_t cur[16], nxt[16];
   tmem_ld16<0>(s_addr, cur);
 #pragma unroll 1
   for (int c = 0; c < NFULL; ++c) {
     tmem_ld_wait();
     if (TAIL > 0 || c + 1 < NFULL) tmem_ld16<0>(s_addr + (c + 1) * 16, nxt);   // (never reads past the block)
-    pp_exp16<16>(cur, sl2, negm, l0, l1, l2, l3);
+    pp_exp16<16>(cur, sl2, negm, la, lb);
     tmem_st8<0>(s_addr + c * 8, cur);
 #pragma unroll
     for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
   }
   if (TAIL > 0) {
     tmem_ld_wait();
-    pp_exp16<TAIL>(cur, sl2, negm, l0, l1, l2, l3);
+    pp_exp16<TAIL>(cur, sl2, negm, la, lb);
     tmem_st8<0>(s_addr + NFULL * 8, cur);
   }
-  return (l0 + l1) + (l2 + l3);
+  return (la.x + la.y) + (lb.x + lb.y);
 }
 
 // One CLS query row (row 0 of the image) on the warp-level tensor-core path (mma.sync.m16n8k16), one warp per item,
@@ -1059,11 +1066,16 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         uint4* srow = reinterpret_cast<uint4*>(stage + row * (VA_D * 2));
 #pragma unroll
         for (int c = 0; c < 11; ++c) {                           // 88 valid d columns = 11 x 16 bytes
+          const float2 i2 = make_float2(inv, inv);              // packed fp32 multiplies (FMUL2)
+          const float2 a = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 0]), __uint_as_float(o[8 * c + 1])), i2);
+          const float2 b = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 2]), __uint_as_float(o[8 * c + 3])), i2);
+          const float2 d = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 4]), __uint_as_float(o[8 * c + 5])), i2);
+          const float2 e = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 6]), __uint_as_float(o[8 * c + 7])), i2);
           uint4 v;
-          v.x = pack_bf16(__uint_as_float(o[8 * c + 0]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
-          v.y = pack_bf16(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
-          v.z = pack_bf16(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
-          v.w = pack_bf16(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+          v.x = pack_bf16(a.x, a.y);
+          v.y = pack_bf16(b.x, b.y);
+          v.z = pack_bf16(d.x, d.y);
+          v.w = pack_bf16(e.x, e.y);
           srow[c] = v;
         }
         fence_proxy_async();                                     // generic-proxy writes -> visible to the TMA (async proxy)
