@@ -58,6 +58,8 @@ TGB_API int tgb_normalize_frames_u8(const uint8_t* frames_thwc, float* out_tchw,
  * F.interpolate's CPU arithmetic followed by .to(torch.uint8).  S % 4 == 0.                                 */
 TGB_API int tgb_resize_bilinear_u8(const uint8_t* frames_thwc, uint8_t* out_thwc, int T, int H0, int W0, int S,
                            tgb_stream_t stream);
+/* Debug / test knob: 0 = choose (word-load kernel when the input is 4-byte aligned; default), 1 = generic byte-load kernel. */
+TGB_API int tgb_resize_set_variant(int variant);
 
 /* ---------------------------------------------------------------- A7  Gumbel span draw ----------------
  * src/models/LSTP_SF_blip2_module.py:424-428: F.gumbel_softmax(cat(start,end), tau, dim=1).argmax(dim=1)

@@ -23,6 +23,7 @@ SIGNATURES = {
     "tgb_sm_count": ([], c_int),
     "tgb_normalize_frames_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_resize_bilinear_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp], c_int),
+    "tgb_resize_set_variant": ([c_int], c_int),
     "tgb_gumbel_argmax": ([c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_vp], c_int),
     "tgb_spans_to_indices": ([c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "tgb_pseudo_span": ([c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp], c_int),

@@ -324,6 +324,135 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* 
     d[k] = (uint32_t)o[4 * k] | ((uint32_t)o[4 * k + 1] << 8) | ((uint32_t)o[4 * k + 2] << 16) | ((uint32_t)o[4 * k + 3] << 24);
 }
 
+// Fast variant (base pointer and total size multiples of 4).  The generic kernel above spends 38 instructions per output
+// byte, a third of them 64-bit address arithmetic for its 48 single-byte loads per thread, and is issue bound at half the
+// HBM roofline.  Here:
+//   * the two horizontal taps of a pixel are adjacent pixels = 6 contiguous bytes, fetched as three aligned 32-bit words
+//     (one address computation, immediate offsets) and aligned with two funnel shifts; at the right edge (i1 == i0) the
+//     first pixel's bytes are replicated into the second pixel's position with two predicated PRMTs;
+//   * byte -> float is ONE PRMT that drops the byte into the mantissa of 2^23 (0x4B0000bb) plus the exact subtraction;
+//   * float -> byte is an add of 2^23 with round-toward-zero (v >= 0: truncation == floor) and PRMT packing, instead of
+//     F2I on the quarter-rate XU pipe;
+//   * taps are computed once per CTA (column tap in registers, row taps in shared memory) for all the rows it walks.
+// Same arithmetic, operation for operation, as the generic kernel (bit-exact with ATen's CPU path).
+__device__ __forceinline__ void resize_load8(const uint32_t* __restrict__ fa, const uint8_t* __restrict__ fbytes, int o,
+                                             int limit, uint32_t& lo, uint32_t& hi) {
+  if (o + 12 <= limit) {                       // three whole words are inside the buffer (always, except at its very end)
+    const uint32_t* w = fa + (o >> 2);
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const uint32_t sh = (static_cast<uint32_t>(o) & 3u) << 3;
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+  } else {                                     // last pixels of the last frame: byte loads, nothing read past the end
+    uint32_t b[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = (o + k < limit) ? __ldg(fbytes + o + k) : 0u;
+    lo = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    hi = b[4] | (b[5] << 8);
+  }
+}
+
+struct XTap { int xoff; uint32_t edge; float w0, w1; };
+
+// One thread = 4 consecutive output pixels of a row (12 output bytes = three aligned words); a CTA of 64 x 4 threads walks
+// `rows_per_cta` output rows of its 256 columns.  (A one-lane-per-pixel mapping, whose word loads touch 3 cache lines per
+// warp instead of 9, measured slower: 3.4 vs 3.9 TB/s -- the kernel is bound by instruction issue, not by L1 wavefronts.)
+__global__ void __launch_bounds__(256) resize_bilinear_u8_fast_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                      int T, int H0, int W0, int S, float scale_h,
+                                                                      float scale_w, int rows_per_cta) {
+  __shared__ XTap xt[4][64];                   // [pixel of the quad][thread column]: conflict-free 16-byte reads
+  const int tid = threadIdx.y * 64 + threadIdx.x;
+  {
+    const int px = blockIdx.x * 256 + tid;     // tid = 4 * column + q
+    if (px < S) {
+      const BilinearTap t = bilinear_tap(px, W0, S, scale_w);
+      XTap e;
+      e.xoff = t.i0 * 3;
+      e.edge = t.i1 == t.i0 ? 1u : 0u;
+      e.w0 = t.w0;
+      e.w1 = t.w1;
+      xt[tid & 3][tid >> 2] = e;
+    }
+  }
+  __syncthreads();
+  const int xq = blockIdx.x * 64 + threadIdx.x;
+  if (xq * 4 >= S) return;
+  const int t = blockIdx.z;
+  const long long frame_bytes = (long long)H0 * W0 * 3;
+  const uint8_t* fb = src + (long long)t * frame_bytes;
+  const int fm = static_cast<int>(reinterpret_cast<uintptr_t>(fb) & 3u);
+  const uint32_t* fa = reinterpret_cast<const uint32_t*>(fb - fm);
+  const uint8_t* fbytes = fb - fm;
+  const int limit = (t == T - 1) ? static_cast<int>(frame_bytes) + fm : 0x7fffffff;
+  const int row_pitch = W0 * 3;
+  constexpr uint32_t MAGIC = 0x4B000000u;      // 2^23: PRMT selector 0x754k puts byte k into its mantissa
+  const int y_end = min(S, (blockIdx.y + 1) * rows_per_cta);
+  for (int y = blockIdx.y * rows_per_cta + threadIdx.y; y < y_end; y += 4) {
+    const BilinearTap ty = bilinear_tap(y, H0, S, scale_h);
+    const int row0 = fm + ty.i0 * row_pitch, row1 = fm + ty.i1 * row_pitch;
+    // all 24 word loads of the thread are issued before the first use (the taps stay in shared memory until needed)
+    uint32_t lo[8], hi[8];
+    const int last_off = max(row0, row1) + xt[3][threadIdx.x].xoff;
+    if (last_off + 12 <= limit) {                // always, except for the last pixels of the last frame
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int xo = xt[q][threadIdx.x].xoff;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int o = (r == 0 ? row0 : row1) + xo;
+          const uint32_t* w = fa + (o >> 2);
+          const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+          const uint32_t sh = (static_cast<uint32_t>(o) & 3u) << 3;
+          lo[2 * q + r] = __funnelshift_r(w0, w1, sh);
+          hi[2 * q + r] = __funnelshift_r(w1, w2, sh);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          resize_load8(fa, fbytes, (r == 0 ? row0 : row1) + xt[q][threadIdx.x].xoff, limit, lo[2 * q + r], hi[2 * q + r]);
+    }
+    uint32_t m[12];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const XTap x = xt[q][threadIdx.x];
+      float top[3], bot[3];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        uint32_t l = lo[2 * q + r], h = hi[2 * q + r];
+        if (x.edge) {                            // second tap = the same pixel: bytes 3,4,5 := bytes 0,1,2
+          h = __byte_perm(l, 0u, 0x4421);
+          l = __byte_perm(l, 0u, 0x0210);
+        }
+        const float a0 = __uint_as_float(__byte_perm(l, MAGIC, 0x7540)) - 8388608.0f;
+        const float a1 = __uint_as_float(__byte_perm(l, MAGIC, 0x7541)) - 8388608.0f;
+        const float a2 = __uint_as_float(__byte_perm(l, MAGIC, 0x7542)) - 8388608.0f;
+        const float b0 = __uint_as_float(__byte_perm(l, MAGIC, 0x7543)) - 8388608.0f;
+        const float b1 = __uint_as_float(__byte_perm(h, MAGIC, 0x7540)) - 8388608.0f;
+        const float b2 = __uint_as_float(__byte_perm(h, MAGIC, 0x7541)) - 8388608.0f;
+        float* dstv = r == 0 ? top : bot;
+        dstv[0] = __fmaf_rn(a0, x.w0, __fmul_rn(b0, x.w1));
+        dstv[1] = __fmaf_rn(a1, x.w0, __fmul_rn(b1, x.w1));
+        dstv[2] = __fmaf_rn(a2, x.w0, __fmul_rn(b2, x.w1));
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = __fmaf_rn(top[c], ty.w0, __fmul_rn(bot[c], ty.w1));
+        m[q * 3 + c] = __float_as_uint(__fadd_rz(v, 8388608.0f));     // low mantissa byte = trunc(v), v in [0, 255]
+      }
+    }
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + (((long long)t * S + y) * S + xq * 4) * 3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const uint32_t p01 = __byte_perm(m[4 * k], m[4 * k + 1], 0x0040);
+      const uint32_t p23 = __byte_perm(m[4 * k + 2], m[4 * k + 3], 0x0040);
+      d[k] = __byte_perm(p01, p23, 0x5410);
+    }
+  }
+}
+
 // Gather: dst[(b*k + i)] = src[b, idx[b,i]] as 16-byte words; blockIdx.y = output frame, grid-stride over words.
 __global__ void __launch_bounds__(256) gather_frames_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx,
                                                             uint4* __restrict__ dst, int N, int k, long long words) {
@@ -525,6 +654,17 @@ extern "C" int tgb_patchify_set_variant(int variant) {
   return TGB_OK;
 }
 
+static int g_resize_variant = 0;   // 0 = choose (fast kernel when the input is 4-byte aligned), 1 = generic byte-load kernel
+
+extern "C" int tgb_resize_set_variant(int variant) {
+  if (variant != 0 && variant != 1) {
+    set_last_error("resize variant must be 0 (auto) or 1 (generic byte-load kernel)");
+    return TGB_EINVAL;
+  }
+  g_resize_variant = variant;
+  return TGB_OK;
+}
+
 extern "C" int tgb_resize_bilinear_u8(const uint8_t* frames_thwc, uint8_t* out_thwc, int T, int H0, int W0, int S,
                                       tgb_stream_t stream) {
   int st = check_device();
@@ -539,8 +679,17 @@ extern "C" int tgb_resize_bilinear_u8(const uint8_t* frames_thwc, uint8_t* out_t
   //  measured slower, 2.2 vs 3.3 TB/s: the kernel is instruction-issue bound at ~42 instructions per output byte, not
   //  load bound; profiles/r1_hbm_kernels.jsonl.)
   dim3 block(64, 4);
-  dim3 grid((S / 4 + 63) / 64, (S + 3) / 4, T);
-  resize_bilinear_u8_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(frames_thwc, out_thwc, H0, W0, S, sh, sw);
+  const long long frame_bytes = (long long)H0 * W0 * 3;
+  if (g_resize_variant == 0 && ((uintptr_t)frames_thwc % 4) == 0 && frame_bytes + 16 < 0x7fffffffLL) {
+    // fast kernel: CTAs walk `rows` output rows so that the per-CTA column taps are amortised; enough CTAs for every SM
+    int rows = 32;
+    while (rows > 4 && (long long)((S + rows - 1) / rows) * ((S / 4 + 63) / 64) * T < 4LL * sm_count()) rows >>= 1;
+    dim3 grid((S / 4 + 63) / 64, (S + rows - 1) / rows, T);
+    resize_bilinear_u8_fast_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(frames_thwc, out_thwc, T, H0, W0, S, sh, sw, rows);
+  } else {
+    dim3 grid((S / 4 + 63) / 64, (S + 3) / 4, T);
+    resize_bilinear_u8_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(frames_thwc, out_thwc, H0, W0, S, sh, sw);
+  }
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

@@ -98,6 +98,11 @@ def resize_bilinear_u8(frames_thwc: torch.Tensor, size: int) -> torch.Tensor:
     return out
 
 
+def resize_set_variant(variant: int) -> None:
+    """0 = auto (word-load kernel for 4-byte aligned inputs), 1 = generic byte-load kernel; test / debug knob."""
+    check(_lib.load().tgb_resize_set_variant(int(variant)))
+
+
 # ------------------------------------------------------------------------------------------------ A7-A9
 def gumbel_argmax(logits: torch.Tensor, gumbel: torch.Tensor, tau: float = 0.5) -> torch.Tensor:
     lg = _need(logits, torch.float32, "logits")
