@@ -155,6 +155,9 @@ TGB_API int tgb_rowstats_cast_f32(const float* x, int64_t ldx, int M, int N, flo
 
 /* Debug / test knob: 0 = choose per problem (default), 1 = single-CTA 128xBN tiles, 2 = CTA-pair 256xBN tiles.      */
 TGB_API int tgb_gemm_set_cta_group(int cta_group);
+/* Debug / A-B knob: 1 = balanced persistent tile schedule (every cluster walks all N blocks in turn; default),
+ * 0 = plain round-robin.                                                                                                    */
+TGB_API int tgb_gemm_set_schedule(int balanced);
 /* Debug / test knob: epilogue warps per CTA, 0 = choose (8; the fp32-residual epilogues always run 8).               */
 TGB_API int tgb_gemm_set_epilogue_warps(int warps);
 

@@ -1,6 +1,7 @@
 """Interleaved A/B timing of GEMM variants (robust to power/thermal drift): median of several rounds.
 
-    python tools/gemm_ab.py            the six ViT GEMM variants next to cuBLAS (torch.matmul, no epilogue) on the same shapes
+    python tools/gemm_ab.py            the six ViT GEMM variants, balanced vs round-robin persistent schedule, next to cuBLAS
+                                       (torch.matmul, no epilogue) on the same shapes
     TGB_LIB=tools/_dbg/lib....so python tools/gemm_ab.py     the same with an experiment build of the library
 """
 import os
@@ -52,14 +53,17 @@ def main():
     for rnd in range(7):
         for name, m, n, k, epi in SHAPES:
             fn = runner(name, epi)
-            fn()
-            res.setdefault((name, "ours"), []).append(timeit(fn))
+            for vname, bal in (("balanced", True), ("roundrobin", False)):
+                ops.gemm_set_schedule(bal)
+                fn()
+                res.setdefault((name, vname), []).append(timeit(fn))
+            ops.gemm_set_schedule(True)
             a, w = bufs[name][0], bufs[name][1]
             res.setdefault((name, "cublas"), []).append(timeit(lambda: torch.matmul(a, w.t())))
     for name, m, n, k, epi in SHAPES:
         fl = 2.0 * m * n * k
         line = f"{name:10s}"
-        for vname in ("ours", "cublas"):
+        for vname in ("balanced", "roundrobin", "cublas"):
             if (name, vname) in res:
                 ms = statistics.median(res[(name, vname)])
                 line += f"  {vname}: {ms:.3f} ms {fl / ms / 1e9:6.0f} TF"

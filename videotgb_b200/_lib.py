@@ -41,6 +41,7 @@ SIGNATURES = {
     "tgb_ln_stats_finalize": ([c_vp, c_int, c_int, c_int, c_f32, c_vp, c_vp], c_int),
     "tgb_rowstats_cast_f32": ([c_vp, c_i64, c_int, c_int, c_f32, c_vp, c_i64, c_vp, c_vp], c_int),
     "tgb_gemm_set_cta_group": ([c_int], c_int),
+    "tgb_gemm_set_schedule": ([c_int], c_int),
     "tgb_gemm_set_epilogue_warps": ([c_int], c_int),
     "tgb_layernorm_f32": ([c_vp, c_i64, c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp], c_int),
     "tgb_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int,
@@ -87,6 +88,8 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
         fn.restype = res
     _lib = lib
+    if os.environ.get("TGB_GEMM_SCHEDULE") == "roundrobin" and hasattr(lib, "tgb_gemm_set_schedule"):     # A/B knob
+        lib.tgb_gemm_set_schedule(0)
     return lib
 
 

@@ -47,6 +47,7 @@ struct GemmParams {
   long long ldo2;
   float2* pstats;
   int nslots;
+  int sched_shift;                                  // persistent tile schedule, see tile_at() in the kernel
 };
 
 template <int EPI> struct EpiTraits {
@@ -197,6 +198,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const int cluster_id = blockIdx.x / CG;
   const int num_clusters = gridDim.x / CG;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  // Persistent schedule: in round i the clusters share the tiles [i*C, (i+1)*C) (C = clusters), cluster c taking position
+  // (c + i*shift) mod C.  A plain round-robin (shift = 0) gives cluster c the N blocks (c + i*C) mod NB: with NB = 6 and
+  // C = 74 (the N = 1408 GEMMs) half of the clusters never see the cheap half-width last N tile and the others see it on
+  // a third of their tiles -- the fast half runs ahead by several tiles, the kernel waits for the slow half, and the
+  // clusters that share an A row block drift so far apart that the K = 6144 GEMM re-read a third of A from DRAM.  The
+  // host picks shift so that (C + shift) mod NB == 1: every cluster walks all N blocks in turn.
+  const int sched_shift = p.sched_shift;
+  auto tile_at = [&](int round) {
+    return round * num_clusters + (cluster_id + round * sched_shift) % num_clusters;
+  };
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -226,7 +237,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int round = 0, tile; (tile = tile_at(round)) < num_tiles; ++round) {
         const int m_blk = tile / p.num_n_blocks;
         const int n_blk = tile - m_blk * p.num_n_blocks;
         const int a_row = (m_blk * CG + (int)rank) * BM;
@@ -261,7 +272,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int round = 0, tile; (tile = tile_at(round)) < num_tiles; ++round) {
         const int n_blk_mma = tile % p.num_n_blocks;
         const uint32_t idesc = (BN == 256 && p.N - n_blk_mma * BN <= BN / 2) ? idesc_half : idesc_full;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -307,7 +318,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     const uint32_t empty0 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
     const uint32_t empty1 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u;
     if (lane == 0) tma_prefetch_desc(&tma_c);
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int round = 0, tile; (tile = tile_at(round)) < num_tiles; ++round) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
       const int row_base = (m_blk * CG + (int)rank) * BM + quarter * 32;
@@ -398,10 +409,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     // piece iterator: (tile, j) with j = sub, sub+NSUB, ... while the piece starts inside N
     auto piece_rows = [&](int tile) { return ((tile / p.num_n_blocks) * CG + (int)rank) * BM + quarter * 32; };
     auto piece_col = [&](int tile, int j) { return (tile % p.num_n_blocks) * BN + j * 16; };
-    auto next_piece = [&](int& tile, int& j) {       // advance; returns false past the end
+    auto next_piece = [&](int& round, int& tile, int& j) {       // advance; returns false past the end
       j += NSUB;
       if (j >= NCHUNK || piece_col(tile, j) >= p.N) {
-        tile += num_clusters;
+        tile = tile_at(++round);
         j = sub;
       }
       return tile < num_tiles;
@@ -410,7 +421,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       mbar_arrive_expect_tx(&my_full[b], RES_BOX_BYTES);
       tma_load_2d(wbase + b * RES_BOX_BYTES, &tma_r, &my_full[b], piece_col(tile, j), piece_rows(tile));
     };
-    int tile = cluster_id, j = sub;
+    int round = 0, tile = tile_at(0), j = sub;
     // (a piece that starts at or beyond N -- narrow problems, the half-empty last N tile -- is still walked: its load is
     //  zero-filled and its store clipped, which keeps one accumulator hand-shake per tile for every warp)
     int acc = 0;
@@ -419,21 +430,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     {
       bool live = tile < num_tiles;
       // load cursor: runs RES_NBOX-1 pieces ahead of the compute cursor
-      int ltile = tile, lj = j, lb = 0;
+      int lround = round, ltile = tile, lj = j, lb = 0;
       bool lmore = live;
       for (int k = 0; k < RES_NBOX - 1 && lmore; ++k) {
         if (lane == 0) issue_load(ltile, lj, lb);
-        lmore = next_piece(ltile, lj);
+        lmore = next_piece(lround, ltile, lj);
         lb = lb + 1 == RES_NBOX ? 0 : lb + 1;
       }
       float2 ssum = make_float2(0.f, 0.f), ssq = make_float2(0.f, 0.f);
       while (live) {
-        int ntile = tile, nj = j;
-        const bool more = next_piece(ntile, nj);
+        int nround = round, ntile = tile, nj = j;
+        const bool more = next_piece(nround, ntile, nj);
         if (lane == 0) bulk_wait_read0();           // the store of piece n-1 has read its box (= the one loaded next)
         if (lmore) {
           if (lane == 0) issue_load(ltile, lj, lb);
-          lmore = next_piece(ltile, lj);
+          lmore = next_piece(lround, ltile, lj);
           lb = lb + 1 == RES_NBOX ? 0 : lb + 1;
         }
         const int row_base = piece_rows(tile);
@@ -503,6 +514,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        round = nround;
         tile = ntile;
         j = nj;
         live = more;
@@ -530,7 +542,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     uint32_t acc_phase = 0;
     const uint32_t empty0 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
     const uint32_t empty1 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int round = 0, tile; (tile = tile_at(round)) < num_tiles; ++round) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
       const int row_base = (m_blk * CG + (int)rank) * BM + quarter * 32;
@@ -733,6 +745,7 @@ __device__ float g_zero_bias[ZERO_BIAS_N];
 static int g_force_cg = 0;     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
 static int g_force_ew = 0;     // 0 = choose per epilogue, 8 / 16 = force
+static int g_sched_balanced = 1;   // 1 = balanced persistent schedule (default), 0 = plain round-robin (A/B knob)
 
 template <int BN, int EPI, int CG, int EW>
 static int launch_gemm_ew(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
@@ -769,6 +782,8 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_clusters = sm_count() / CG;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  // (clusters + shift) mod n_blocks == 1: every cluster walks the N blocks in turn (see tile_at in the kernel)
+  p.sched_shift = g_sched_balanced ? (((1 - clusters) % p.num_n_blocks) + p.num_n_blocks) % p.num_n_blocks : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(Cfg::THREADS);
@@ -861,6 +876,11 @@ extern "C" int tgb_gemm_set_epilogue_warps(int warps) {
     return TGB_EINVAL;
   }
   g_force_ew = warps;
+  return TGB_OK;
+}
+
+extern "C" int tgb_gemm_set_schedule(int balanced) {
+  g_sched_balanced = balanced ? 1 : 0;
   return TGB_OK;
 }
 

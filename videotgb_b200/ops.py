@@ -327,6 +327,11 @@ def gemm_set_cta_group(cta_group: int) -> None:
     check(_lib.load().tgb_gemm_set_cta_group(int(cta_group)))
 
 
+def gemm_set_schedule(balanced: bool) -> None:
+    """True = balanced persistent tile schedule (default), False = plain round-robin; A/B knob."""
+    check(_lib.load().tgb_gemm_set_schedule(1 if balanced else 0))
+
+
 def gemm_set_epilogue_warps(warps: int) -> None:
     """0 = auto (8), 8 or 16 (the fp32-residual epilogues always run 8 warps); test / debug knob."""
     check(_lib.load().tgb_gemm_set_epilogue_warps(int(warps)))
