@@ -142,6 +142,9 @@ TGB_API int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw
  *                       out_bf16 [M, ldo2] = bf16(out) and partial_stats f32 [M, slots, 2] = (sum, sum of squares) of
  *                       each row over the columns of one slot; slots = tgb_gemm_ln_stats_slots(M, N) (two per 256-column tile); every slot is
  *                       written exactly once per launch (no atomics: results are run-to-run deterministic)
+ * The consumer multiplies the UN-normalised rows on the tensor cores, so its error grows with |row mean| / row std
+ * (measured: 1x the separate-LayerNorm error at 0.25, 2x at 4, 4.6e-2 at 32); tgb_ln_stats_finalize can track the largest
+ * ratio it sees in max_ratio (f32 scalar, zero it first; NULL = off) so that the host can fall back to tgb_layernorm_f32.
  * tgb_ln_stats_finalize reduces the slots to rowstats (float64 combine, biased variance, rstd = 1/sqrt(var + eps));
  * tgb_rowstats_cast_f32 produces rowstats and the bf16 copy for rows that did not come out of a GEMM (first layer).  */
 TGB_API int tgb_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,
@@ -149,7 +152,7 @@ TGB_API int tgb_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t 
                      void* out, int64_t ldo, void* out_bf16, int64_t ldo2, float* partial_stats, tgb_stream_t stream);
 TGB_API int tgb_gemm_ln_stats_slots(int M, int N);
 TGB_API int tgb_ln_stats_finalize(const float* partial_stats, int M, int slots, int N, float eps, float* rowstats,
-                          tgb_stream_t stream);
+                          float* max_ratio, tgb_stream_t stream);
 TGB_API int tgb_rowstats_cast_f32(const float* x, int64_t ldx, int M, int N, float eps, void* out_bf16, int64_t ldo,
                           float* rowstats, tgb_stream_t stream);
 

@@ -90,6 +90,26 @@ def test_vit_layernorm_fold_matches_separate_layernorm(vit2):
     assert r_fused <= max(1.5 * r_plain, 5e-3)
 
 
+def test_vit_layernorm_fold_falls_back_on_large_row_means():
+    """A residual stream whose rows sit far from zero (|mean| / std > 4) would push the folded LayerNorm past the parity
+    bar; the first pass after loading such weights measures the ratio and switches to the separate LayerNorm pass."""
+    sd = dict(syn.vision_state_dict(syn.VisionCfg(layers=2)))
+    sd["embeddings.position_embedding"] = sd["embeddings.position_embedding"] + 3.0      # every row offset by +3, std ~0.05
+    m = Blip2VisionModel(NS(num_hidden_layers=2)).to(DEV)
+    m.load_state_dict(sd)
+    px = cases.vit_pixels(2).to(DEV)
+    with pytest.warns(UserWarning, match="separate LayerNorm"):
+        out = m(pixel_values=px).last_hidden_state
+    assert m.fuse_layernorm is False and m.fold_ratio_seen > m.fold_max_mean_over_std
+    with torch.no_grad():
+        ref32, _ = torch_ref.vit_forward(to_dev(sd), px, layers=2)
+    assert_parity(out, ref32, "fallback to separate LayerNorm")
+    # benign weights re-enable the fold
+    m.load_state_dict(syn.vision_state_dict(syn.VisionCfg(layers=2)))
+    m(pixel_values=px)
+    assert m.fuse_layernorm is True and m.fold_ratio_seen <= m.fold_max_mean_over_std
+
+
 def test_vit_u8_fast_path(vit2):
     sd, m, _, _ = vit2
     u8 = syn.synthetic_frames_u8(2, seed=11).to(DEV)

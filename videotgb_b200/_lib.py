@@ -38,7 +38,7 @@ SIGNATURES = {
     "tgb_gemm_bf16_ln": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64,
                           c_vp, c_i64, c_vp, c_vp], c_int),
     "tgb_gemm_ln_stats_slots": ([c_int, c_int], c_int),
-    "tgb_ln_stats_finalize": ([c_vp, c_int, c_int, c_int, c_f32, c_vp, c_vp], c_int),
+    "tgb_ln_stats_finalize": ([c_vp, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp], c_int),
     "tgb_rowstats_cast_f32": ([c_vp, c_i64, c_int, c_int, c_f32, c_vp, c_i64, c_vp, c_vp], c_int),
     "tgb_gemm_set_cta_group": ([c_int], c_int),
     "tgb_gemm_set_schedule": ([c_int], c_int),

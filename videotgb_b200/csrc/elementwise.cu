@@ -101,8 +101,11 @@ __global__ void __launch_bounds__(256) rowstats_cast_kernel(const float* __restr
 // LayerNorm fold: per-row (sum, sum of squares) slots written by the TGB_EPI_F32_RESID_STATS epilogue -> (mean, rstd).
 // One thread per row, slots summed in index order in float64 (deterministic; the subtraction E[x^2] - mean^2 is exact
 // to fp32 partial-sum accuracy).
+// max_ratio (optional): running maximum of |mean| * rstd over all rows, kept as the bit pattern of a non-negative float --
+// the fold's error grows with that ratio (see tgb_gemm_bf16_ln), the host checks it once after loading weights.
 __global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __restrict__ part, int M, int slots, int N,
-                                                                float eps, float2* __restrict__ stats) {
+                                                                float eps, float2* __restrict__ stats,
+                                                                float* __restrict__ max_ratio) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
   const float2* pr = part + (long long)row * slots;
@@ -115,7 +118,14 @@ __global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __
   const double mean = s / N;
   double var = q / N - mean * mean;
   var = var > 0.0 ? var : 0.0;
-  stats[row] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  stats[row] = make_float2(static_cast<float>(mean), rstd);
+  if (max_ratio != nullptr) {
+    float ratio = fabsf(static_cast<float>(mean)) * rstd;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(__activemask(), ratio, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(max_ratio), __float_as_int(ratio));
+  }
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, long long ldx,
@@ -186,14 +196,14 @@ __global__ void replace_ids_kernel(long long* __restrict__ ids, long long n, lon
 using namespace tgb;
 
 extern "C" int tgb_ln_stats_finalize(const float* partial_stats, int M, int slots, int N, float eps, float* rowstats,
-                                     tgb_stream_t stream) {
+                                     float* max_ratio, tgb_stream_t stream) {
   int st = check_device();
   if (st != TGB_OK) return st;
   TGB_CHECK_ARG(partial_stats && rowstats && M >= 0 && slots > 0 && N > 0, "ln_stats_finalize: bad arguments");
   TGB_CHECK_ARG(((uintptr_t)partial_stats % 8) == 0 && ((uintptr_t)rowstats % 8) == 0, "ln_stats_finalize: misaligned");
   if (M == 0) return TGB_OK;
   ln_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2*>(partial_stats), M, slots, N, eps, reinterpret_cast<float2*>(rowstats));
+      reinterpret_cast<const float2*>(partial_stats), M, slots, N, eps, reinterpret_cast<float2*>(rowstats), max_ratio);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

@@ -287,8 +287,10 @@ def ln_stats_slots(m: int, n: int) -> int:
     return int(_lib.load().tgb_gemm_ln_stats_slots(int(m), int(n)))
 
 
-def ln_stats_finalize(partial_stats: torch.Tensor, n: int, eps: float, rowstats: torch.Tensor) -> torch.Tensor:
-    """partial_stats f32 [M, slots, 2] (sum, sum of squares) -> rowstats f32 [M, 2] (mean, rstd)."""
+def ln_stats_finalize(partial_stats: torch.Tensor, n: int, eps: float, rowstats: torch.Tensor,
+                      max_ratio: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """partial_stats f32 [M, slots, 2] (sum, sum of squares) -> rowstats f32 [M, 2] (mean, rstd).
+    max_ratio: optional f32 scalar tensor that accumulates max |mean| * rstd over the rows (zero it first)."""
     _need(partial_stats, torch.float32, "partial_stats")
     _need(rowstats, torch.float32, "rowstats")
     m, slots, two = partial_stats.shape
@@ -297,7 +299,10 @@ def ln_stats_finalize(partial_stats: torch.Tensor, n: int, eps: float, rowstats:
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(_lib.load().tgb_ln_stats_finalize(_p(partial_stats), m, slots, int(n), float(eps), _p(rowstats), _stream()))
+    if max_ratio is not None:
+        _need(max_ratio, torch.float32, "max_ratio")
+    check(_lib.load().tgb_ln_stats_finalize(_p(partial_stats), m, slots, int(n), float(eps), _p(rowstats), _p(max_ratio),
+                                            _stream()))
     if _PROFILE is not None:
         e1.record()
         _PROFILE.append(("layernorm", (m, n, "finalize"), e0, e1))
