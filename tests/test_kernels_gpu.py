@@ -129,8 +129,22 @@ def test_resize_bilinear_bit_exact():
                        (1, 225, 223, 224), (4, 2, 2, 8), (2, 481, 854, 224), (1, 2160, 3840, 224)]:
         u8 = rng.integers(0, 256, size=(t, h, w, 3), dtype=np.uint8)
         u8[0, :, : w // 2] = 200                               # flat region
-        got = ops.resize_bilinear_u8(torch.from_numpy(u8).to(DEV), s).cpu().numpy()
-        assert np.array_equal(got, transform_ref.resize_bilinear_u8(u8, s)), (t, h, w, s)
+        want = transform_ref.resize_bilinear_u8(u8, s)
+        d8 = torch.from_numpy(u8).to(DEV)
+        got = ops.resize_bilinear_u8(d8, s).cpu().numpy()          # word-load kernel (aligned input)
+        assert np.array_equal(got, want), (t, h, w, s)
+        ops.resize_set_variant(1)                                   # generic byte-load kernel
+        try:
+            got = ops.resize_bilinear_u8(d8, s).cpu().numpy()
+        finally:
+            ops.resize_set_variant(0)
+        assert np.array_equal(got, want), (t, h, w, s, "generic")
+        if (h * w * 3) % 4 == 0 and t > 1:                          # a view that starts 1 frame + 0 bytes in, then an odd offset
+            flat = torch.empty(d8.numel() + 3, dtype=torch.uint8, device=DEV)
+            flat[3:] = d8.flatten()
+            odd = flat[3:].view(t, h, w, 3)                         # base pointer = allocation + 3: not word aligned
+            got = ops.resize_bilinear_u8(odd, s).cpu().numpy()
+            assert np.array_equal(got, want), (t, h, w, s, "unaligned base")
     # the whole reference chain behind the host mirror (decoded frames -> normalised fp32 TCHW)
     from videotgb_b200.transforms import DataConfig, VideoNormalizer
     vn = VideoNormalizer(DataConfig(target_size=32))
@@ -421,6 +435,33 @@ def test_gemm_ln_rejects_bad_arguments():
     with pytest.raises(RuntimeError):
         ops.gemm_ln(a, w, torch.zeros(8, device=DEV), ops.EPI_BF16_LN, out, rowstats=torch.zeros(4, 2, device=DEV),
                     colsum=torch.zeros(8, device=DEV))           # rowstats rows != M
+
+
+def test_gemm_schedules_agree():
+    """The balanced persistent schedule only changes which cluster computes which tile: results are bit-identical to the
+    plain round-robin one, for every epilogue family."""
+    g = torch.Generator().manual_seed(17)
+    m, n, k = 257 * 9, 1408, 1408
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) * 0.03).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    resid = torch.randn(m, n, generator=g).to(DEV)
+    outs = []
+    for balanced in (True, False):
+        ops.gemm_set_schedule(balanced)
+        try:
+            o_bf16 = ops.gemm(a, w, bias, ops.EPI_BF16_GELU)
+            o_res = ops.gemm(a, w, bias, ops.EPI_F32_RESID, resid=resid)
+            o_f32 = ops.gemm(a, w, bias, ops.EPI_F32)
+            xb = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+            part = torch.empty(m, ops.ln_stats_slots(m, n), 2, device=DEV)
+            x = resid.clone()
+            ops.gemm_ln(a, w, bias, ops.EPI_F32_RESID_STATS, x, resid=x, out_bf16=xb, partial_stats=part)
+        finally:
+            ops.gemm_set_schedule(True)
+        outs.append((o_bf16, o_res, o_f32, xb, part, x))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
 
 
 def test_gemm_rejects_bad_arguments():
