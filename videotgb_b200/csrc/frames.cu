@@ -357,39 +357,54 @@ struct XTap { int xoff; uint32_t edge; float w0, w1; };
 // One thread = 4 consecutive output pixels of a row (12 output bytes = three aligned words); a CTA of 64 x 4 threads walks
 // `rows_per_cta` output rows of its 256 columns.  (A one-lane-per-pixel mapping, whose word loads touch 3 cache lines per
 // warp instead of 9, measured slower: 3.4 vs 3.9 TB/s -- the kernel is bound by instruction issue, not by L1 wavefronts.)
+struct YTap { int off0, off1; float w0, w1; };
+constexpr int RESIZE_MAX_ROWS = 32;
+
 __global__ void __launch_bounds__(256) resize_bilinear_u8_fast_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                       int T, int H0, int W0, int S, float scale_h,
                                                                       float scale_w, int rows_per_cta) {
   __shared__ XTap xt[4][64];                   // [pixel of the quad][thread column]: conflict-free 16-byte reads
+  __shared__ YTap yt[RESIZE_MAX_ROWS];         // row taps of the CTA's output rows (byte offsets inside the frame)
   const int tid = threadIdx.y * 64 + threadIdx.x;
+  const int t = blockIdx.z;
+  const long long frame_bytes = (long long)H0 * W0 * 3;
+  const uint8_t* fb = src + (long long)t * frame_bytes;
+  const int fm = static_cast<int>(reinterpret_cast<uintptr_t>(fb) & 3u);
+  const int y_base = blockIdx.y * rows_per_cta;
   {
     const int px = blockIdx.x * 256 + tid;     // tid = 4 * column + q
     if (px < S) {
-      const BilinearTap t = bilinear_tap(px, W0, S, scale_w);
+      const BilinearTap tp = bilinear_tap(px, W0, S, scale_w);
       XTap e;
-      e.xoff = t.i0 * 3;
-      e.edge = t.i1 == t.i0 ? 1u : 0u;
-      e.w0 = t.w0;
-      e.w1 = t.w1;
+      e.xoff = tp.i0 * 3;
+      e.edge = tp.i1 == tp.i0 ? 1u : 0u;
+      e.w0 = tp.w0;
+      e.w1 = tp.w1;
       xt[tid & 3][tid >> 2] = e;
+    }
+    if (tid < rows_per_cta && y_base + tid < S) {
+      const BilinearTap tp = bilinear_tap(y_base + tid, H0, S, scale_h);
+      YTap e;
+      e.off0 = fm + tp.i0 * W0 * 3;
+      e.off1 = fm + tp.i1 * W0 * 3;
+      e.w0 = tp.w0;
+      e.w1 = tp.w1;
+      yt[tid] = e;
     }
   }
   __syncthreads();
   const int xq = blockIdx.x * 64 + threadIdx.x;
   if (xq * 4 >= S) return;
-  const int t = blockIdx.z;
-  const long long frame_bytes = (long long)H0 * W0 * 3;
-  const uint8_t* fb = src + (long long)t * frame_bytes;
-  const int fm = static_cast<int>(reinterpret_cast<uintptr_t>(fb) & 3u);
   const uint32_t* fa = reinterpret_cast<const uint32_t*>(fb - fm);
   const uint8_t* fbytes = fb - fm;
   const int limit = (t == T - 1) ? static_cast<int>(frame_bytes) + fm : 0x7fffffff;
-  const int row_pitch = W0 * 3;
   constexpr uint32_t MAGIC = 0x4B000000u;      // 2^23: PRMT selector 0x754k puts byte k into its mantissa
-  const int y_end = min(S, (blockIdx.y + 1) * rows_per_cta);
-  for (int y = blockIdx.y * rows_per_cta + threadIdx.y; y < y_end; y += 4) {
-    const BilinearTap ty = bilinear_tap(y, H0, S, scale_h);
-    const int row0 = fm + ty.i0 * row_pitch, row1 = fm + ty.i1 * row_pitch;
+  // the right-edge case (second tap == first tap) only exists in the last quad(s) of a row: one branch per thread
+  const bool any_edge = (xt[0][threadIdx.x].edge | xt[1][threadIdx.x].edge | xt[2][threadIdx.x].edge | xt[3][threadIdx.x].edge) != 0u;
+  const int y_end = min(S - y_base, rows_per_cta);
+  for (int yr = threadIdx.y; yr < y_end; yr += 4) {
+    const YTap ty = yt[yr];
+    const int row0 = ty.off0, row1 = ty.off1;
     // all 24 word loads of the thread are issued before the first use (the taps stay in shared memory until needed)
     uint32_t lo[8], hi[8];
     const int last_off = max(row0, row1) + xt[3][threadIdx.x].xoff;
@@ -414,6 +429,17 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_fast_kernel(const uint
         for (int r = 0; r < 2; ++r)
           resize_load8(fa, fbytes, (r == 0 ? row0 : row1) + xt[q][threadIdx.x].xoff, limit, lo[2 * q + r], hi[2 * q + r]);
     }
+    if (any_edge) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (xt[q][threadIdx.x].edge) {           // second tap = the same pixel: bytes 3,4,5 := bytes 0,1,2
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            hi[2 * q + r] = __byte_perm(lo[2 * q + r], 0u, 0x4421);
+            lo[2 * q + r] = __byte_perm(lo[2 * q + r], 0u, 0x0210);
+          }
+        }
+    }
     uint32_t m[12];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -421,17 +447,15 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_fast_kernel(const uint
       float top[3], bot[3];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        uint32_t l = lo[2 * q + r], h = hi[2 * q + r];
-        if (x.edge) {                            // second tap = the same pixel: bytes 3,4,5 := bytes 0,1,2
-          h = __byte_perm(l, 0u, 0x4421);
-          l = __byte_perm(l, 0u, 0x0210);
-        }
+        const uint32_t l = lo[2 * q + r], h = hi[2 * q + r];
+        // byte -> float: PRMT into the 2^23 mantissa + exact subtraction on the FMA pipe for four of the six samples, the
+        // XU pipe's I2F.U8 (byte select built in, quarter rate, otherwise idle) for the other two
         const float a0 = __uint_as_float(__byte_perm(l, MAGIC, 0x7540)) - 8388608.0f;
         const float a1 = __uint_as_float(__byte_perm(l, MAGIC, 0x7541)) - 8388608.0f;
-        const float a2 = __uint_as_float(__byte_perm(l, MAGIC, 0x7542)) - 8388608.0f;
+        const float a2 = static_cast<float>((l >> 16) & 0xffu);
         const float b0 = __uint_as_float(__byte_perm(l, MAGIC, 0x7543)) - 8388608.0f;
         const float b1 = __uint_as_float(__byte_perm(h, MAGIC, 0x7540)) - 8388608.0f;
-        const float b2 = __uint_as_float(__byte_perm(h, MAGIC, 0x7541)) - 8388608.0f;
+        const float b2 = static_cast<float>((h >> 8) & 0xffu);
         float* dstv = r == 0 ? top : bot;
         dstv[0] = __fmaf_rn(a0, x.w0, __fmul_rn(b0, x.w1));
         dstv[1] = __fmaf_rn(a1, x.w0, __fmul_rn(b1, x.w1));
@@ -443,7 +467,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_fast_kernel(const uint
         m[q * 3 + c] = __float_as_uint(__fadd_rz(v, 8388608.0f));     // low mantissa byte = trunc(v), v in [0, 255]
       }
     }
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst + (((long long)t * S + y) * S + xq * 4) * 3);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + (((long long)t * S + y_base + yr) * S + xq * 4) * 3);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const uint32_t p01 = __byte_perm(m[4 * k], m[4 * k + 1], 0x0040);
