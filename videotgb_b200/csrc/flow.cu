@@ -10,28 +10,31 @@ namespace tgb {
 // im2col: out[(n,oy,ox), (ky*kw + kx)*C + c] = x[(n, oy*sh - ph + ky, ox*sw - pw + kx), c]  (0 outside the image),
 // columns [kh*kw*C, ldo) zero.  VEC path: C % 8 == 0 -> one 16-byte copy per 8 channels.
 // ---------------------------------------------------------------------------------------------------------
-// Vector path: one thread owns (output pixel, 8-channel chunk) and walks the kh*kw taps, so the integer divisions are
-// paid once per thread instead of once per 16 bytes; consecutive lanes write consecutive 16-byte chunks of a tap segment.
+// Vector path: one thread owns (output pixel, 8-channel chunk) and walks the kh*kw taps; consecutive lanes write
+// consecutive 16-byte chunks of a tap segment.  blockIdx.y walks the output rows (n, oy), blockIdx.x the (ox, chunk) pairs
+// of one row, so the only per-thread divisions are two 32-bit ones (the flat 64-bit index it replaces cost five 64-bit
+// divisions per thread -- more instructions than the copies themselves).
 __global__ void __launch_bounds__(256) im2col_nhwc_vec_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int H, int W,
                                                               int C, int kh, int kw, int sh, int sw, int ph, int pw, int Ho,
-                                                              int Wo, long long rows, __nv_bfloat16* __restrict__ out,
+                                                              int Wo, int NHo, __nv_bfloat16* __restrict__ out,
                                                               long long ldo) {
-  const int c8 = C >> 3;
+  const unsigned c8 = static_cast<unsigned>(C) >> 3;
   const int K = kh * kw * C;
-  const long long total = rows * c8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / c8;
-    const int c = (int)(i - r * c8) << 3;
-    const int ox = (int)(r % Wo);
-    const long long t = r / Wo;
-    const int oy = (int)(t % Ho);
-    const long long n = t / Ho;
-    const int iy0 = oy * sh - ph, ix0 = ox * sw - pw;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<unsigned>(Wo) * c8) return;
+  const int ox = static_cast<int>(idx / c8);
+  const int c = static_cast<int>(idx - static_cast<unsigned>(ox) * c8) << 3;
+  const int ix0 = ox * sw - pw;
+  for (int ry = blockIdx.y; ry < NHo; ry += gridDim.y) {
+    const int n = ry / Ho;
+    const int oy = ry - n * Ho;
+    const int iy0 = oy * sh - ph;
+    const long long r = (long long)ry * Wo + ox;
     __nv_bfloat16* o = out + r * ldo + c;
     for (int ky = 0; ky < kh; ++ky) {
       const int iy = iy0 + ky;
       const bool yok = iy >= 0 && iy < H;
-      const __nv_bfloat16* srow = x + ((n * H + iy) * W) * ldx + c;
+      const __nv_bfloat16* srow = x + (((long long)n * H + iy) * W) * ldx + c;
       for (int kx = 0; kx < kw; ++kx) {
         const int ix = ix0 + kx;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -39,37 +42,40 @@ __global__ void __launch_bounds__(256) im2col_nhwc_vec_kernel(const __nv_bfloat1
         *reinterpret_cast<uint4*>(o + (ky * kw + kx) * C) = v;
       }
     }
-    if (c == 0)                                                 // zero the K padding of this row (at most 7 columns... up to ldo)
+    if (c == 0)                                                 // zero the K padding of this row (up to ldo)
       for (int k = K; k < (int)ldo; ++k) out[r * ldo + k] = __float2bfloat16(0.f);
   }
 }
 
-// Scalar path (C = 2 / 3 input channels): one thread per output element.
+// Scalar path (C = 2 / 3 input channels): one thread per (ox, output column) pair, walking the output rows (n, oy) its
+// blockIdx.y is responsible for; the column decomposition (tap, channel) is done once per thread in 32-bit arithmetic.
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int H, int W,
                                                           int C, int kh, int kw, int sh, int sw, int ph, int pw, int Ho,
-                                                          int Wo, long long rows, __nv_bfloat16* __restrict__ out,
+                                                          int Wo, int NHo, __nv_bfloat16* __restrict__ out,
                                                           long long ldo) {
   const int K = kh * kw * C;
-  const int units = (int)ldo;
-  const long long total = rows * units;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / units;
-    const int col = (int)(i - r * units);
-    const int ox = (int)(r % Wo);
-    const long long t = r / Wo;
-    const int oy = (int)(t % Ho);
-    const long long n = t / Ho;
-    bool ok = col < K;
-    int c = 0, iy = 0, ix = 0;
-    if (ok) {
-      const int tap = col / C;
-      c = col - tap * C;
-      const int ky = tap / kw, kx = tap - ky * kw;
-      iy = oy * sh - ph + ky;
-      ix = ox * sw - pw + kx;
-      ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-    }
-    out[r * ldo + col] = ok ? x[((n * H + iy) * W + ix) * ldx + c] : __float2bfloat16(0.f);
+  const unsigned units = static_cast<unsigned>(ldo);
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<unsigned>(Wo) * units) return;
+  const int ox = static_cast<int>(idx / units);
+  const int col = static_cast<int>(idx - static_cast<unsigned>(ox) * units);
+  const bool in_k = col < K;
+  int c = 0, ky = 0, kx = 0;
+  if (in_k) {
+    const int tap = col / C;
+    c = col - tap * C;
+    ky = tap / kw;
+    kx = tap - ky * kw;
+  }
+  const int ix = ox * sw - pw + kx;
+  const bool xok = in_k && ix >= 0 && ix < W;
+  for (int ry = blockIdx.y; ry < NHo; ry += gridDim.y) {
+    const int n = ry / Ho;
+    const int oy = ry - n * Ho;
+    const int iy = oy * sh - ph + ky;
+    const bool ok = xok && iy >= 0 && iy < H;
+    const long long r = (long long)ry * Wo + ox;
+    out[r * ldo + col] = ok ? x[(((long long)n * H + iy) * W + ix) * ldx + c] : __float2bfloat16(0.f);
   }
 }
 
@@ -144,27 +150,31 @@ __global__ void __launch_bounds__(256) instnorm_finalize_kernel(const float* __r
   }
 }
 
-// fully parallel apply: 4 channels per thread, 16-byte accesses
+// fully parallel apply: 4 channels per thread, 16-byte accesses; blockIdx.y = image, 32-bit index math inside it (the
+// flat 64-bit index this replaces paid three 64-bit divisions per 16 bytes and ran at a quarter of HBM speed)
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ fin, int HW,
-                                                             int C, int relu, long long total4, float* __restrict__ of,
+                                                             int C, int relu, float* __restrict__ of,
                                                              __nv_bfloat16* __restrict__ ob) {
-  const int c4n = C >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4n) << 2;
-    const long long np = i / c4n;                                 // n*HW + p
-    const long long n = np / HW;
-    const float4 v = *reinterpret_cast<const float4*>(x + np * C + c);
-    const float4 s0 = *reinterpret_cast<const float4*>(fin + (n * C + c) * 2);         // mean0 rstd0 mean1 rstd1
-    const float4 s1 = *reinterpret_cast<const float4*>(fin + (n * C + c) * 2 + 4);
+  const unsigned c4n = static_cast<unsigned>(C) >> 2;
+  const unsigned per_image = static_cast<unsigned>(HW) * c4n;
+  const long long n = blockIdx.y;
+  const float* xn = x + n * HW * C;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += gridDim.x * blockDim.x) {
+    const unsigned p = i / c4n;
+    const int c = static_cast<int>(i - p * c4n) << 2;
+    const long long off = (long long)p * C + c;
+    const float4 v = *reinterpret_cast<const float4*>(xn + off);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(fin + (n * C + c) * 2));         // mean0 rstd0 mean1 rstd1
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(fin + (n * C + c) * 2 + 4));
     float4 o;
     o.x = (v.x - s0.x) * s0.y; o.y = (v.y - s0.z) * s0.w; o.z = (v.z - s1.x) * s1.y; o.w = (v.w - s1.z) * s1.w;
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (of) *reinterpret_cast<float4*>(of + np * C + c) = o;
+    if (of) *reinterpret_cast<float4*>(of + n * HW * C + off) = o;
     if (ob) {
       uint2 pk;
       pk.x = pack_bf16(o.x, o.y);
       pk.y = pack_bf16(o.z, o.w);
-      *reinterpret_cast<uint2*>(ob + np * C + c) = pk;
+      *reinterpret_cast<uint2*>(ob + n * HW * C + off) = pk;
     }
   }
 }
@@ -377,10 +387,20 @@ extern "C" int tgb_im2col_nhwc_bf16(const void* x, int64_t ldx, int N, int H, in
   const bool vec = C % 8 == 0 && ldx % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0;
   auto xb = (const __nv_bfloat16*)x;
   auto ob = (__nv_bfloat16*)out;
-  if (vec)
-    im2col_nhwc_vec_kernel<<<ew_grid(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>(xb, ldx, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, rows, ob, ldo);
-  else
-    im2col_nhwc_kernel<<<ew_grid(rows * ldo), 256, 0, (cudaStream_t)stream>>>(xb, ldx, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, rows, ob, ldo);
+  if (vec) {
+    const long long nho = (long long)N * Ho;
+    TGB_CHECK_ARG(nho < 0x7fffffffLL && (long long)Wo * (C / 8) < 0x7fffffffLL, "im2col: problem too large");
+    dim3 grid((unsigned)(((long long)Wo * (C / 8) + 255) / 256), (unsigned)(nho < 65535 ? nho : 65535));
+    im2col_nhwc_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xb, ldx, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, (int)nho, ob, ldo);
+  } else {
+    const long long nho = (long long)N * Ho;
+    TGB_CHECK_ARG(nho < 0x7fffffffLL && (long long)Wo * ldo < 0x7fffffffLL, "im2col: problem too large");
+    // each thread walks NHo / gridDim.y rows: a few rows per thread keep the per-thread column decomposition amortised
+    long long gy = nho < 65535 ? nho : 65535;
+    const long long gx = ((long long)Wo * ldo + 255) / 256;
+    while (gy > 1 && gx * gy > 64LL * sm_count()) gy = (gy + 1) / 2;
+    im2col_nhwc_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(xb, ldx, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, (int)nho, ob, ldo);
+  }
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }
@@ -397,9 +417,13 @@ extern "C" int tgb_instance_norm_nhwc(const float* x, int N, int HW, int C, floa
   dim3 grid((C + 31) / 32, N, IN_SPLITS);
   instnorm_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, HW, C, workspace);
   instnorm_finalize_kernel<<<ew_grid((long long)N * C), 256, 0, (cudaStream_t)stream>>>(workspace, HW, C, eps, (long long)N * C, fin);
-  const long long total4 = (long long)N * HW * (C / 4);
-  instnorm_apply_kernel<<<ew_grid(total4), 256, 0, (cudaStream_t)stream>>>(x, fin, HW, C, relu, total4, out_f32,
-                                                                         (__nv_bfloat16*)out_bf16);
+  const long long per_image = (long long)HW * (C / 4);
+  TGB_CHECK_ARG(per_image < 0x7fffffffLL && N <= 65535, "instance_norm: problem too large");
+  long long bx = (per_image + 255) / 256;
+  const long long cap = ((long long)sm_count() * 16 + N - 1) / N;                  // ~16 CTAs per SM over all images
+  if (bx > cap) bx = cap > 0 ? cap : 1;
+  instnorm_apply_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, (cudaStream_t)stream>>>(x, fin, HW, C, relu, out_f32,
+                                                                                          (__nv_bfloat16*)out_bf16);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }
