@@ -201,9 +201,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   // Persistent schedule: in round i the clusters share the tiles [i*C, (i+1)*C) (C = clusters), cluster c taking position
   // (c + i*shift) mod C.  A plain round-robin (shift = 0) gives cluster c the N blocks (c + i*C) mod NB: with NB = 6 and
   // C = 74 (the N = 1408 GEMMs) half of the clusters never see the cheap half-width last N tile and the others see it on
-  // a third of their tiles -- the fast half runs ahead by several tiles, the kernel waits for the slow half, and the
-  // clusters that share an A row block drift so far apart that the K = 6144 GEMM re-read a third of A from DRAM.  The
-  // host picks shift so that (C + shift) mod NB == 1: every cluster walks all N blocks in turn.
+  // a third of their tiles -- the fast half runs ahead by several tiles and the kernel waits for the slow half.  The host
+  // searches the shift that minimises the busiest cluster's work (balanced_shift).
   const int sched_shift = p.sched_shift;
   auto tile_at = [&](int round) {
     return round * num_clusters + (cluster_id + round * sched_shift) % num_clusters;
@@ -742,6 +741,40 @@ static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, l
 constexpr int ZERO_BIAS_N = 8192;
 __device__ float g_zero_bias[ZERO_BIAS_N];
 
+// Shift of the persistent schedule (tile_at in the kernel) that minimises the busiest cluster's work.  Only a half-width
+// last N tile makes tiles unequal (it costs ~0.65 of a full one: half the MMA time, the same A traffic); without one every
+// shift is equally good.  Exhaustive search over the shifts with that cost model, cached per problem shape.
+static int balanced_shift(int clusters, int m_blocks, int n_blocks, bool half_last) {
+  const long long tiles = (long long)m_blocks * n_blocks;
+  if (!half_last || tiles <= clusters || clusters <= 1) return 0;
+  struct Key { int c, m, n; };
+  static Key keys[16];
+  static int vals[16];
+  static int used = 0;
+  for (int i = 0; i < used; ++i)
+    if (keys[i].c == clusters && keys[i].m == m_blocks && keys[i].n == n_blocks) return vals[i];
+  const int rounds = (int)((tiles + clusters - 1) / clusters);
+  int best = 0;
+  long long best_cost = -1;
+  for (int s = 0; s < clusters; ++s) {
+    long long worst = 0;
+    for (int c = 0; c < clusters && (best_cost < 0 || worst < best_cost); ++c) {
+      long long cost = 0;                                   // in units of 1/20 tile: full = 20, half = 13
+      for (int r = 0; r < rounds; ++r) {
+        const long long t = (long long)r * clusters + (c + (long long)r * s) % clusters;
+        if (t >= tiles) break;
+        cost += (t % n_blocks == n_blocks - 1) ? 13 : 20;
+      }
+      if (cost > worst) worst = cost;
+    }
+    if (best_cost < 0 || worst < best_cost) { best_cost = worst; best = s; }
+  }
+  const int slot = used < 16 ? used++ : 15;
+  keys[slot] = Key{clusters, m_blocks, n_blocks};
+  vals[slot] = best;
+  return best;
+}
+
 static int g_force_cg = 0;     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
 static int g_force_ew = 0;     // 0 = choose per epilogue, 8 / 16 = force
@@ -782,8 +815,8 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_clusters = sm_count() / CG;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  // (clusters + shift) mod n_blocks == 1: every cluster walks the N blocks in turn (see tile_at in the kernel)
-  p.sched_shift = g_sched_balanced ? (((1 - clusters) % p.num_n_blocks) + p.num_n_blocks) % p.num_n_blocks : 0;
+  p.sched_shift = g_sched_balanced ? balanced_shift(clusters, p.num_m_blocks, p.num_n_blocks,
+                                                     BN == 256 && p.N - (p.num_n_blocks - 1) * BN <= BN / 2) : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(Cfg::THREADS);
