@@ -12,6 +12,8 @@ What it pins:
   resize.npz           -- N3: the reference ResizeVideo/ToUint8/ToTHWC(/ToTensorVideo/NormalizeVideo) chain on decoded frames.
   raft.npz             -- N1: the reference RAFT class on a seeded frame pair (flow_up subsampled, fnet feature sample).
   transform.npz        -- A0: reference ToTensorVideo/NormalizeVideo on random u8 frames.
+  task_module.npz      -- (b): the unmodified reference `eval_forward` methods (BLIP-2 and InstructBLIP task modules)
+                          on the reference containers built from HF configs: what they pass to `language_model.generate`.
   vit_small.npz ...    -- A10-A16, A1-A6: the reference classes (through reference_shim) loaded with the
                           seeded synthetic state dicts, fp32, small inputs.  Outputs stored as fp16-safe fp32
                           slices + full-tensor statistics to keep fixtures small.
@@ -322,10 +324,61 @@ def gen_models():
     print(json.dumps({k: v for k, v in meta.items()}, indent=0)[:2000])
 
 
+def gen_task_module():
+    """(b) the boundary at its own seam: the UNMODIFIED `LSTPSFModule.eval_forward` methods of the reference task modules
+    (src/models/LSTP_SF_blip2_module.py:382-506 BLIP-2, src/models/LSTP_SF_module.py:456-580 InstructBLIP) run on the
+    reference's own container / sampler classes built from real HF config objects, CPU fp32.  The stand-in language
+    model records what `generate` receives; that (inputs_embeds, attention_mask) and the returned ids are the fixture
+    `tests/test_boundary_gpu.py` holds the drop-in classes to."""
+    import importlib
+    reference_shim.install()
+    sys.path.insert(1, os.path.join(ROOT, "tests"))
+    import reference_stubs
+    reference_stubs.install()
+    from tests import task_module_case as tc
+    arrays, meta = {}, {}
+    for tag, modname, instruct in (("blip2", "src.models.LSTP_SF_blip2_module", False),
+                                   ("instruct", "src.models.LSTP_SF_module", True)):
+        mod = importlib.import_module(modname)
+        assert mod.__file__.startswith(REF), mod.__file__
+        cfg, bert_cfg = tc.hf_configs(instruct)
+        container_cls = mod.InstructBlipForConditionalGeneration if instruct else mod.Blip2ForConditionalGeneration
+        assert container_cls.__module__.startswith("src.models.components") and \
+            sys.modules[container_cls.__module__].__file__.startswith(REF)
+        sds = tc.state_dicts(instruct)
+        model = container_cls(cfg)
+        res = model.load_state_dict(tc.container_state_dict(sds), strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+        assert all(k.startswith(("language_model.", "temporal_projection.")) or "position_ids" in k for k in res.missing_keys), \
+            res.missing_keys
+        lm = tc.CaptureLM()
+        model.language_model = lm
+        sampler = mod.RopeBertModel(config=bert_cfg)
+        res = sampler.load_state_dict(sds["sampler"], strict=False)
+        assert not res.unexpected_keys and all("position_ids" in k for k in res.missing_keys), res
+        task = mod.LSTPSFModule.__new__(mod.LSTPSFModule)            # __init__ needs hub checkpoints; attributes suffice
+        torch.nn.Module.__init__(task)
+        task.model, task.temporal_encoder = model.eval(), sampler.eval()
+        task.generate_configs = dict(max_new_tokens=3)
+        batch, gumbel = tc.make_batch(instruct)
+        with tc.fixed_gumbel(gumbel):
+            outputs = mod.LSTPSFModule.eval_forward(task, batch)
+        emb, am = lm.seen["inputs_embeds"], lm.seen["attention_mask"]
+        assert lm.seen["kwargs"] == dict(max_new_tokens=3)
+        arrays[tag + "_inputs_embeds"] = emb.numpy().astype(np.float32)
+        arrays[tag + "_attention_mask"] = am.numpy()
+        arrays[tag + "_outputs"] = outputs.numpy()
+        meta[tag] = dict(shape=list(emb.shape), absmax=float(emb.abs().max()), std=float(emb.std()))
+        print(tag, meta[tag], outputs.tolist())
+    np.savez_compressed(os.path.join(GOLD, "task_module.npz"), **arrays)
+    with open(os.path.join(GOLD, "task_module_meta.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     reference_shim.install()
-    which = sys.argv[1:] or ["select", "pseudo_span", "gumbel", "transform", "resize", "raft", "models"]
+    which = sys.argv[1:] or ["select", "pseudo_span", "gumbel", "transform", "resize", "raft", "models", "task_module"]
     for w in which:
         globals()["gen_" + w]()
         print("generated", w)

@@ -17,43 +17,9 @@ import torch
 from torch import nn
 
 from . import ops, selection
-from .modeling import (Blip2QFormerModel, Blip2VisionModel, InstructBlipQFormerModel, InstructBlipVisionModel,
-                       _KernelModule, _Linear)
+from .containers import (Blip2ForConditionalGeneration, InstructBlipForConditionalGeneration,  # noqa: F401
+                         LanguageProjection)
 from .sampler import RopeBertModel
-
-
-class _Blip2Like(nn.Module):
-    """`self.model` of the reference: vision_model, qformer, query_tokens, language_projection, temporal_projection
-    (xblip2.py:1540-1556 / xinstructblip.py:1255-1273).  The language model itself is out of scope (unchanged HF)."""
-
-    def __init__(self, vision_config=None, qformer_config=None, llm_hidden: int = 2048, instruct: bool = False,
-                 num_query_tokens: int = 32):
-        super().__init__()
-        self.vision_model = (InstructBlipVisionModel if instruct else Blip2VisionModel)(vision_config)
-        self.qformer = (InstructBlipQFormerModel if instruct else Blip2QFormerModel)(qformer_config)
-        self.query_tokens = nn.Parameter(torch.zeros(1, num_query_tokens, self.qformer.hidden))
-        self.language_projection = LanguageProjection(self.qformer.hidden, llm_hidden)
-        self.temporal_projection = _Linear(self.qformer.hidden, llm_hidden)     # kept for checkpoint compatibility only
-
-
-class LanguageProjection(_KernelModule):
-    """nn.Linear(768, H_llm) (xblip2.py:1552) on the tcgen05 GEMM; accepts [..., 768] fp32/bf16, returns fp32."""
-
-    def __init__(self, in_features: int, out_features: int):
-        super().__init__()
-        self.in_features, self.out_features = in_features, out_features
-        self.weight = nn.Parameter(torch.empty(out_features, in_features).normal_(0.0, 0.02))
-        self.bias = nn.Parameter(torch.zeros(out_features))
-
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        self._device_check(x)
-        if self._packed is None:
-            self._packed = (self._bf16(self.weight), self._f32(self.bias))
-        w, b = self._packed
-        x2 = x.reshape(-1, self.in_features)
-        a = x2.contiguous() if x2.dtype == torch.bfloat16 else ops.cast_bf16(x2.to(torch.float32).contiguous())
-        y = ops.gemm(a, w, b, ops.EPI_F32)
-        return y.view(*x.shape[:-1], self.out_features)
 
 
 class VideoTGBEncoder(nn.Module):
@@ -61,12 +27,43 @@ class VideoTGBEncoder(nn.Module):
                  instruct: bool = False, with_flow_extractor: bool = False):
         super().__init__()
         self.instruct = instruct
-        self.model = _Blip2Like(vision_config, qformer_config, llm_hidden, instruct)
+        cfg = SimpleNamespace(vision_config=vision_config, qformer_config=qformer_config, num_query_tokens=32,
+                              text_config=SimpleNamespace(hidden_size=llm_hidden), use_decoder_only_language_model=instruct)
+        # `self.model` of the reference task modules, without the (unchanged, out-of-scope) language model
+        self.model = (InstructBlipForConditionalGeneration if instruct else Blip2ForConditionalGeneration)(
+            cfg, language_model=False)
         self.temporal_encoder = RopeBertModel(sampler_config)
         if with_flow_extractor:            # offline inference computes the flow online (eval/utils/model.py:37,75-84)
             from .raft import RAFT
             self.of_extractor = RAFT()
         self.token_exchange = None      # optional distributed.TokenAllGather: all-gather of the Q-Former tokens
+
+    @classmethod
+    def from_modules(cls, model, temporal_encoder, of_extractor=None) -> "VideoTGBEncoder":
+        """Wrap an existing container (`Blip2ForConditionalGeneration` / `InstructBlipForConditionalGeneration`, e.g. from
+        `from_pretrained`) and sampler -- the two attributes the reference task modules hold (`self.model`,
+        `self.temporal_encoder`, LSTP_SF_blip2_module.py:84-89) -- without rebuilding them."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.instruct = bool(getattr(model, "instruct", False))
+        self.model, self.temporal_encoder = model, temporal_encoder
+        if of_extractor is not None:
+            self.of_extractor = of_extractor
+        self.token_exchange = None
+        return self
+
+    @torch.no_grad()
+    def eval_forward(self, batch, generate_configs=None, mode: str = "fusion", gumbel=None, generator=None):
+        """The whole `eval_forward` of the reference task modules (LSTP_SF_blip2_module.py:382-506, LSTP_SF_module.py:
+        456-580): hot path -> `cat` with the question embeddings -> the UNCHANGED language model's `generate` -> the LLaMA
+        id fix-up.  Needs a container that owns a language model."""
+        lm = self.model.language_model
+        if lm is None:
+            raise RuntimeError("eval_forward needs a language model; this container was built with language_model=False")
+        tokens = self.encode(batch, mode=mode, variant="eval", assemble="concat", gumbel=gumbel, generator=generator)
+        inputs_embeds, attention_mask = self.llm_inputs(tokens, batch, self.model.get_input_embeddings().weight)
+        outputs = lm.generate(inputs_embeds=inputs_embeds, attention_mask=attention_mask, **(generate_configs or {}))
+        return self.fix_generated_ids(outputs, self.model.config.text_config.architectures[0])
 
     # ---- stages -------------------------------------------------------------------------------------------
     @torch.no_grad()

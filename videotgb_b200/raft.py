@@ -74,24 +74,27 @@ def _encoder(out_dim: int, batch_norm: bool) -> nn.Module:
 
 
 class InputPadder:
-    """Pads images so that both sides are divisible by 8 (xraft.py:29-49)."""
+    """Replicate-pads [..., H, W] images up to the next multiple of 8 on both sides (xraft.py:29-49): centred padding in
+    'sintel' mode, bottom-only rows otherwise."""
 
     def __init__(self, dims, mode="sintel"):
         self.ht, self.wd = dims[-2:]
-        pad_ht = (((self.ht // 8) + 1) * 8 - self.ht) % 8
-        pad_wd = (((self.wd // 8) + 1) * 8 - self.wd) % 8
-        if mode == "sintel":
-            self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, pad_ht // 2, pad_ht - pad_ht // 2]
-        else:
-            self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, 0, pad_ht]
+        rows, cols = -self.ht % 8, -self.wd % 8
+        top = rows // 2 if mode == "sintel" else 0
+        self._pad = [cols // 2, cols - cols // 2, top, rows - top]          # F.pad order: left, right, top, bottom
 
     def pad(self, input):
         return F.pad(input, self._pad, mode="replicate")
 
     def unpad(self, x):
-        ht, wd = x.shape[-2:]
-        c = [self._pad[2], ht - self._pad[3], self._pad[0], wd - self._pad[1]]
-        return x[..., c[0]:c[1], c[2]:c[3]]
+        left, right, top, bottom = self._pad
+        return x[..., top: x.shape[-2] - bottom, left: x.shape[-1] - right]
+
+
+def dp_state_to_normal(state_dict):
+    """raft_utils/utils.py:85-91: a `torch.nn.DataParallel` checkpoint -> plain keys.  As in the reference, ONLY keys
+    that start with `module` survive, with every `module.` removed."""
+    return {k.replace("module.", ""): v for k, v in state_dict.items() if k.startswith("module")}
 
 
 class RAFT(_KernelModule):

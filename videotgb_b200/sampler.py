@@ -91,6 +91,40 @@ class RopeBertModel(_KernelModule):
     def get_input_embeddings(self):
         return self.embeddings.word_embeddings
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, config=None, **unused):
+        """`RopeBertModel.from_pretrained(sampler_name_or_path, config=BertConfig(fusion_layer=6, encoder_width=768))`
+        (LSTP_SF_blip2_module.py:88-89).  The reference initialises from a plain BERT checkpoint (`bert-base-uncased`):
+        HF strips the `bert.` base-model prefix (xropebert.py:805) and renames legacy `LayerNorm.gamma/beta`; everything
+        the checkpoint does not hold -- temporal_embeddings, cross-attention, the rotary tables, mrc_head -- keeps its
+        fresh initialisation (N(0, 0.02) weights, xropebert.py:821-835).  A VideoTGB checkpoint (keys already in this
+        model's naming, optionally under `temporal_encoder.`) loads the same way."""
+        from .containers import _report, read_checkpoint
+        if config is None:
+            import transformers
+            config = transformers.BertConfig.from_pretrained(pretrained_model_name_or_path)
+        model = cls(config)
+        own = model.state_dict()
+        mapped, unexpected = {}, []
+        for k, v in read_checkpoint(pretrained_model_name_or_path).items():
+            k2 = k
+            for prefix in ("temporal_encoder.", "bert."):
+                if k2.startswith(prefix):
+                    k2 = k2[len(prefix):]
+            k2 = k2.replace("LayerNorm.gamma", "LayerNorm.weight").replace("LayerNorm.beta", "LayerNorm.bias")
+            if k2 in own and tuple(own[k2].shape) == tuple(v.shape):
+                mapped[k2] = v.float() if v.is_floating_point() else v
+            elif not k2.endswith("position_ids"):
+                unexpected.append(k)
+        res = model.load_state_dict(mapped, strict=False)
+        model.loaded_keys = sorted(mapped)
+        # a plain BERT checkpoint leaves the sampler-specific parameters at their initialisation, as in the reference
+        _report([], [k for k in unexpected if not k.startswith(("cls.", "bert.pooler.", "model.", "of_extractor."))],
+                f"RopeBertModel.from_pretrained({pretrained_model_name_or_path})")
+        model.missing_keys = list(res.missing_keys)
+        model.eval()
+        return model
+
     def _pack(self):
         if self._packed is not None:
             return self._packed
