@@ -1,21 +1,38 @@
 #!/usr/bin/env python
 """Headline benchmark: frames/sec through sampler + ViT-g + Q-Former (+ projection) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one synthetic batch of BASELINE.json config 2 per rank
-(32 videos x 64 candidate frames 224^2, 32-frame optical flow, sampler selects 32 frames per video -> 1024 frames
-through EVA-ViT-g (39 layers), the BLIP-2 Q-Former and language_projection -> [32, 1024, 2048] LLM tokens):
+Default (`--config 2`, the line the driver records): a "step" is one pass of the hot path over one synthetic batch of
+BASELINE.json config 2 per rank (32 videos x 64 candidate frames 224^2, 32-frame optical flow, sampler selects 32 frames
+per video -> 1024 frames through EVA-ViT-g (39 layers), the BLIP-2 Q-Former and language_projection -> [32, 1024, 2048]
+LLM tokens):
 
-  value  device-timed (CUDA events, max over ranks) with the inputs already resident in HBM
-  e2e    the same step through the public API (`VideoTGBEncoder.encode_u8`) from PINNED HOST buffers: H2D of the u8
-         frames, the flow and the ids inside the timed region, D2H of the resulting tokens
-  roofline      the tcgen05 GEMM kernel family: algorithmic flops of its launches / their CUDA-event time
+  value         device-timed (CUDA events, max over ranks) with the inputs already resident in HBM
+  e2e           the same step through the public API (`VideoTGBEncoder.encode_u8`) from PINNED HOST buffers: H2D of the
+                u8 frames, the flow and the ids inside the timed region, D2H of the resulting tokens
+  roofline      the dominant tcgen05 GEMM: algorithmic flops of its launches / their CUDA-event time (+ all GEMMs, ViT
+                attention, per-shape table)
+  roofline_hbm  the HBM-bound kernels of the path (gather, flow patch reduction, normalise+patchify, normalise) on
+                buffers >> L2: algorithmic bytes / CUDA-event time against the measured copy bandwidth
+  gpu_reference the reference's own PyTorch path on the same GPU (oracle port under torch.autocast(bf16): cuBLAS +
+                eager attention), 256 frames, next to this repo's kernels on the same frames -- the fair speed comparison
+  parity        the checker run on the timed batch: selected indices == oracle, one spot-checked frame's tokens vs the
+                fp32 oracle (north_star tolerance 2e-2 / cosine 0.999)
   cpu_baseline  the oracle port (reference algorithm, fp32 torch CPU, all host threads) on a bounded sample
 
 Weak scaling: every rank processes its own 32 videos; the only exchange is the NCCL all-gather of the bf16 Q-Former
-tokens (48 KiB/frame).  `--impl reference` times the reference algorithm (oracle port) on the host cores.
+tokens (48 KiB/frame), written by the last LayerNorm kernel straight into the gather buffer.
+
+The other BASELINE configs (parity-tested in tests/; these lines are for profiles/, the driver records config 2):
+  --config 3   InstructBLIP-Vicuna-7B path: 128-frame videos, 12-layer multi-modal sampler, 32 frames selected,
+               instruction-conditioned Q-Former, mean-pooled [B, 32, 4096] tokens; weak scaling (videos per rank)
+  --config 4   ONE ActivityNet-QA-shaped video: 1024 candidates sharded by frame over the N ranks, replicated span
+               selection, the 32 selected frames re-distributed evenly, tokens all-gathered; STRONG scaling
+  --config 5   sweep frames/video x batch through the whole path; one JSON line with a `sweep` array
+
+`--impl reference` times the reference algorithm (oracle port) on the host cores.
 """
 from __future__ import annotations
 
@@ -35,6 +52,7 @@ UNIT = "frames/s"
 
 # algorithmic GFLOP per selected frame: ViT-g 520.72, Q-Former (BLIP-2) 12.75, projection 0.10
 GFLOP_PER_FRAME = 533.57
+SWEEP_POINTS = [(8, 1), (8, 16), (8, 64), (32, 1), (32, 16), (32, 64), (128, 1), (128, 16), (512, 1), (512, 4), (2048, 1)]
 
 
 def parse():
@@ -43,17 +61,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--videos", type=int, default=32)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--videos", type=int, default=None, help="videos per GPU (config 2: 32, config 3: 8)")
     ap.add_argument("--nframe", type=int, default=32)
-    ap.add_argument("--candidates", type=int, default=64)
-    ap.add_argument("--lof", type=int, default=32)
+    ap.add_argument("--candidates", type=int, default=None, help="candidate frames per video (config 2: 64, 3: 128, 4: 1024)")
+    ap.add_argument("--lof", type=int, default=None, help="flow frames per video (config 2: 32; configs 3/4: = candidates)")
     ap.add_argument("--tq", type=int, default=16)
     ap.add_argument("--vit-layers", type=int, default=39, help="debug only; the reported config uses 39")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline_hbm / gpu_reference / parity (config 2)")
     ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--gpu-ref-frames", type=int, default=256)
     ap.add_argument("--profile", action="store_true",
                     help="for runs under ncu: 1 untimed warm-up + 1 step of the resident path, nothing else (not a bench value)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    defaults = {2: (32, 64, 32), 3: (8, 128, 128), 4: (1, 1024, 1024), 5: (1, 32, 32)}[a.config]
+    a.videos = defaults[0] if a.videos is None else a.videos
+    a.candidates = defaults[1] if a.candidates is None else a.candidates
+    a.lof = defaults[2] if a.lof is None else a.lof
+    return a
 
 
 # ------------------------------------------------------------------------------------------------ CPU (oracle) arm
@@ -101,17 +127,25 @@ def cpu_reference(frames: int, steps: int, warmup: int, vit_layers: int = 39, lo
     return frames / dt, dt * 1e3, cores
 
 
+def cpu_sample_text(frames: int, lof: int) -> str:
+    return (f"bounded CPU sample of the same path: 1 video x {2 * frames} candidates ({lof}-frame flow) -> {frames} selected "
+            f"frames per step through the 39-layer ViT-g + Q-Former + projection, oracle port (torch fp32, all host threads)")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frames = args.cpu_frames if (args.steps + args.warmup) <= 10 else max(2, args.cpu_frames // 2)
-    fps, ms, cores = cpu_reference(frames, args.steps, args.warmup, args.vit_layers, args.lof, args.tq)
-    sample = f"1 video x {2 * frames} candidates -> {frames} frames per step, oracle port (torch fp32 CPU)"
+    frames = args.cpu_frames
+    lof = min(args.lof, 32)
+    fps, ms, cores = cpu_reference(frames, args.steps, args.warmup, args.vit_layers, lof, args.tq)
+    sample = cpu_sample_text(frames, lof)
+    cfg = workload_config(args)
+    cfg["cpu_sample"] = sample
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": workload_config(args),
+            "config": cfg,
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -119,6 +153,25 @@ def run_reference(args):
 
 
 def workload_config(args):
+    if args.config == 3:
+        return {"workload": f"BASELINE config 3: InstructBLIP-Vicuna-7B path, {args.videos} long videos x {args.candidates} frames "
+                            f"per GPU, 12-layer multi-modal sampler selects {args.nframe} frames, instruction-conditioned Q-Former, "
+                            f"mean-pooled [B,32,4096] tokens, bf16",
+                "videos_per_gpu": args.videos, "nframe": args.nframe, "candidates": args.candidates, "flow_frames": args.lof,
+                "vit_layers": args.vit_layers, "llm_hidden": 4096, "parallelism": "video sharding, dp",
+                "l2": "flushed_between_steps"}
+    if args.config == 4:
+        return {"workload": f"BASELINE config 4: one ActivityNet-QA-shaped video, {args.candidates} candidate frames scored, top-k "
+                            f"span gather of {args.nframe} frames, candidates sharded by frame across the GPUs, bf16",
+                "videos": 1, "nframe": args.nframe, "candidates": args.candidates, "flow_frames": args.lof,
+                "vit_layers": args.vit_layers, "llm_hidden": 2048,
+                "parallelism": "candidates sharded by frame; selected frames re-distributed evenly (all-to-all); token all-gather",
+                "l2": "inputs_larger_than_l2"}
+    if args.config == 5:
+        return {"workload": "BASELINE config 5: throughput sweep, frames/video x batch per GPU through the whole path "
+                            "(candidates = flow frames = frames/video), bf16",
+                "points": [list(p) for p in SWEEP_POINTS], "vit_layers": args.vit_layers, "llm_hidden": 2048,
+                "parallelism": "video sharding, dp", "l2": "flushed_between_points"}
     return {"workload": f"BASELINE config 2: BLIP2-Flan-T5-xl path, {args.videos} videos x {args.nframe} sampled frames 224^2 "
                         f"(from {args.candidates} candidates, {args.lof}-frame flow) per GPU, bf16",
             "videos_per_gpu": args.videos, "nframe": args.nframe, "candidates": args.candidates, "flow_frames": args.lof,
@@ -169,37 +222,244 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
+# ------------------------------------------------------------------------------------------------ GPU arm: shared
 def gemm_flops(shape):
     m, n, k, _ = shape
     return 2.0 * m * n * k
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from types import SimpleNamespace as NS
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except OSError:
+        return {}
+
+
+class Ctx:
+    """Process-group / device plumbing shared by the config runners."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path (use --impl reference)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        torch.manual_seed(1234)
+        self.peaks = load_peaks()
+        self._flush = None
+
+    def encoder(self, instruct=False, llm_hidden=2048, max_pos=512, flow_extractor=False):
+        from types import SimpleNamespace as NS
+        from videotgb_b200.pipeline import VideoTGBEncoder
+        torch = self.torch
+        torch.manual_seed(1234)                      # identical random-init weights on every rank
+        with torch.device(self.dev):
+            enc = VideoTGBEncoder(NS(num_hidden_layers=self.args.vit_layers), None,
+                                  NS(fusion_layer=6, encoder_width=768, max_position_embeddings=max_pos), llm_hidden,
+                                  instruct=instruct, with_flow_extractor=flow_extractor)
+            with torch.no_grad():
+                enc.model.query_tokens.normal_(0.0, 0.02)
+        return enc.eval()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flush_l2(self):
+        """Write a buffer larger than the 126 MB L2 (used where a step's inputs are smaller than L2)."""
+        if self._flush is None:
+            self._flush = self.torch.empty(256 << 20, dtype=self.torch.uint8, device=self.dev)
+        self._flush.fill_(1)
+
+    def timed(self, fn, steps, whole=False, flush=False):
+        """CUDA-event time per step on the launching stream, barrier + synchronize on both sides, MAX over ranks."""
+        torch = self.torch
+        self.barrier()
+        if flush:                                    # per-step events so the flush itself stays outside the timed time
+            total = 0.0
+            for _ in range(steps):
+                self.flush_l2()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                total += e0.elapsed_time(e1)
+            ms = torch.tensor([total / steps], device=self.dev)
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if whole:
+                fn(steps)
+            else:
+                for _ in range(steps):
+                    fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / steps], device=self.dev)
+        self.barrier()
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return ms.item()
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def base_line(args, ctx, value, ms, scaling="weak"):
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args)}
+
+
+# ------------------------------------------------------------------------------------------------ extras (config 2)
+def hbm_roofline(ctx):
+    """HBM-bound kernels of the path on buffers >> the 126 MB L2: algorithmic bytes per launch /
+    average CUDA-event launch time, against MEASURED_PEAKS.json hbm_gbs."""
+    torch, dev = ctx.torch, ctx.dev
+    from videotgb_b200 import ops
+    peak = ctx.peaks.get("hbm_gbs", 6550.0)
+
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    rows = []
+
+    def row(kernel, unit_bytes, units, unit, ms):
+        gbs = unit_bytes * units / ms / 1e6
+        rows.append({"kernel": kernel, "bound": "hbm", "bytes_per_unit": unit_bytes, "units_per_launch": units, "unit": unit,
+                     "avg_launch_ms": round(ms, 4), "achieved": round(gbs, 1), "peak": peak, "frac": round(gbs / peak, 3)})
+
+    f = 2048
+    u8 = torch.randint(0, 256, (f, 224, 224, 3), dtype=torch.uint8, device=dev)
+    idx = torch.sort(torch.randint(0, 64, (32, 32), device=dev), dim=1).values
+    row("gather_frames_kernel (u8 decoded frames, the product path)", 2 * 150528, 1024, "selected frame",
+        timeit(lambda: ops.gather_frames(u8.view(32, 64, 224, 224, 3), idx)))
+    row("patchify_u8_pair_kernel (A0 normalise fused into A10 im2col, bf16 out)", 150528 + 256 * 592 * 2, f, "frame",
+        timeit(lambda: ops.patchify_u8(u8, 14, 592)))
+    row("normalize_u8_kernel (A0, fp32 TCHW out: the reference's layout)", 150528 + 602112, f, "frame",
+        timeit(lambda: ops.normalize_frames_u8(u8)))
+    del u8
+    src = torch.randn(16, 64, 3, 224, 224, device=dev)
+    idx16 = idx[:16].contiguous()
+    row("gather_frames_kernel (fp32 frames, the reference's dtype)", 2 * 602112, 512, "selected frame",
+        timeit(lambda: ops.gather_frames(src, idx16)))
+    del src
+    flow = torch.randn(1024, 2, 224, 224, device=dev)
+    fcw = torch.randn(196, device=dev)
+    row("of_patch_reduce_kernel (A1 flow embedding: conv+fc reassociated)", 401408, 1024, "candidate flow frame",
+        timeit(lambda: ops.of_patch_reduce(flow, fcw)))
+    del flow
+    torch.cuda.empty_cache()
+    return {"peak_source": "MEASURED_PEAKS.json hbm_gbs" if ctx.peaks else "fallback 6550", "unit": "GB/s",
+            "l2": "buffers_larger_than_l2", "kernels": rows}
+
+
+def gpu_reference(ctx, enc, frames):
+    """The reference's own PyTorch path on this GPU: the oracle port of the ViT-g + Q-Former forward under
+    torch.autocast(bf16) (what Lightning `precision: bf16` runs: cuBLAS GEMMs, eager softmax attention), on `frames`
+    frames, next to this repo's kernels on the SAME frames and weights.  A reported baseline; oracle code is only the
+    thing being compared against."""
+    torch, dev = ctx.torch, ctx.dev
+    from oracle import torch_ref
+    m = enc.model
+    vsd = dict(m.vision_model.state_dict())
+    qsd = dict(m.qformer.state_dict())
+    px = torch.randn(frames, 3, 224, 224, device=dev)
+    qt = m.query_tokens.detach().expand(frames, -1, -1)
+
+    def torch_path():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            img, _ = torch_ref.vit_forward(vsd, px, layers=ctx.args.vit_layers)
+            return torch_ref.qformer_forward(qsd, qt, img, None)
+
+    def ours():
+        with torch.no_grad():
+            img = m.vision_model(pixel_values=px, return_dict=True).last_hidden_state
+            return m.qformer(query_embeds=qt, encoder_hidden_states=img)[0]
+
+    def timeit(fn, iters=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    a, b = torch_path().float(), ours().float()
+    rel = ((a - b).abs().max() / a.abs().max()).item()
+    ms_t, ms_o = timeit(torch_path), timeit(ours)
+    del px
+    torch.cuda.empty_cache()
+    return {"what": "reference PyTorch GPU path (oracle port, torch.autocast bf16, cuBLAS + eager attention): "
+                    "ViT-g + BLIP-2 Q-Former on the same B200, same frames and weights",
+            "frames": frames, "value": frames / ms_t * 1e3, "unit": UNIT, "ms": ms_t,
+            "ours_same_frames": {"value": frames / ms_o * 1e3, "ms": ms_o}, "speedup": ms_t / ms_o,
+            "max_rel_diff_between_the_two": rel}
+
+
+def parity_block(ctx, enc, resident, gen):
+    """The checker on the timed batch: one more step with explicit Gumbel noise; the oracle re-derives the selection from
+    the same logits + noise (bit-exact), and one spot-checked frame goes through the fp32 oracle ViT-g + Q-Former +
+    projection on the GPU (north_star tolerance)."""
+    torch, dev = ctx.torch, ctx.dev
+    from oracle import select_ref, torch_ref, transform_ref
+    b, lof = resident["of"].shape[:2]
+    k = resident["nframe"]
+    gum = [-torch.empty(2 * b, lof, 1, device=dev).exponential_(generator=gen).log() for _ in range(2)]
+    out, aux = enc.encode_u8(resident, gumbel=gum, return_aux=True)
+    torch.cuda.synchronize()
+    sl, el = aux.start_logits.cpu(), aux.end_logits.cpu()
+    draws = [select_ref.gumbel_argmax(sl, el, g.cpu()) for g in gum]
+    want_idx = select_ref.select_batch([d[0] for d in draws], [d[1] for d in draws], resident["of_lengths"].tolist(),
+                                       resident["frames_u8"].shape[1], k)
+    idx_equal = bool(torch.equal(aux.indices.cpu(), want_idx))
+    vid, pos = b // 2, k // 3                                      # the spot-checked frame
+    frame = resident["frames_u8"][vid, int(want_idx[vid, pos])].cpu().numpy()[None]
+    px = torch.from_numpy(transform_ref.normalize_u8_thwc(frame)).to(dev)
+    m = enc.model
+    with torch.no_grad():
+        img, _ = torch_ref.vit_forward(dict(m.vision_model.state_dict()), px, layers=ctx.args.vit_layers)
+        qo = torch_ref.qformer_forward(dict(m.qformer.state_dict()), m.query_tokens.detach(), img, None)
+        want = torch.nn.functional.linear(qo, m.language_projection.weight, m.language_projection.bias)[0]
+    got = out[vid, pos * 32: (pos + 1) * 32].float()
+    rel = ((got - want).abs().max() / want.abs().max()).item()
+    cos = torch.nn.functional.cosine_similarity(got.flatten().double(), want.flatten().double(), dim=0).item()
+    return {"checker": "oracle (select_ref on the batch's own logits + noise; torch_ref fp32 on the GPU for one frame)",
+            "indices_equal_oracle": idx_equal, "videos_checked": b, "spot_frame": {"video": vid, "position": pos},
+            "tokens_max_rel_err": rel, "tokens_cosine": cos, "tolerance": {"max_rel_err": 2e-2, "cosine": 0.999},
+            "ok": bool(idx_equal and rel <= 2e-2 and cos >= 0.999)}
+
+
+# ------------------------------------------------------------------------------------------------ config 2 (headline)
+def run_config2(args, ctx):
+    torch, dist, dev, rank, world = ctx.torch, ctx.dist, ctx.dev, ctx.rank, ctx.world
     from videotgb_b200 import ops
     from videotgb_b200.distributed import TokenAllGather
-    from videotgb_b200.pipeline import VideoTGBEncoder
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path (use --impl reference)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(1234)
-
-    with torch.device(dev):
-        enc = VideoTGBEncoder(NS(num_hidden_layers=args.vit_layers), None, NS(fusion_layer=6, encoder_width=768), 2048)
-        with torch.no_grad():
-            enc.model.query_tokens.normal_(0.0, 0.02)
-    enc.eval()
+    enc = ctx.encoder()
     if world > 1:
         enc.token_exchange = TokenAllGather()
 
@@ -276,28 +536,6 @@ def run_ours(args):
                 ev_out.record(d2h_stream)
         main.wait_event(ev_out)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, whole=False):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if whole:
-            fn(steps)
-        else:
-            for _ in range(steps):
-                fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
-        barrier()
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
     if args.profile:
         step_resident()
         torch.cuda.synchronize()
@@ -307,16 +545,16 @@ def run_ours(args):
         return
     for _ in range(max(3, args.warmup)):
         step_resident()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(ctx.local)
     if rank == 0:
         clocks.start()
     launches0 = ops.LAUNCHES
-    ms = timed(step_resident, args.steps)
+    ms = ctx.timed(step_resident, args.steps)
     launches = ops.LAUNCHES - launches0
     clock_info = clocks.stop() if rank == 0 else None
 
     run_e2e(2)                                   # warm the pinned paths
-    ms_e2e = timed(run_e2e, args.steps, whole=True)
+    ms_e2e = ctx.timed(run_e2e, args.steps, whole=True)
 
     # ---- roofline leg: CUDA-event time of every GEMM launch of one more step (same stream, same shapes)
     with ops.profile_launches() as prof:
@@ -324,6 +562,7 @@ def run_ours(args):
     gemm_ms = sum(t for (nm, shp, t) in prof.records if nm == "gemm")
     gemm_fl = sum(gemm_flops(shp) for (nm, shp, t) in prof.records if nm == "gemm")
     attn_ms = sum(t for (nm, shp, t) in prof.records if nm == "attention")
+    vit_attn_ms = sum(t for (nm, shp, t) in prof.records if nm == "attention" and shp[1:] == (16, 257, 257, 88))
     ln_ms = sum(t for (nm, shp, t) in prof.records if nm == "layernorm")
     n_gemm = sum(1 for r in prof.records if r[0] == "gemm")
     by_shape = {}
@@ -334,42 +573,56 @@ def run_ours(args):
             e[1] += t
     # the dominant kernel = the GEMM shape with the largest share of the step (fc1 + GELU of the ViT MLP)
     dom_shape, (dom_n, dom_ms) = max(by_shape.items(), key=lambda kv: kv[1][1])
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except OSError:
-        pass
+    peaks = ctx.peaks
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_hbm = peaks.get("hbm_gbs", 6550.0)
     achieved_tf = gemm_flops(dom_shape) / (dom_ms / dom_n * 1e-3) / 1e12
     all_gemm_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, None
     try:                      # DRAM bytes of that launch from the committed `ncu --set full` capture (profiles/)
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tr = json.load(f)
         if list(dom_shape) == tr.get("shape"):
             traffic = tr.get("dram_bytes_per_launch")
+            traffic_note = f"constant from the committed ncu capture {tr.get('source', 'profiles/roofline_traffic.json')}, not measured in this run"
+        else:
+            traffic_note = f"no committed ncu capture for shape {list(dom_shape)} (profiles/roofline_traffic.json holds {tr.get('shape')})"
     except (OSError, ValueError):
-        pass
+        traffic_note = "profiles/roofline_traffic.json missing"
     epi_names = {0: "bias", 1: "bias+erf-GELU", 2: "bias (fp32 out)", 3: "bias+fp32 residual", 4: "row-bias (patch embed)",
                  5: "bias+ReLU", 6: "folded LayerNorm+bias", 7: "folded LayerNorm+bias+erf-GELU",
                  8: "bias+fp32 residual+bf16 copy+LayerNorm statistics"}
+    # ViT attention against both of its roofs: 4*S^2*d flops per head; fused-QKV read + ctx write bytes
+    nf_total = b * k
+    attn_flops = 4.0 * 257 * 257 * 88 * 16 * nf_total * args.vit_layers
+    attn_bytes = nf_total * 257 * (4224 + 1408) * 2.0 * args.vit_layers
+    attention = None
+    if vit_attn_ms > 0:
+        attention = {"kernel": "vit_attention_pp_kernel (tcgen05)", "ms_per_step": vit_attn_ms,
+                     "tflops": attn_flops / (vit_attn_ms * 1e-3) / 1e12, "frac_of_tensor_peak": attn_flops / (vit_attn_ms * 1e-3) / 1e12 / peak_tf,
+                     "hbm_gbs": attn_bytes / (vit_attn_ms * 1e-3) / 1e9, "frac_of_hbm_peak": attn_bytes / (vit_attn_ms * 1e-3) / 1e9 / peak_hbm}
+
+    extras = {}
+    if not args.no_extras:
+        if rank == 0:
+            extras["roofline_hbm"] = hbm_roofline(ctx)
+            extras["gpu_reference"] = gpu_reference(ctx, enc, args.gpu_ref_frames)
+            ex, enc.token_exchange = enc.token_exchange, None          # the checker step is local to rank 0
+            extras["parity"] = parity_block(ctx, enc, resident, gen)
+            enc.token_exchange = ex
+        ctx.barrier()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     frames_total = b * k * world
-    line = {
-        "metric": METRIC, "value": frames_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+    line = base_line(args, ctx, frames_total / (ms * 1e-3), ms)
+    line.update({
         "e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e},
         "gpu_launches": launches,
         "clocks": clock_info,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_note,
                      "kernel": f"gemm_bf16_tcgen05_kernel M={dom_shape[0]} N={dom_shape[1]} K={dom_shape[2]} "
                                f"epilogue={epi_names.get(dom_shape[3], dom_shape[3])}",
                      "launches": dom_n, "avg_launch_ms": dom_ms / dom_n, "share_of_step": dom_ms / ms,
@@ -377,21 +630,217 @@ def run_ours(args):
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                      "all_gemm": {"launches": n_gemm, "ms_per_step": gemm_ms, "tflops": all_gemm_tf,
                                   "frac": all_gemm_tf / peak_tf if peak_tf else None},
-                     "gemm_shapes": [{"M": k[0], "N": k[1], "K": k[2], "epilogue": epi_names.get(k[3], k[3]), "launches": v[0],
-                                      "ms": round(v[1], 3), "tflops": round(gemm_flops(k) * v[0] / (v[1] * 1e-3) / 1e12, 1)}
-                                     for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]],
-                     "attention_ms_per_step": attn_ms, "layernorm_ms_per_step": ln_ms},
+                     "gemm_shapes": [{"M": kk[0], "N": kk[1], "K": kk[2], "epilogue": epi_names.get(kk[3], kk[3]), "launches": v[0],
+                                      "ms": round(v[1], 3), "tflops": round(gemm_flops(kk) * v[0] / (v[1] * 1e-3) / 1e12, 1),
+                                      "frac": round(gemm_flops(kk) * v[0] / (v[1] * 1e-3) / 1e12 / peak_tf, 3)}
+                                     for kk, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]],
+                     "attention_ms_per_step": attn_ms, "vit_attention": attention, "layernorm_ms_per_step": ln_ms},
         "path_tflops": frames_total / world * GFLOP_PER_FRAME / (ms * 1e-3) / 1e3,
         "path_frac_of_peak": (b * k * GFLOP_PER_FRAME / (ms * 1e-3) / 1e3) / peak_tf if peak_tf else None,
-    }
+    })
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
-        fps, cms, cores = cpu_reference(args.cpu_frames, 1, 1, args.vit_layers, args.lof, args.tq)
+        lof_cpu = min(lof, 32)
+        fps, cms, cores = cpu_reference(args.cpu_frames, 1, 1, args.vit_layers, lof_cpu, args.tq)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"1 video x {2 * args.cpu_frames} candidates -> {args.cpu_frames} frames, 1 timed step "
-                                          f"after 1 warm-up, oracle port (torch fp32 CPU), {cms:.0f} ms"}
+                                "sample": cpu_sample_text(args.cpu_frames, lof_cpu) + f"; 1 timed step after 1 warm-up, {cms:.0f} ms"}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ config 3
+def run_config3(args, ctx):
+    """InstructBLIP-Vicuna-7B path: each rank encodes its own `videos` long videos (weak scaling)."""
+    torch, dev, rank, world = ctx.torch, ctx.dev, ctx.rank, ctx.world
+    from videotgb_b200 import ops
+    enc = ctx.encoder(instruct=True, llm_hidden=4096, max_pos=max(512, args.lof + 2))
+    b, t, k, tq, tt = args.videos, args.candidates, args.nframe, args.tq, 24
+    g = torch.Generator().manual_seed(77 + rank)
+    host = {
+        "frames_u8": torch.randint(0, 256, (b, t, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory(),
+        "of": (torch.randn(b, args.lof, 2, 224, 224, generator=g) * 0.25).pin_memory(),
+        "of_mask": torch.ones(b, args.lof + 2, dtype=torch.long).pin_memory(),
+        "sampler_question": torch.randint(1000, 30522, (b, tq), generator=g).pin_memory(),
+        "sampler_question_attention_mask": torch.ones(b, tq, dtype=torch.long).pin_memory(),
+        "qformer_text": torch.randint(1000, 30522, (b, tt), generator=g).pin_memory(),
+        "qformer_text_attention_mask": torch.ones(b, tt, dtype=torch.long).pin_memory(),
+    }
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    lengths = torch.full((b,), args.lof, dtype=torch.int32, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    resident = dict({kk: v.to(dev) for kk, v in host.items()}, of_lengths=lengths, nframe=k)
+    dev_in = {kk: torch.empty_like(v, device=dev) for kk, v in host.items()}
+    out_host = torch.empty((b, 32, 4096), dtype=torch.float32).pin_memory()
+
+    def step():
+        return enc.encode_u8(resident, mode="multi_modal", variant="ratio", assemble="mean", generator=gen)
+
+    def step_e2e():
+        for kk, v in host.items():
+            dev_in[kk].copy_(v, non_blocking=True)
+        out = enc.encode_u8(dict(dev_in, of_lengths=lengths, nframe=k), mode="multi_modal", variant="ratio", assemble="mean",
+                            generator=gen)
+        out_host.copy_(out, non_blocking=True)
+
+    one = dict({kk: v[:1].contiguous() for kk, v in resident.items() if torch.is_tensor(v) and kk != "of_lengths"},
+               of_lengths=lengths[:1], nframe=k)
+
+    def step_one():
+        return enc.encode_u8(one, mode="multi_modal", variant="ratio", assemble="mean", generator=gen)
+
+    for _ in range(max(3, args.warmup)):
+        step(); step_one()
+    clocks = ClockSampler(ctx.local)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.LAUNCHES
+    ms = ctx.timed(step, args.steps, flush=True)
+    launches = ops.LAUNCHES - l0
+    clock_info = clocks.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = ctx.timed(step_e2e, args.steps, flush=True)
+    ms_one = ctx.timed(step_one, max(args.steps, 10), flush=True)
+    if rank != 0:
+        return
+    frames_total = b * k * world
+    line = base_line(args, ctx, frames_total / (ms * 1e-3), ms)
+    line.update({"e2e": {"value": frames_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                         "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e},
+                 "gpu_launches": launches, "clocks": clock_info,
+                 "candidate_frames_per_s": b * t * world / (ms * 1e-3), "videos_per_s": b * world / (ms * 1e-3),
+                 "single_video_latency_ms": ms_one})
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ config 4
+def run_config4(args, ctx):
+    """ONE long video, candidates sharded by frame over the ranks (strong scaling).  `value` counts the candidate frames
+    the path processes per second (every candidate is scored; `nframe` of them are encoded)."""
+    torch, dist, dev, rank, world = ctx.torch, ctx.dist, ctx.dev, ctx.rank, ctx.world
+    from videotgb_b200 import ops
+    t, k, tq = args.candidates, args.nframe, args.tq
+    if t % world:
+        raise SystemExit("--candidates must divide by the number of GPUs")
+    enc = ctx.encoder(max_pos=t + 2)
+    g = torch.Generator().manual_seed(4321)                  # the same video on every rank; each keeps its shard only
+    tl = t // world
+    frames = torch.randint(0, 256, (1, t, 224, 224, 3), generator=g, dtype=torch.uint8)[:, rank * tl: (rank + 1) * tl]
+    of = (torch.randn(1, t, 2, 224, 224, generator=g) * 0.25)[:, rank * tl: (rank + 1) * tl]
+    host = {"frames_u8": frames.contiguous().pin_memory(), "of": of.contiguous().pin_memory()}
+    common = dict(of_mask=torch.ones(1, t + 2, dtype=torch.long, device=dev),
+                  of_lengths=torch.tensor([t], dtype=torch.int32, device=dev),
+                  sampler_question=torch.randint(1000, 30522, (1, tq), generator=g).to(dev),
+                  sampler_question_attention_mask=torch.ones(1, tq, dtype=torch.long, device=dev), nframe=k)
+    resident = dict(common, **{kk: v.to(dev) for kk, v in host.items()})
+    dev_in = {kk: torch.empty_like(v, device=dev) for kk, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = torch.empty((1, k * 32, 2048), dtype=torch.float32).pin_memory()
+    gen = torch.Generator(device=dev).manual_seed(17)         # same seed everywhere; rank 0's draw is broadcast anyway
+
+    def run(batch):
+        if world == 1:
+            return enc.encode_u8(batch, generator=gen)
+        return enc.encode_sharded_u8(batch, generator=gen)
+
+    def step():
+        return run(resident)
+
+    def step_e2e():
+        for kk, v in host.items():
+            dev_in[kk].copy_(v, non_blocking=True)
+        out_host.copy_(run(dict(common, **dev_in)), non_blocking=True)
+
+    # stage times (resident inputs): scoring all candidates vs the rest (select + redistribute + encode + gather)
+    def score_only():
+        return enc.temporal_encoder(encoder_embeds=resident["of"], attention_mask=resident["of_mask"],
+                                    encoder_hidden_states=resident["sampler_question"],
+                                    encoder_attention_mask=resident["sampler_question_attention_mask"], mode="fusion",
+                                    flow_group=(dist.group.WORLD if world > 1 else None))
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    clocks = ClockSampler(ctx.local)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.LAUNCHES
+    ms = ctx.timed(step, args.steps)
+    launches = ops.LAUNCHES - l0
+    clock_info = clocks.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = ctx.timed(step_e2e, args.steps)
+    score_only()
+    ms_score = ctx.timed(score_only, args.steps)
+    if rank != 0:
+        return
+    line = base_line(args, ctx, t / (ms * 1e-3), ms, scaling="strong")
+    line.update({"e2e": {"value": t / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
+                         "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e},
+                 "gpu_launches": launches, "clocks": clock_info, "counts": "candidate frames per second (all scored, nframe encoded)",
+                 "ms_per_video": ms, "selected_frames_per_s": k / (ms * 1e-3), "score_ms": ms_score,
+                 "select_redistribute_encode_gather_ms": ms - ms_score, "frames_encoded_per_rank": k // world,
+                 "candidates_per_rank": tl})
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ config 5
+def run_config5(args, ctx):
+    """Sweep frames/video x batch per GPU; every rank runs its own batch (weak scaling), time = max over ranks."""
+    torch, dev, rank, world = ctx.torch, ctx.dev, ctx.rank, ctx.world
+    from videotgb_b200 import ops
+    from videotgb_b200.distributed import TokenAllGather
+    enc = ctx.encoder(max_pos=2112)
     if world > 1:
-        dist.destroy_process_group()
+        enc.token_exchange = TokenAllGather()
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    rows, l0 = [], ops.LAUNCHES
+    clocks = ClockSampler(ctx.local)
+    if rank == 0:
+        clocks.start()
+    for k, b in SWEEP_POINTS:
+        batch = {
+            "frames_u8": torch.randint(0, 256, (b, k, 224, 224, 3), dtype=torch.uint8, device=dev),
+            "of": torch.randn(b, k, 2, 224, 224, device=dev) * 0.25,
+            "of_mask": torch.ones(b, k + 2, dtype=torch.long, device=dev),
+            "of_lengths": torch.full((b,), k, dtype=torch.int32, device=dev),
+            "sampler_question": torch.randint(1000, 30522, (b, 16), device=dev),
+            "sampler_question_attention_mask": torch.ones(b, 16, dtype=torch.long, device=dev),
+            "nframe": k,
+        }
+
+        def step():
+            out = enc.encode_u8(batch, generator=gen)
+            if enc.token_exchange is not None:
+                enc.token_exchange.wait()
+            return out
+
+        for _ in range(3):
+            step()
+        steps = 3 if b * k >= 512 else 10
+        ms = ctx.timed(step, steps, flush=True)
+        rows.append({"frames_per_video": k, "videos_per_gpu": b, "frames_per_gpu": b * k, "ms_per_step": round(ms, 3),
+                     "frames_per_s": round(b * k * world / ms * 1e3, 1), "timed_steps": steps})
+        del batch
+        torch.cuda.empty_cache()
+    clock_info = clocks.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    best = max(rows, key=lambda r: r["frames_per_s"])
+    line = base_line(args, ctx, best["frames_per_s"], best["ms_per_step"])
+    line.update({"gpu_launches": ops.LAUNCHES - l0, "clocks": clock_info, "sweep": rows,
+                 "value_is": f"the best sweep point ({best['frames_per_video']} frames/video x {best['videos_per_gpu']} videos per GPU)"})
+    if world == 1 and not args.no_cpu_baseline:
+        fps, cms, cores = cpu_reference(args.cpu_frames, 1, 1, args.vit_layers, 8, args.tq)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": cpu_sample_text(args.cpu_frames, 8) + f"; 1 timed step after 1 warm-up, {cms:.0f} ms "
+                                          "(the CPU path's cost per frame does not depend on the sweep point)"}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    try:
+        {2: run_config2, 3: run_config3, 4: run_config4, 5: run_config5}[args.config](args, ctx)
+    finally:
+        ctx.finish()
 
 
 if __name__ == "__main__":

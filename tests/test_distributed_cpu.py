@@ -60,23 +60,31 @@ def _worker_frames(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from videotgb_b200.distributed import all_gather_frame_rows, all_gather_selected_tokens, owned_selection
+        from videotgb_b200.distributed import (all_gather_encoded_tokens, all_gather_frame_rows, encode_plan,
+                                               redistribute_selected_frames)
         g = torch.Generator().manual_seed(1)
-        b, t_local, d, nframe = 2, 5, 16, 6
+        b, t_local, d = 2, 5, 16
         full = torch.randn(b, world * t_local, d, generator=g)                  # every rank can rebuild the truth
         got = all_gather_frame_rows(full[:, rank * t_local: (rank + 1) * t_local].contiguous())
         ok = torch.equal(got, full)
-        # selection spread unevenly over the ranks (4 frames on rank 0, 2 on rank 1), and one rank owning nothing
-        for sel in ([0, 1, 3, 4, 7, 9], [5, 5, 6, 7, 8, 9]):
-            idx = torch.tensor(sel)
-            mine, first, counts = owned_selection(idx, rank, t_local)
-            toks = torch.randn(world * t_local, 4, d, generator=torch.Generator().manual_seed(2))   # token of global frame f
-            local = toks[[m + rank * t_local for m in mine]] if mine else torch.zeros(0, 4, d)
-            out = all_gather_selected_tokens(local, counts, nframe)
-            ok = ok and torch.equal(out, toks[sel]) and sum(counts) == nframe and len(mine) == counts[rank] if rank < len(counts) else ok
+        # the whole video's u8 frames (every rank can rebuild the truth); rank r holds [r*t_local, (r+1)*t_local)
+        video = torch.randint(0, 256, (1, world * t_local, 4, 4, 3), generator=torch.Generator().manual_seed(7), dtype=torch.uint8)
+        shard = video[:, rank * t_local: (rank + 1) * t_local].contiguous()
+        toks = torch.randn(world * t_local, 4, d, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16)
+        # selections: spread over both ranks; clustered entirely in rank 1's range; duplicates; odd k (uneven split)
+        for sel in ([0, 1, 3, 4, 7, 9], [5, 5, 6, 7, 8, 9], [0, 0, 1, 1, 2, 2], [2, 3, 8], [1, 2, 3, 4, 6]):
+            plan = encode_plan(sel, rank, world, t_local)
+            k = len(sel)
+            ok = ok and plan.counts == [(r + 1) * k // world - r * k // world for r in range(world)]
+            ok = ok and sum(plan.send_splits) == len(plan.send_local) and sum(plan.recv_splits) == plan.hi - plan.lo
+            mine = redistribute_selected_frames(shard, plan)
+            ok = ok and torch.equal(mine, video[0, sel[plan.lo: plan.hi]])       # the frames this rank ENCODES, in order
+            out = all_gather_encoded_tokens(toks[sel[plan.lo: plan.hi]].contiguous(), plan.counts)
+            ok = ok and torch.equal(out, toks[sel])
         q.put((rank, bool(ok)))
     except Exception as e:                                  # noqa: BLE001
-        q.put((rank, repr(e)))
+        import traceback
+        q.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
 
@@ -93,6 +101,27 @@ def test_frame_sharded_gathers_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)], res
+
+
+def test_encode_plan_is_even_and_consistent():
+    """Host logic of the config-4 split for every world size: positions are split evenly, and what rank s sends to
+    rank d is exactly what d expects from s."""
+    from videotgb_b200.distributed import encode_plan
+    import random
+    rnd = random.Random(0)
+    for world in (1, 2, 4, 8):
+        t_local = 1024 // world
+        for k in (4, 32, 33):
+            for _ in range(10):
+                lo = rnd.randrange(0, 1024 - 64)
+                sel = sorted(rnd.choice(range(lo, lo + 64)) for _ in range(k))          # clustered span, duplicates
+                plans = [encode_plan(sel, r, world, t_local) for r in range(world)]
+                assert [p.hi - p.lo for p in plans] == plans[0].counts and sum(plans[0].counts) == k
+                assert max(plans[0].counts) - min(plans[0].counts) <= 1
+                for s_ in range(world):
+                    for d_ in range(world):
+                        assert plans[s_].send_splits[d_] == plans[d_].recv_splits[s_]
+                    assert [i + s_ * t_local for i in plans[s_].send_local] == [i for i in sel if i // t_local == s_]
 
 
 def test_shard_videos_covers_everything():

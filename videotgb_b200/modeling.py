@@ -66,6 +66,16 @@ def _cfg(config, name, default=None):
     return default if v is None else v
 
 
+def _default_return_dict(config) -> bool:
+    """`config.use_return_dict` of the reference (transformers 4.36); transformers 5 renamed it to `return_dict`."""
+    d = getattr(config, "__dict__", {})
+    for name in ("return_dict", "_return_dict", "use_return_dict"):
+        if d.get(name) is not None:
+            return bool(d[name])
+    v = getattr(config, "return_dict", None)
+    return True if v is None else bool(v)
+
+
 class _KernelModule(nn.Module):
     """Common plumbing: lazily packed bf16 weights, invalidated whenever parameters may have changed."""
 
@@ -138,6 +148,20 @@ class _GraphCache:
             dst.copy_(src)
         graph.replay()
         return tuple(t.clone() for t in static_out)
+
+
+def _attach_bf16(t: torch.Tensor, copy: torch.Tensor) -> None:
+    """Remember the kernels' own bf16 rendering of an fp32 output (the next stage's tensor-core operand).  Keyed on the
+    tensor's version counter: an in-place edit of the fp32 tensor by the caller invalidates it."""
+    t._tgb_bf16 = copy
+    t._tgb_bf16_version = t._version
+
+
+def _cached_bf16(t: torch.Tensor) -> Optional[torch.Tensor]:
+    c = getattr(t, "_tgb_bf16", None)
+    if c is None or getattr(t, "_tgb_bf16_version", None) != t._version or c.shape != t.shape:
+        return None
+    return c
 
 
 def _model_output(cls_name: str, **kw):
@@ -335,7 +359,7 @@ class Blip2VisionModel(_KernelModule):
 
     def forward(self, pixel_values: Optional[torch.Tensor] = None, output_attentions: Optional[bool] = None,
                 output_hidden_states: Optional[bool] = None, return_dict: Optional[bool] = None):
-        return_dict = return_dict if return_dict is not None else _cfg(self.config, "use_return_dict", True)
+        return_dict = return_dict if return_dict is not None else _default_return_dict(self.config)
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")
         if output_attentions or output_hidden_states:
@@ -349,7 +373,7 @@ class Blip2VisionModel(_KernelModule):
         cols = ops.patchify(px, self.patch, pk.kpad)
         last, last_bf16 = self.encode_patches(cols, nf)
         pooled = ops.layernorm(last[:, 0, :], pk.post[0], pk.post[1], self.eps, want_bf16=False, want_f32=True)[1]
-        last._tgb_bf16 = last_bf16                  # lets the Q-Former skip a re-cast of its K/V operand
+        _attach_bf16(last, last_bf16)               # lets the Q-Former skip a re-cast of its K/V operand
         if not return_dict:
             return (last, pooled)
         return _model_output("BaseModelOutputWithPooling", last_hidden_state=last, pooler_output=pooled,
@@ -362,7 +386,7 @@ class Blip2VisionModel(_KernelModule):
         pk = self._pack()
         cols = ops.patchify_u8(frames_thwc, self.patch, pk.kpad)
         last, last_bf16 = self.encode_patches(cols, frames_thwc.shape[0])
-        last._tgb_bf16 = last_bf16
+        _attach_bf16(last, last_bf16)
         return last
 
 
@@ -456,8 +480,8 @@ class _QFormerBase(_KernelModule):
         return of, ob
 
     def _image_operand(self, encoder_hidden_states: torch.Tensor) -> torch.Tensor:
-        cached = getattr(encoder_hidden_states, "_tgb_bf16", None)
-        if cached is not None and cached.shape == encoder_hidden_states.shape:
+        cached = _cached_bf16(encoder_hidden_states)
+        if cached is not None:
             return cached.reshape(-1, cached.shape[-1])
         e = encoder_hidden_states
         if e.dtype == torch.bfloat16:
@@ -470,10 +494,12 @@ class _QFormerBase(_KernelModule):
             return None
         return ((1.0 - mask.to(torch.float32)) * value).contiguous()
 
-    def _run_layers(self, layers, x_f32, x_bf16, nf, seq, nq, img, s_img, self_mask, cross_mask):
+    def _run_layers(self, layers, x_f32, x_bf16, nf, seq, nq, img, s_img, self_mask, cross_mask, final_bf16_out=None):
+        """-> (fp32, bf16) [nf*seq, d].  `final_bf16_out` (bf16 [nf*nq, d], contiguous): the LAST LayerNorm of the query
+        rows writes its bf16 result there -- e.g. straight into this rank's slot of the NCCL all-gather buffer."""
         d, h, hd = self.hidden, self.heads, self.head_dim
         scale = 1.0 / math.sqrt(hd)
-        for lp in layers:
+        for li, lp in enumerate(layers):
             # self-attention over all `seq` rows (queries + instruction tokens)
             qkv = ops.gemm(x_bf16, lp.qkv_w, lp.qkv_b, ops.EPI_BF16)
             ctx = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nf, h, seq, seq, hd, scale, self_mask)
@@ -496,7 +522,10 @@ class _QFormerBase(_KernelModule):
                 q_f32, q_bf16 = self._post_ln(acc, c.o_ln, self.eps)
             inter = ops.gemm(q_bf16, lp.iq_w, lp.iq_b, ops.EPI_BF16_GELU)
             acc = ops.gemm(inter, lp.oq_w, lp.oq_b, ops.EPI_F32_RESID, resid=q_f32)
-            q_f32, q_bf16 = self._post_ln(acc, lp.oq_ln, self.eps)
+            if final_bf16_out is not None and li == len(layers) - 1:
+                q_bf16, q_f32 = ops.layernorm(acc, lp.oq_ln[0], lp.oq_ln[1], self.eps, out_bf16=final_bf16_out, want_f32=True)
+            else:
+                q_f32, q_bf16 = self._post_ln(acc, lp.oq_ln, self.eps)
             if seq > nq:
                 inter = ops.gemm(t_bf16, lp.it_w, lp.it_b, ops.EPI_BF16_GELU)
                 acc = ops.gemm(inter, lp.ot_w, lp.ot_b, ops.EPI_F32_RESID, resid=t_f32)
@@ -505,10 +534,12 @@ class _QFormerBase(_KernelModule):
                 x_bf16 = torch.cat([q_bf16.view(nf, nq, d), t_bf16.view(nf, seq - nq, d)], 1).view(-1, d)
             else:
                 x_f32, x_bf16 = q_f32, q_bf16
-        return x_f32
+        return x_f32, x_bf16
 
-    def _finish(self, x_f32, nf, seq, return_dict):
+    def _finish(self, x_f32, nf, seq, return_dict, x_bf16=None):
         seq_out = x_f32.view(nf, seq, self.hidden)
+        if x_bf16 is not None:       # the same values rounded to bf16 (written by the last LayerNorm): projection / NCCL operand
+            _attach_bf16(seq_out, x_bf16.view(nf, seq, self.hidden))
         pooled = seq_out[:, 0, :]
         if not return_dict:
             return (seq_out, pooled)
@@ -533,8 +564,11 @@ class Blip2QFormerModel(_QFormerBase):
     def forward(self, query_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, head_mask=None,
                 encoder_hidden_states: Optional[torch.Tensor] = None,
                 encoder_attention_mask: Optional[torch.Tensor] = None, past_key_values=None, use_cache=None,
-                output_attentions=None, output_hidden_states=None, return_dict: Optional[bool] = None):
-        return_dict = return_dict if return_dict is not None else _cfg(self.config, "use_return_dict", True)
+                output_attentions=None, output_hidden_states=None, return_dict: Optional[bool] = None,
+                tokens_out_bf16: Optional[torch.Tensor] = None):
+        """`tokens_out_bf16` (extension, bf16 [F, 32, 768] contiguous): receives the bf16 copy of the output directly from
+        the last LayerNorm kernel (the all-gather send slot, distributed.TokenAllGather.slot)."""
+        return_dict = return_dict if return_dict is not None else _default_return_dict(self.config)
         if past_key_values is not None or output_attentions or output_hidden_states or head_mask is not None:
             raise NotImplementedError("KV cache / attention outputs / head masks are not on the VideoTGB hot path")
         self._device_check(query_embeds)
@@ -549,13 +583,20 @@ class Blip2QFormerModel(_QFormerBase):
         self_mask = self._additive(attention_mask, -10000.0)
         # image masks are all-ones on this path (LSTP_SF_blip2_module.py:469); the additive form is exact either way
         cross_mask = self._additive(encoder_attention_mask, torch.finfo(torch.float32).min)
+        if tokens_out_bf16 is not None and (tokens_out_bf16.dtype != torch.bfloat16 or not tokens_out_bf16.is_contiguous()
+                                            or tokens_out_bf16.numel() != nf * nq * d):
+            raise ValueError("tokens_out_bf16 must be a contiguous bf16 [F, num_query, hidden] tensor")
         if self_mask is None and cross_mask is None and img is not None and self._use_graph(nf):
             def body(xf, xb, im):
-                return (self._run_layers(pk.layers, xf, xb, nf, nq, nq, im, s_img, None, None),)
-            (x,) = self._graphs.run(("qformer", nf, nq, s_img), [x_f32, x_bf16, img], body)
+                return self._run_layers(pk.layers, xf, xb, nf, nq, nq, im, s_img, None, None)
+            x, xb = self._graphs.run(("qformer", nf, nq, s_img), [x_f32, x_bf16, img], body)
+            if tokens_out_bf16 is not None:
+                tokens_out_bf16.view(-1, d).copy_(xb)
+                xb = tokens_out_bf16.view(-1, d)
         else:
-            x = self._run_layers(pk.layers, x_f32, x_bf16, nf, nq, nq, img, s_img, self_mask, cross_mask)
-        return self._finish(x, nf, nq, return_dict)
+            x, xb = self._run_layers(pk.layers, x_f32, x_bf16, nf, nq, nq, img, s_img, self_mask, cross_mask,
+                                     None if tokens_out_bf16 is None else tokens_out_bf16.view(-1, d))
+        return self._finish(x, nf, nq, return_dict, xb)
 
 
 class InstructBlipQFormerModel(_QFormerBase):
@@ -586,7 +627,7 @@ class InstructBlipQFormerModel(_QFormerBase):
                 encoder_hidden_states: Optional[torch.Tensor] = None,
                 encoder_attention_mask: Optional[torch.Tensor] = None, past_key_values=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, return_dict: Optional[bool] = None):
-        return_dict = return_dict if return_dict is not None else _cfg(self.config, "use_return_dict", True)
+        return_dict = return_dict if return_dict is not None else _default_return_dict(self.config)
         if input_ids is None and query_embeds is None:
             raise ValueError("You have to specify query_embeds when input_ids is None")
         if query_embeds is None:
@@ -621,5 +662,5 @@ class InstructBlipQFormerModel(_QFormerBase):
             s_img = encoder_hidden_states.shape[1]
         self_mask = self._additive(attention_mask, -10000.0)
         cross_mask = self._additive(encoder_attention_mask, torch.finfo(torch.float32).min)
-        x = self._run_layers(pk.layers, x_f32.view(-1, d), x_bf16.view(-1, d), nf, seq, nq, img, s_img, self_mask, cross_mask)
+        x, _ = self._run_layers(pk.layers, x_f32.view(-1, d), x_bf16.view(-1, d), nf, seq, nq, img, s_img, self_mask, cross_mask)
         return self._finish(x, nf, seq, return_dict)

@@ -19,6 +19,7 @@ from torch import nn
 from . import ops, selection
 from .containers import (Blip2ForConditionalGeneration, InstructBlipForConditionalGeneration,  # noqa: F401
                          LanguageProjection)
+from .modeling import _cached_bf16
 from .sampler import RopeBertModel
 
 
@@ -96,8 +97,12 @@ class VideoTGBEncoder(nn.Module):
     def tokens(self, sampled_pixel_values: torch.Tensor, batch_size: int, batch=None, assemble: str = "concat",
                widths=None) -> torch.Tensor:
         """A10-A16: frames -> `language_model_inputs` ([B, nframe*32, H_llm] concat, or [B, 32, H_llm] mean-pooled)."""
+        image_embeddings = self.model.vision_model(pixel_values=sampled_pixel_values, return_dict=True).last_hidden_state
+        return self.assemble(self._query_output(image_embeddings, batch_size, batch), batch_size, assemble, widths)
+
+    def _query_output(self, image_embeddings: torch.Tensor, batch_size: int, batch=None) -> torch.Tensor:
+        """A14 / A15 as the task modules call the Q-Former (LSTP_SF_blip2_module.py:471-477, LSTP_SF_module.py:545-560)."""
         m = self.model
-        image_embeddings = m.vision_model(pixel_values=sampled_pixel_values, return_dict=True).last_hidden_state
         nf = image_embeddings.shape[0]
         query_tokens = m.query_tokens.expand(nf, -1, -1)
         if self.instruct:
@@ -107,18 +112,20 @@ class VideoTGBEncoder(nn.Module):
             qmask = torch.ones(query_tokens.shape[:-1], dtype=torch.long, device=ids.device)
             out = m.qformer(input_ids=ids, attention_mask=torch.cat([qmask, tmask], dim=1), query_embeds=query_tokens,
                             encoder_hidden_states=image_embeddings, encoder_attention_mask=None, return_dict=True)
-            query_output = out.last_hidden_state[:, : query_tokens.size(1), :]
-        else:
-            query_output = m.qformer(query_embeds=query_tokens, encoder_hidden_states=image_embeddings,
-                                     encoder_attention_mask=None)[0]
-        return self.assemble(query_output, batch_size, assemble, widths)
+            return out.last_hidden_state[:, : query_tokens.size(1), :]
+        slot = None
+        if self.token_exchange is not None:          # bf16 tokens go from the last LayerNorm straight into the NCCL buffer
+            slot = self.token_exchange.slot(nf, query_tokens.shape[1], m.qformer.hidden, image_embeddings.device)
+        return m.qformer(query_embeds=query_tokens, encoder_hidden_states=image_embeddings, encoder_attention_mask=None,
+                         tokens_out_bf16=slot)[0]
 
     def assemble(self, query_output: torch.Tensor, batch_size: int, mode: str = "concat", widths=None) -> torch.Tensor:
         m = self.model
         if self.token_exchange is not None:
             self.token_exchange.exchange(query_output)      # NCCL all-gather on a side stream, overlaps the projection
         if mode == "concat":                       # LSTP_SF_blip2_module.py:480-481
-            y = m.language_projection(query_output)
+            pre = _cached_bf16(query_output)      # the Q-Former's own bf16 rounding of these values: no re-cast
+            y = m.language_projection(query_output if pre is None else pre)
             return y.reshape(batch_size, -1, y.shape[-1])
         if mode != "mean":
             raise ValueError(mode)
@@ -152,21 +159,8 @@ class VideoTGBEncoder(nn.Module):
 
     def tokens_from_u8(self, sampled_u8: torch.Tensor, batch_size: int, batch=None, assemble: str = "concat"):
         """Same as `tokens` for u8 THWC frames: normalise (A0) is fused into the patchify kernel."""
-        m = self.model
-        image_embeddings = m.vision_model.forward_u8(sampled_u8)
-        nf = image_embeddings.shape[0]
-        query_tokens = m.query_tokens.expand(nf, -1, -1)
-        if self.instruct:
-            nframe = nf // batch_size
-            ids = torch.repeat_interleave(batch["qformer_text"], nframe, 0)
-            tmask = torch.repeat_interleave(batch["qformer_text_attention_mask"], nframe, 0)
-            qmask = torch.ones(query_tokens.shape[:-1], dtype=torch.long, device=ids.device)
-            out = m.qformer(input_ids=ids, attention_mask=torch.cat([qmask, tmask], dim=1), query_embeds=query_tokens,
-                            encoder_hidden_states=image_embeddings, return_dict=True)
-            query_output = out.last_hidden_state[:, : query_tokens.size(1), :]
-        else:
-            query_output = m.qformer(query_embeds=query_tokens, encoder_hidden_states=image_embeddings)[0]
-        return self.assemble(query_output, batch_size, assemble)
+        image_embeddings = self.model.vision_model.forward_u8(sampled_u8)
+        return self.assemble(self._query_output(image_embeddings, batch_size, batch), batch_size, assemble)
 
     # ---- the whole path -----------------------------------------------------------------------------------
     @torch.no_grad()
@@ -192,8 +186,11 @@ class VideoTGBEncoder(nn.Module):
                           return_aux: bool = False):
         """BASELINE config 4: ONE long video whose candidates are sharded by frame over `group` (rank r holds frames and
         flow [r*T_local, (r+1)*T_local) in `frames_u8` [1,T_local,H,W,3] and `of` [1,T_local,2,H,W]; `of_mask`,
-        `of_lengths`, the question and `nframe` describe the whole video).  Every rank returns the same
-        `language_model_inputs` [1, nframe*32, H_llm] the unsharded `encode_u8` produces."""
+        `of_lengths`, the question and `nframe` describe the whole video).  Scoring is sharded by candidate, the
+        selection is replicated, and the `nframe` selected frames are then re-distributed EVENLY (all-to-all of the u8
+        frames) so that every rank encodes nframe/W of them.  Every rank returns the same `language_model_inputs`
+        [1, nframe*32, H_llm] the unsharded `encode_u8` produces, bit for bit (replaces the
+        process-level chunking of eval/scripts/run_qa_activitynet.sh:16-39)."""
         import torch.distributed as dist
         from . import distributed as D
         if self.instruct:
@@ -217,17 +214,21 @@ class VideoTGBEncoder(nn.Module):
                 dist.broadcast(g, src=dist.get_global_rank(group, 0), group=group)
         cs, ce = selection.draw_spans(start_logits, end_logits, 2, 0.5, gumbel, None)
         idx = selection.select_indices(cs, ce, batch["of_lengths"], t_local * world, nframe, variant)
-        mine, _, counts = D.owned_selection(idx[0], rank, t_local)
+        plan = D.encode_plan(idx[0].tolist(), rank, world, t_local)     # one host sync per video (the reference syncs per comparison)
+        counts = plan.counts
         m = self.model
-        if mine:
-            local_idx = torch.tensor([mine], dtype=torch.int64, device=px.device)
-            sampled = ops.gather_frames(px.contiguous(), local_idx)
+        sampled = D.redistribute_selected_frames(px.contiguous(), plan, group)          # [k/W, H, W, 3] u8 per rank
+        nq, hid = m.query_tokens.shape[1], m.qformer.hidden
+        if sampled.shape[0]:
             image_embeddings = m.vision_model.forward_u8(sampled)
             query_tokens = m.query_tokens.expand(image_embeddings.shape[0], -1, -1)
-            query_output = m.qformer(query_embeds=query_tokens, encoder_hidden_states=image_embeddings)[0]
+            qout = m.qformer(query_embeds=query_tokens, encoder_hidden_states=image_embeddings)[0]
+            tokens_local = _cached_bf16(qout)
+            if tokens_local is None:
+                tokens_local = ops.cast_bf16(qout.to(torch.float32).contiguous().view(-1, hid)).view(-1, nq, hid)
         else:
-            query_output = torch.zeros((0, m.query_tokens.shape[1], self.model.qformer.hidden), dtype=torch.float32, device=px.device)
-        tokens = D.all_gather_selected_tokens(query_output.to(torch.float32).contiguous(), counts, nframe, group)
+            tokens_local = torch.zeros((0, nq, hid), dtype=torch.bfloat16, device=px.device)
+        tokens = D.all_gather_encoded_tokens(tokens_local, counts, group)               # bf16 [k, 32, 768]
         y = m.language_projection(tokens)
         out = y.reshape(1, -1, y.shape[-1])
         if return_aux:
