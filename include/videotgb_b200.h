@@ -58,8 +58,6 @@ TGB_API int tgb_normalize_frames_u8(const uint8_t* frames_thwc, float* out_tchw,
  * F.interpolate's CPU arithmetic followed by .to(torch.uint8).  S % 4 == 0.                                 */
 TGB_API int tgb_resize_bilinear_u8(const uint8_t* frames_thwc, uint8_t* out_thwc, int T, int H0, int W0, int S,
                            tgb_stream_t stream);
-/* Debug / test knob: 0 = choose (word-load kernel when the input is 4-byte aligned; default), 1 = generic byte-load kernel. */
-TGB_API int tgb_resize_set_variant(int variant);
 
 /* ---------------------------------------------------------------- A7  Gumbel span draw ----------------
  * src/models/LSTP_SF_blip2_module.py:424-428: F.gumbel_softmax(cat(start,end), tau, dim=1).argmax(dim=1)
@@ -107,8 +105,6 @@ TGB_API int tgb_gather_frames(const void* src, const int64_t* indices, void* dst
 TGB_API int tgb_patchify_f32(const float* pixels_tchw, void* out_bf16, int F, int S, int P, int ld, tgb_stream_t stream);
 TGB_API int tgb_patchify_u8(const uint8_t* frames_thwc, void* out_bf16, int F, int S, int P, int ld,
                     const float* mean3_host, const float* std3_host, tgb_stream_t stream);
-/* Debug / test knob: 0 = choose (default), 1 = never use the single-fma pair kernel for u8 frames.                  */
-TGB_API int tgb_patchify_set_variant(int variant);
 /* hidden[f, 0, :] = class_embedding + position_embedding[0]   (xblip2.py:114-116)   hidden: f32 [F, tokens, D] */
 TGB_API int tgb_fill_cls_rows(float* hidden, const float* cls, const float* pos0, int F, int tokens, int D,
                       tgb_stream_t stream);
@@ -156,14 +152,6 @@ TGB_API int tgb_ln_stats_finalize(const float* partial_stats, int M, int slots, 
 TGB_API int tgb_rowstats_cast_f32(const float* x, int64_t ldx, int M, int N, float eps, void* out_bf16, int64_t ldo,
                           float* rowstats, tgb_stream_t stream);
 
-/* Debug / test knob: 0 = choose per problem (default), 1 = single-CTA 128xBN tiles, 2 = CTA-pair 256xBN tiles.      */
-TGB_API int tgb_gemm_set_cta_group(int cta_group);
-/* Debug / A-B knob: 1 = balanced persistent tile schedule (every cluster walks all N blocks in turn; default),
- * 0 = plain round-robin.                                                                                                    */
-TGB_API int tgb_gemm_set_schedule(int balanced);
-/* Debug / test knob: epilogue warps per CTA, 0 = choose (8; the fp32-residual epilogues always run 8).               */
-TGB_API int tgb_gemm_set_epilogue_warps(int warps);
-
 /* ---------------------------------------------------------------- LayerNorm ---------------------------
  * nn.LayerNorm over the last dim (xblip2.py:222-224,511; :703,:782; xropebert.py:91).  x: f32 [M,N] (ldx).
  * Writes bf16 and/or f32 outputs (either may be NULL).  N % 4 == 0, N <= 8192.                            */
@@ -183,10 +171,6 @@ TGB_API int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int64_
  * through a 3-D TMA map, ld_qkv >= 4224).  out: bf16 [frames*257, ld_out], head h at columns 88h.                    */
 TGB_API int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int frames, float scale,
                                    tgb_stream_t stream);
-
-/* Debug / test knob: 0 = ping-pong kernel (two query tiles in flight, online softmax over two key blocks; default),
- * 1 = one-shot kernel (whole score row in tensor memory; kept as a cross-check).                                    */
-TGB_API int tgb_vit_attention_set_variant(int variant);
 
 /* ---------------------------------------------------------------- A1/A2/A4 temporal sampler -----------
  * TemporalOFEmbedding (src/models/components/xropebert.py:103-129): Conv2d(2,768,k16,s16) -> flatten(2) ->

@@ -23,7 +23,6 @@ SIGNATURES = {
     "tgb_sm_count": ([], c_int),
     "tgb_normalize_frames_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_resize_bilinear_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp], c_int),
-    "tgb_resize_set_variant": ([c_int], c_int),
     "tgb_gumbel_argmax": ([c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_vp], c_int),
     "tgb_spans_to_indices": ([c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "tgb_pseudo_span": ([c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp], c_int),
@@ -31,7 +30,6 @@ SIGNATURES = {
     "tgb_gather_frames": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_sz, c_vp], c_int),
     "tgb_patchify_f32": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp], c_int),
     "tgb_patchify_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
-    "tgb_patchify_set_variant": ([c_int], c_int),
     "tgb_fill_cls_rows": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp], c_int),
     "tgb_gemm_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_int, c_int,
                        c_vp, c_i64, c_int, c_vp], c_int),
@@ -40,9 +38,6 @@ SIGNATURES = {
     "tgb_gemm_ln_stats_slots": ([c_int, c_int], c_int),
     "tgb_ln_stats_finalize": ([c_vp, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp], c_int),
     "tgb_rowstats_cast_f32": ([c_vp, c_i64, c_int, c_int, c_f32, c_vp, c_i64, c_vp, c_vp], c_int),
-    "tgb_gemm_set_cta_group": ([c_int], c_int),
-    "tgb_gemm_set_schedule": ([c_int], c_int),
-    "tgb_gemm_set_epilogue_warps": ([c_int], c_int),
     "tgb_layernorm_f32": ([c_vp, c_i64, c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp], c_int),
     "tgb_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int,
                             c_int, c_f32, c_vp], c_int),
@@ -53,7 +48,6 @@ SIGNATURES = {
     "tgb_rope_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp], c_int),
     "tgb_linear_small_f32": ([c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp], c_int),
     "tgb_vit_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_f32, c_vp], c_int),
-    "tgb_vit_attention_set_variant": ([c_int], c_int),
     "tgb_llm_inputs_f32": ([c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_replace_ids": ([c_vp, c_i64, c_i64, c_i64, c_vp], c_int),
     "tgb_im2col_nhwc_bf16": ([c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp], c_int),
@@ -67,6 +61,16 @@ SIGNATURES = {
     "tgb_raft_prep_image": ([c_vp, c_int, c_int, c_int, c_vp, c_i64, c_vp], c_int),
     "tgb_cast_f32_bf16": ([c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp], c_int),
     "tgb_group_mean_f32": ([c_vp, c_vp, c_int, c_int, c_i64, c_vp], c_int),
+}
+
+# test / A-B knobs (csrc/tgb_debug.h): exported by the library, not part of the contract in include/videotgb_b200.h
+DEBUG_SIGNATURES = {
+    "tgb_resize_set_variant": ([c_int], c_int),
+    "tgb_patchify_set_variant": ([c_int], c_int),
+    "tgb_gemm_set_cta_group": ([c_int], c_int),
+    "tgb_gemm_set_schedule": ([c_int], c_int),
+    "tgb_gemm_set_epilogue_warps": ([c_int], c_int),
+    "tgb_vit_attention_set_variant": ([c_int], c_int),
 }
 
 _lib = None
@@ -83,7 +87,7 @@ def load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         raise TgbError(f"{LIB_PATH} is missing -- build it with `python -m videotgb_b200.build`; there is no fallback path")
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (args, res) in SIGNATURES.items():
+    for name, (args, res) in {**SIGNATURES, **DEBUG_SIGNATURES}.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res

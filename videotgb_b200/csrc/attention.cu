@@ -301,11 +301,7 @@ static int launch_attention_chunked(const AttnParams& p, cudaStream_t stream) {
   const int KC = 256;
   const size_t smem = (size_t)KC * (C::KP + C::VP) * 2 + (size_t)KC * 4;
   auto kern = attention_chunked_kernel<D>;
-  static bool configured = false;
-  if (!configured) {
-    TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const int mtiles = (p.Sq + 15) / 16;
   const int warps = mtiles < 8 ? mtiles : 8;
   dim3 grid(p.B * p.H, (mtiles + warps - 1) / warps);
@@ -321,11 +317,7 @@ static int launch_attention(const AttnParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)SkPad * (C::KP + C::VP) * 2 + (size_t)SkPad * 4;
   if (smem > 112 * 1024) return launch_attention_chunked<D>(p, stream);     // long key sequences: stream K/V
   auto kern = attention_kernel<D>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = 227 * 1024;
-  }
+  TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
   const int mtiles = (p.Sq + 15) / 16;
   int warps = mtiles < 9 ? mtiles : 9;            // 9 warps x 2 rounds cover the ViT's 17 row tiles
   kern<<<p.B * p.H, warps * 32, smem, stream>>>(p);

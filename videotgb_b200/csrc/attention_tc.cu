@@ -1118,7 +1118,7 @@ extern "C" __attribute__((visibility("default"))) int tgb_debug_attn_trace(long 
 }
 #endif
 
-static int g_vit_attention_variant = 0;   // 0 = ping-pong kernel (default), 1 = one-shot kernel (cross-check)
+static std::atomic<int> g_vit_attention_variant{0};   // 0 = ping-pong kernel (default), 1 = one-shot kernel (cross-check)
 
 extern "C" int tgb_vit_attention_set_variant(int variant) {
   TGB_CHECK_ARG(variant == 0 || variant == 1, "vit_attention_set_variant: 0 (ping-pong) or 1 (one-shot)");
@@ -1169,12 +1169,10 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
       return TGB_ECUDA;
     }
   }
-  static bool configured = false;
-  if (!configured) {
+  TGB_ONCE_PER_DEVICE({
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM_TOTAL));
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_TOTAL));
-    configured = true;
-  }
+  });
   VitAttnParams p;
   p.qkv = (const __nv_bfloat16*)qkv;
   p.out = (__nv_bfloat16*)out;

@@ -5,8 +5,10 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <cstdio>
+#include <atomic>
 
 #include "../../include/videotgb_b200.h"
+#include "tgb_debug.h"
 
 namespace tgb {
 
@@ -26,6 +28,21 @@ int cuda_status(cudaError_t e, const char* what);
   do {                                                              \
     cudaError_t _e = (call);                                        \
     if (_e != cudaSuccess) return ::tgb::cuda_status(_e, #call);    \
+  } while (0)
+
+// Per-function attributes (cudaFuncSetAttribute: the > 48 KB dynamic shared memory opt-in) apply to the CURRENT device
+// only, so "already configured" is remembered per call site AND per device.  Re-running `stmt` is idempotent, so a race
+// between two host threads costs one redundant driver call; devices beyond 63 simply reconfigure on every launch.
+#define TGB_ONCE_PER_DEVICE(stmt)                                                                   \
+  do {                                                                                              \
+    static std::atomic<unsigned long long> tgb_once_mask_{0ull};                                    \
+    int tgb_dev_ = 0;                                                                               \
+    TGB_CUDA(cudaGetDevice(&tgb_dev_));                                                             \
+    const unsigned long long tgb_bit_ = tgb_dev_ < 64 ? (1ull << tgb_dev_) : 0ull;                  \
+    if (!(tgb_once_mask_.load(std::memory_order_acquire) & tgb_bit_)) {                             \
+      stmt;                                                                                         \
+      tgb_once_mask_.fetch_or(tgb_bit_, std::memory_order_release);                                 \
+    }                                                                                               \
   } while (0)
 
 int check_device();      // TGB_OK if the current device is sm_100, else TGB_EARCH

@@ -107,24 +107,26 @@ __global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __
                                                                 float eps, float2* __restrict__ stats,
                                                                 float* __restrict__ max_ratio) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= M) return;
-  const float2* pr = part + (long long)row * slots;
-  double s = 0.0, q = 0.0;
-  for (int j = 0; j < slots; ++j) {
-    const float2 v = pr[j];
-    s += static_cast<double>(v.x);
-    q += static_cast<double>(v.y);
+  float ratio = 0.f;                       // rows past M take part in the warp reduction with a neutral value (no early exit)
+  if (row < M) {
+    const float2* pr = part + (long long)row * slots;
+    double s = 0.0, q = 0.0;
+    for (int j = 0; j < slots; ++j) {
+      const float2 v = pr[j];
+      s += static_cast<double>(v.x);
+      q += static_cast<double>(v.y);
+    }
+    const double mean = s / N;
+    double var = q / N - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    stats[row] = make_float2(static_cast<float>(mean), rstd);
+    ratio = fabsf(static_cast<float>(mean)) * rstd;
   }
-  const double mean = s / N;
-  double var = q / N - mean * mean;
-  var = var > 0.0 ? var : 0.0;
-  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  stats[row] = make_float2(static_cast<float>(mean), rstd);
   if (max_ratio != nullptr) {
-    float ratio = fabsf(static_cast<float>(mean)) * rstd;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(__activemask(), ratio, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(max_ratio), __float_as_int(ratio));
+    for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
+    if ((threadIdx.x & 31) == 0 && ratio > 0.f) atomicMax(reinterpret_cast<int*>(max_ratio), __float_as_int(ratio));
   }
 }
 

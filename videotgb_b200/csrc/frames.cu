@@ -527,7 +527,7 @@ static uint16_t bf16_bits_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 
-static int g_patchify_variant = 0;   // 0 = choose, 1 = force the table / residual-corrected kernels (tests)
+static std::atomic<int> g_patchify_variant{0};   // 0 = choose, 1 = force the table / residual-corrected kernels (tests)
 
 static Norm3 make_norm(const float* mean, const float* stdv) {
   Norm3 n;
@@ -575,11 +575,8 @@ static int patchify_common(const void* src, void* out, int F, int S, int P, int 
   cudaStream_t st_ = (cudaStream_t)stream;
 #define TGB_PATCHIFY(U, PCV, FST)                                                                                      \
   do {                                                                                                                \
-    static bool cfg = false;                                                                                          \
-    if (!cfg) {                                                                                                       \
-      TGB_CUDA(cudaFuncSetAttribute(patchify_kernel<U, PCV, FST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      cfg = true;                                                                                                     \
-    }                                                                                                                 \
+    TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(patchify_kernel<U, PCV, FST>,                                  \
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));     \
     patchify_kernel<U, PCV, FST><<<grid, 256, smem, st_>>>(src, (__nv_bfloat16*)out, items, S, P, ld, nm, nf);        \
   } while (0)
   NormFast nf = {};
@@ -614,11 +611,8 @@ static int patchify_common(const void* src, void* out, int F, int S, int P, int 
   if (fma_ok) {
     const size_t rb = ((size_t)P * S * 3 + 15) & ~(size_t)15;
     const size_t sm = 2 * rb + (size_t)(S / P) * ld * 2;
-    static bool cfg = false;
-    if (!cfg) {
-      TGB_CUDA(cudaFuncSetAttribute(patchify_u8_pair_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      cfg = true;
-    }
+    TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(patchify_u8_pair_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      200 * 1024)));
     int per = (int)((227 * 1024) / (sm + 1024));
     if (per > 8) per = 8;
     if (per < 1) per = 1;
@@ -686,7 +680,7 @@ extern "C" int tgb_patchify_set_variant(int variant) {
   return TGB_OK;
 }
 
-static int g_resize_variant = 0;   // 0 = choose (fast kernel when the input is 4-byte aligned), 1 = generic byte-load kernel
+static std::atomic<int> g_resize_variant{0};   // 0 = choose (fast kernel when the input is 4-byte aligned), 1 = generic byte-load kernel
 
 extern "C" int tgb_resize_set_variant(int variant) {
   if (variant != 0 && variant != 1) {

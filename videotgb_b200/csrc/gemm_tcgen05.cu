@@ -18,6 +18,8 @@
 // CG=1 (single-CTA, M=128 tiles) is kept for small problems and as a cross-check of the paired path.
 #include "common.cuh"
 
+#include <mutex>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -751,6 +753,8 @@ static int balanced_shift(int clusters, int m_blocks, int n_blocks, bool half_la
   static Key keys[16];
   static int vals[16];
   static int used = 0;
+  static std::mutex mu;                                     // the cache is shared by every host thread / stream
+  std::lock_guard<std::mutex> lock(mu);
   for (int i = 0; i < used; ++i)
     if (keys[i].c == clusters && keys[i].m == m_blocks && keys[i].n == n_blocks) return vals[i];
   const int rounds = (int)((tiles + clusters - 1) / clusters);
@@ -775,10 +779,10 @@ static int balanced_shift(int clusters, int m_blocks, int n_blocks, bool half_la
   return best;
 }
 
-static int g_force_cg = 0;     // 0 = choose, 1 / 2 = force (tests exercise both paths)
+static std::atomic<int> g_force_cg{0};     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
-static int g_force_ew = 0;     // 0 = choose per epilogue, 8 / 16 = force
-static int g_sched_balanced = 1;   // 1 = balanced persistent schedule (default), 0 = plain round-robin (A/B knob)
+static std::atomic<int> g_force_ew{0};     // 0 = choose per epilogue, 8 / 16 = force
+static std::atomic<int> g_sched_balanced{1};   // 1 = balanced persistent schedule (default), 0 = plain round-robin (A/B knob)
 
 template <int BN, int EPI, int CG, int EW>
 static int launch_gemm_ew(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
@@ -807,15 +811,11 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
     }
   }
   auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, EW>;
-  static bool configured = false;
-  if (!configured) {
-    TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_clusters = sm_count() / CG;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  p.sched_shift = g_sched_balanced ? balanced_shift(clusters, p.num_m_blocks, p.num_n_blocks,
+  p.sched_shift = g_sched_balanced.load() ? balanced_shift(clusters, p.num_m_blocks, p.num_n_blocks,
                                                      BN == 256 && p.N - (p.num_n_blocks - 1) * BN <= BN / 2) : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
@@ -837,7 +837,8 @@ template <int BN, int EPI, int CG>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmParams& p, cudaStream_t stream) {
   // 8 epilogue warps by default (measured with tools/gemm_ab.py: the bias / GELU epilogues are marginally better with 8
   // warps and the extra pipeline stage than with 16)
-  int ew = g_force_ew ? g_force_ew : 8;
+  const int force_ew = g_force_ew.load();
+  int ew = force_ew ? force_ew : 8;
   if (EpiTraits<EPI>::RESID) ew = 8;           // two double-buffered residual boxes per warp; the statistics slot layout
                                                // (2 per 256-column tile) is fixed
   if (ew == 16) return launch_gemm_ew<BN, EPI, CG, 16>(A, lda, W, ldw, p, stream);
@@ -881,7 +882,8 @@ static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
   int best_bn = 256, best_cg = 2;
   double best_cost = -1.0;
   for (int cg = 2; cg >= 1; --cg) {
-    if (g_force_cg && cg != g_force_cg) continue;
+    const int force_cg = g_force_cg.load();
+    if (force_cg && cg != force_cg) continue;
     const long long mblocks = (M + BM * cg - 1) / (BM * cg);
     for (int i = 0; i < 4; ++i) {
       const int bn = cands[i];

@@ -20,7 +20,8 @@ int cuda_status(cudaError_t e, const char* what) {
   return TGB_ECUDA;
 }
 
-static int g_dev_checked = -1, g_sms = 0, g_cc_major = 0;
+// per host thread: the "current device" is per-thread state, and so is this cache of its properties
+static thread_local int g_dev_checked = -1, g_sms = 0, g_cc_major = 0;
 
 static int probe() {
   int dev = 0;
@@ -55,6 +56,6 @@ int sm_count() {
 }  // namespace tgb
 
 extern "C" const char* tgb_last_error(void) { return tgb::g_err; }
-extern "C" int tgb_version(void) { return 100; }
+extern "C" int tgb_version(void) { return 200; }
 extern "C" int tgb_device_check(void) { return tgb::check_device(); }
 extern "C" int tgb_sm_count(void) { return tgb::sm_count(); }

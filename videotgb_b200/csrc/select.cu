@@ -261,11 +261,7 @@ extern "C" int tgb_gumbel_argmax(const float* logits, const float* gumbel, float
   if (R == 0) return TGB_OK;
   const size_t smem = (size_t)L * sizeof(float);
   if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      TGB_CUDA(cudaFuncSetAttribute(gumbel_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      configured = true;
-    }
+    TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(gumbel_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
   }
   gumbel_argmax_kernel<<<R, GA_THREADS, smem, (cudaStream_t)stream>>>(logits, gumbel, tau, L, (long long*)index);
   TGB_CUDA(cudaGetLastError());

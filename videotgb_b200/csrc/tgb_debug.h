@@ -1,0 +1,31 @@
+/*
+ * Test / A-B knobs of the kernels.  NOT part of the drop-in contract (include/videotgb_b200.h): they select between
+ * kernel variants that compute the same result, are process-global (atomics), and exist so that the parity tests can
+ * exercise every variant.  The library exports them; tests and tools/ bind them by name.
+ */
+#ifndef TGB_DEBUG_H_
+#define TGB_DEBUG_H_
+
+#include "../../include/videotgb_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 0 = choose (word-load kernel when the input is 4-byte aligned; default), 1 = generic byte-load kernel. */
+TGB_API int tgb_resize_set_variant(int variant);
+/* 0 = choose (default), 1 = never use the single-fma pair kernel for u8 frames. */
+TGB_API int tgb_patchify_set_variant(int variant);
+/* 0 = choose per problem (default), 1 = single-CTA 128xBN tiles, 2 = CTA-pair 256xBN tiles. */
+TGB_API int tgb_gemm_set_cta_group(int cta_group);
+/* 1 = balanced persistent tile schedule (default), 0 = plain round-robin. */
+TGB_API int tgb_gemm_set_schedule(int balanced);
+/* epilogue warps per CTA, 0 = choose (8; the fp32-residual epilogues always run 8). */
+TGB_API int tgb_gemm_set_epilogue_warps(int warps);
+/* 0 = ping-pong kernel (default), 1 = one-shot kernel (whole score row in tensor memory; cross-check). */
+TGB_API int tgb_vit_attention_set_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
