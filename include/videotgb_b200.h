@@ -65,6 +65,13 @@ TGB_API int tgb_resize_bilinear_u8(const uint8_t* frames_thwc, uint8_t* out_thwc
  * Computes softmax((logits+gumbel)/tau) in fp32 and returns the FIRST index of its maximum.               */
 TGB_API int tgb_gumbel_argmax(const float* logits, const float* gumbel, float tau, int R, int L, int64_t* index,
                       tgb_stream_t stream);
+/* One round of the draw (LSTP_SF_blip2_module.py:424-430, the body of `for i in range(top_k)`) in ONE launch, without the
+ * cat / log / neg / split statements around it: start_logits, end_logits f32 [B, L]; noise f32 [2B, L] (rows [0,B) pair
+ * with the start logits, rows [B,2B) with the end logits, as in cat(dim=0)).  noise_is_exponential = 1: `noise` holds the
+ * Exp(1) draws of torch.Tensor.exponential_ and the Gumbel noise is formed as -log(e) (torch/nn/functional.py
+ * gumbel_softmax); 0: `noise` is the Gumbel noise itself.  cand_start, cand_end: i64 [B] (row i of the [top_k, B] lists). */
+TGB_API int tgb_span_draw(const float* start_logits, const float* end_logits, const float* noise, int noise_is_exponential,
+                  float tau, int B, int L, int64_t* cand_start, int64_t* cand_end, tgb_stream_t stream);
 
 /* ---------------------------------------------------------------- A8  spans -> frame indices ----------
  * src/models/LSTP_SF_blip2_module.py:433-459 (eval), :284-312 (train, inclusive end),
@@ -180,6 +187,12 @@ TGB_API int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
  * flow f32 [frames, C, S, S]; fc_weight f32 [(S/16)^2]; z bf16 [frames, ldz], ldz >= C*256.               */
 TGB_API int tgb_of_patch_reduce(const float* flow, const float* fc_weight, void* z_bf16, int frames, int C, int S, int P,
                                 int ldz, tgb_stream_t stream);
+/* A3 masks.  out[b,i] = (1.0 - mask[b,i]) * value in fp32: get_extended_attention_mask (xropebert.py:986-1012, value
+ * -10000.0) and invert_attention_mask (value = finfo.min; the Q-Former twins xblip2.py:1033-1060).  last_index[b] =
+ * sum(mask[b,:]) - 1, the `of_mask.sum(dim=1) - 1` of TemporalOFEmbedding (xropebert.py:121).  mask i64 [B,S] of 0/1;
+ * out f32 [B,S] or NULL; last_index i32 [B] or NULL.                                                              */
+TGB_API int tgb_additive_mask(const int64_t* mask, int B, int S, float value, float* out, int32_t* last_index,
+                              tgb_stream_t stream);
 /* xropebert.py:118-127: cat(bos, y, zero row); row ends[b] := eos; += frame_pos_embed[t]; LayerNorm(eps).
  * y f32 [B, L, N]; ends i32 [B] (= of_mask.sum(1)-1); out [B, L+2, N] as f32 and/or bf16.                   */
 TGB_API int tgb_sampler_assemble(const float* y, const float* bos, const float* eos, const float* pos, const int32_t* ends,

@@ -68,6 +68,47 @@ def test_gumbel_argmax_golden_and_ties():
         assert torch.equal(ops.gumbel_argmax(lg.to(DEV), gm.to(DEV)).cpu(), torch.cat([si, ei]))
 
 
+def test_span_draw_one_launch_matches_reference_statements():
+    """`tgb_span_draw`: one round of the reference loop body (cat -> gumbel_softmax -> argmax -> split) in one launch.
+    (1) explicit Gumbel noise: the golden fixtures and the two-pointer form equal the cat() form; (2) Exp(1) draws:
+    -log(e) formed inside the kernel gives the same indices as torch's own `-e.log()` feeding F.gumbel_softmax's formula,
+    and `draw_spans(generator=)` reproduces F.gumbel_softmax run on the device with the same generator state."""
+    import torch.nn.functional as F
+    from videotgb_b200 import selection
+    z = np.load(os.path.join(GOLDEN, "gumbel.npz"))
+    for tag in "abc":
+        s, e, g = (torch.from_numpy(z[f"{tag}_{k}"]).to(DEV) for k in ("start", "end", "gumbel"))
+        b = s.shape[0]
+        cs = torch.empty(b, dtype=torch.int64, device=DEV)
+        ce = torch.empty(b, dtype=torch.int64, device=DEV)
+        ops.span_draw(s[..., 0].contiguous(), e[..., 0].contiguous(), g[..., 0].contiguous(), False, 0.5, cs, ce)
+        want = torch.from_numpy(z[f"{tag}_index"])[:, 0]
+        assert torch.equal(torch.cat([cs, ce]).cpu(), want)
+    gen = torch.Generator(device=DEV).manual_seed(77)
+    for b, length in ((32, 34), (3, 1026), (2, 4000)):
+        s = torch.randn(b, length, 1, device=DEV, generator=gen)
+        e = torch.randn(b, length, 1, device=DEV, generator=gen)
+        ex = torch.empty(2 * b, length, device=DEV).exponential_(generator=gen)
+        cs = torch.empty(b, dtype=torch.int64, device=DEV)
+        ce = torch.empty(b, dtype=torch.int64, device=DEV)
+        ops.span_draw(s[..., 0].contiguous(), e[..., 0].contiguous(), ex, True, 0.5, cs, ce)
+        want = ((torch.cat([s, e], 0)[..., 0] + (-ex.log())) / 0.5).softmax(1).argmax(1)
+        assert torch.equal(torch.cat([cs, ce]), want)
+        # the whole draw against F.gumbel_softmax with the same device generator state (the reference statement)
+        state = gen.get_state()
+        got_s, got_e = selection.draw_spans(s, e, top_k=2, tau=0.5, generator=gen)
+        gen.set_state(state)
+        torch.cuda.manual_seed(0)
+        logits = torch.cat([s, e], 0)
+        ref_s, ref_e = [], []
+        for _ in range(2):
+            gum = -torch.empty_like(logits, memory_format=torch.legacy_contiguous_format).exponential_(generator=gen).log()
+            idx = ((logits + gum) / 0.5).softmax(1).argmax(1)
+            ref_s.append(idx[:b, 0]); ref_e.append(idx[b:, 0])
+        assert torch.equal(got_s, torch.stack(ref_s)) and torch.equal(got_e, torch.stack(ref_e))
+    del F
+
+
 # ------------------------------------------------------------------------------------------------ A8
 def _run_select(cases, kw):
     out = []
@@ -516,18 +557,20 @@ def test_attention(b, h, sq, sk, d, masked):
     assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("frames,scale_in,late_peak", [(1, 1.0, False), (3, 1.0, False), (19, 2.5, False), (2, 1.0, True),
-                                                       (150, 1.0, False)])
+                                                       (150, 1.0, False), (300, 1.0, True)])
 def test_vit_attention_tcgen05(frames, scale_in, late_peak, variant):
-    """The tensor-memory attention kernels (0: ping-pong, two key blocks with online softmax; 1: one-shot) vs torch and
-    vs the mma.sync kernel.  `late_peak` plants dominant keys in the second key block (rows >= 144) for half of the
-    queries, which forces the ping-pong kernel through its accumulator-rescale path."""
+    """The tensor-memory attention kernels (0: three key blocks over a ring of score buffers, online softmax; 1: one-shot;
+    2: ping-pong, two key blocks) vs torch and vs the mma.sync kernel.  `late_peak` plants dominant keys in the later key
+    blocks (rows 150-160 and 200) for half of the queries, which forces the online-softmax kernels through their
+    accumulator-rescale path (300 frames: more than two items per CTA, so every barrier wraps with rescales in flight)."""
     g = torch.Generator().manual_seed(frames)
     qkv = (torch.randn(frames * 257, 4224, generator=g) * scale_in).to(torch.bfloat16)
     if late_peak:
         x = qkv.float().view(frames, 257, 3, 16, 88)
         x[:, 200, 1] = x[:, 5, 0] * 3.0            # key 200 aligned with query 5 (and correlated with nothing else)
+        x[:, 100, 1] = x[:, 131, 0] * 2.5          # key 100 (second of three blocks) aligned with query 131 (tile 1)
         x[:, 150:160, 1] *= 4.0                    # a band of large keys
         x[:, 1::2, 0] *= 2.0                       # odd queries sharper than even ones -> per-row decisions differ
         qkv = x.view(frames * 257, 4224).to(torch.bfloat16)

@@ -110,6 +110,61 @@ def test_vit_layernorm_fold_falls_back_on_large_row_means():
     assert m.fuse_layernorm is True and m.fold_ratio_seen <= m.fold_max_mean_over_std
 
 
+def test_vit_layernorm_fold_monitors_every_pass():
+    """The fold's safety ratio is tracked on EVERY pass, not only on the first batch after a weight load: weights whose
+    patch embedding has a common offset make the row mean follow the frame's brightness, so a benign first batch passes
+    the calibration and a later bright batch drives |row mean| / row std past the limit.  The running maximum is read
+    without a synchronisation at the start of the following call, which warns and switches to the separate LayerNorm."""
+    sd = dict(syn.vision_state_dict(syn.VisionCfg(layers=2)))
+    sd["embeddings.patch_embedding.weight"] = sd["embeddings.patch_embedding.weight"] + 0.006
+    m = Blip2VisionModel(NS(num_hidden_layers=2)).to(DEV)
+    m.load_state_dict(sd)
+    benign = cases.vit_pixels(2).to(DEV)
+    benign = benign - benign.mean(dim=(1, 2, 3), keepdim=True)              # zero pixel sum per frame
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        m(pixel_values=benign)
+    assert m.fuse_layernorm is True and m.fold_ratio_seen <= m.fold_max_mean_over_std
+    bright = torch.full_like(benign, 2.0) + 0.1 * benign
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        m(pixel_values=bright)                                              # still folded: the ratio is only recorded
+    torch.cuda.synchronize()
+    with pytest.warns(UserWarning, match="separate LayerNorm"):
+        out = m(pixel_values=bright).last_hidden_state
+    assert m.fuse_layernorm is False and m.fold_ratio_seen > m.fold_max_mean_over_std
+    with torch.no_grad():
+        ref32, _ = torch_ref.vit_forward(to_dev(sd), bright, layers=2)
+    assert_parity(out, ref32, "bright batch after the automatic fallback")
+
+
+def test_vit_layernorm_fold_eva_like_statistics():
+    """EVA-ViT-g-like residual statistics: a few massive channels (+-60..300, growing with depth) and a row mean that
+    drifts away from zero layer by layer.  Outlier channels raise the row std, so the fold's |mean| / std ratio stays
+    small and the folded LayerNorm keeps parity with the fp32 oracle (bf16's relative precision is scale-free; only a
+    large common offset costs digits)."""
+    layers = 4
+    sd = dict(syn.vision_state_dict(syn.VisionCfg(layers=layers)))
+    for i in range(layers):
+        for name in (f"encoder.layers.{i}.self_attn.projection.bias", f"encoder.layers.{i}.mlp.fc2.bias"):
+            b = sd[name].clone()
+            b += 0.15 * (i + 1)                                             # common offset: the row mean grows with depth
+            b[7] += 30.0 * (i + 1)
+            b[300] -= 75.0 * (i + 1)
+            b[1100] += 40.0 * (i + 1)
+            sd[name] = b
+    m = Blip2VisionModel(NS(num_hidden_layers=layers)).to(DEV)
+    m.load_state_dict(sd)
+    px = cases.vit_pixels(2).to(DEV)
+    out = m(pixel_values=px).last_hidden_state
+    assert m.fuse_layernorm is True, m.fold_ratio_seen
+    print(f"EVA-like statistics: max |row mean| / row std = {m.fold_ratio_seen:.3f}")
+    with torch.no_grad():
+        ref32, _ = torch_ref.vit_forward(to_dev(sd), px, layers=layers)
+    assert_parity(out, ref32, "folded LayerNorm under EVA-like statistics")
+
+
 def test_vit_u8_fast_path(vit2):
     sd, m, _, _ = vit2
     u8 = syn.synthetic_frames_u8(2, seed=11).to(DEV)

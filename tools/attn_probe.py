@@ -46,12 +46,15 @@ def probe(f, seed=0, scale_v=1.0):
 def bench(f, iters=10):
     qkv = torch.randn(f * 257, 4224, device="cuda").to(torch.bfloat16)
     out = torch.empty(f * 257, 1408, dtype=torch.bfloat16, device="cuda")
-    def one_shot():
-        ops.vit_attention_set_variant(1)
-        ops.vit_attention(qkv, f, 88 ** -0.5, out=out)
-        ops.vit_attention_set_variant(0)
-    for name, fn in (("tcgen05 ping-pong", lambda: ops.vit_attention(qkv, f, 88 ** -0.5, out=out)),
-                     ("tcgen05 one-shot", one_shot),
+    def variant(v):
+        def run():
+            ops.vit_attention_set_variant(v)
+            ops.vit_attention(qkv, f, 88 ** -0.5, out=out)
+            ops.vit_attention_set_variant(0)
+        return run
+    for name, fn in (("tcgen05 three-block", variant(0)),
+                     ("tcgen05 ping-pong", variant(2)),
+                     ("tcgen05 one-shot", variant(1)),
                      ("mma.sync", lambda: ops.attention(qkv[:, :1408], qkv[:, 1408:2816], qkv[:, 2816:], f, 16, 257, 257, 88, 88 ** -0.5, out=out))):
         for _ in range(3):
             fn()
@@ -67,9 +70,11 @@ def bench(f, iters=10):
 
 
 if __name__ == "__main__":
+    ops.vit_attention_set_variant(int(os.environ.get("TGB_ATTN_VARIANT", "0")))
     ok = True
     for f in (1, 2, 3, 20):
         ok = probe(f, seed=f) and ok
     ok = probe(4, seed=9, scale_v=3.0) and ok
     if ok and "--bench" in sys.argv:
         bench(256)
+        bench(512)

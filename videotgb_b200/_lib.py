@@ -24,6 +24,8 @@ SIGNATURES = {
     "tgb_normalize_frames_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_resize_bilinear_u8": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp], c_int),
     "tgb_gumbel_argmax": ([c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_vp], c_int),
+    "tgb_additive_mask": ([c_vp, c_int, c_int, c_f32, c_vp, c_vp, c_vp], c_int),
+    "tgb_span_draw": ([c_vp, c_vp, c_vp, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_spans_to_indices": ([c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "tgb_pseudo_span": ([c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_span_ce_loss": ([c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp], c_int),

@@ -1093,6 +1093,496 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
   }
 }
 
+// =====================================================================================================================
+// Three-block variant (default).  Same roles as the ping-pong kernel, re-cut so that no warpgroup ever waits for a
+// tensor-core round trip it does not depend on:
+//   keys   three blocks of 96 / 96 / 80 rows (65 valid in the last); a "unit" is (query tile t, key block kb), units of
+//          an item run in the order r = 2*kb + t:  (0,0) (1,0) (0,1) (1,1) (0,2) (1,2)
+//   TMEM   three S/P buffers of 96 columns used as a RING over the units (unit u -> buffer u % 3; the bf16 P aliases
+//          the first 48 columns) | O_t fp32 [288 + 96 t, +96).  S of unit u+3 is issued right behind P V of unit u --
+//          the tensor pipe executes in order, so the write of S(u+3) cannot pass the read of P(u) -- which puts the S
+//          of a warpgroup's NEXT unit in flight one whole unit ahead: when a softmax warpgroup publishes P it finds its
+//          next score block already waiting (the ping-pong kernel idled ~1.9k of 9.4k clk per item there).
+//   warps  0 TMEM alloc + TMA producer | 1 MMA issuer | 2 / 3 CLS query row (key blocks 0 + 2 / block 1) |
+//          4-7 / 8-11 softmax warpgroups of tile 0 / 1 (one thread per query row) |
+//          12-15 epilogue warpgroup: O_t / l -> bf16 -> staging tile -> bulk tensor store, for both tiles -- the
+//          softmax warpgroups go straight on to the next item instead of waiting for their last P V.
+//   online softmax over three blocks with the conditional accumulator rescale of the ping-pong kernel; the (rare)
+//   rescale first waits for the tile's previous P V on its own barrier (pv_done), because S(u) no longer implies it.
+// =====================================================================================================================
+constexpr int P3_THREADS = 16 * 32;
+constexpr int P3_KB = 96;                          // keys per block (blocks 0 and 1); block 2 = keys [192, 272)
+constexpr int P3_KB2 = 272 - 2 * P3_KB;            // 80
+constexpr int P3_VALID2 = VA_S - 2 * P3_KB;        // 65 valid keys in block 2
+constexpr uint32_t P3_COL_S = 0, P3_S_STRIDE = 96, P3_COL_O = 288, P3_O_STRIDE = 96;
+constexpr int P3_SMEM_Q = 0;
+constexpr int P3_SMEM_K = 4 * PP_Q_BYTES;
+constexpr int P3_SMEM_V = P3_SMEM_K + 2 * VA_KBLK_BYTES;
+constexpr int P3_SMEM_BAR = P3_SMEM_V + 2 * VA_KBLK_BYTES;       // 204800: 30 mbarriers + the TMEM slot
+constexpr int P3_SMEM_CLS = P3_SMEM_BAR + 256;                   // float [2 warps][96] scores | float [100] exchange
+constexpr int P3_SMEM_L = P3_SMEM_CLS + (2 * 96 + 100) * 4;  // float [2 tiles][128] row sums for the epilogue warpgroup
+constexpr int P3_SMEM_STAGE = (P3_SMEM_L + 2 * 128 * 4 + 127) / 128 * 128;
+constexpr int P3_SMEM_TOTAL = P3_SMEM_STAGE + PP_STAGE_BYTES + 1024;     // + alignment slack
+static_assert(P3_SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+constexpr int P3_BLK_BYTES = P3_KB * 128;                         // one d block of key block 0 / 1 (12288 = 12 swizzle atoms)
+constexpr int P3_BLK2_BYTES = P3_KB2 * 128;
+
+template <int NCOLS, int NVALID>
+__device__ __forceinline__ float p3_row_max(uint32_t s_addr) {
+  static_assert(NCOLS == 96 || NCOLS == 80, "two key-block widths");
+  uint32_t v[NCOLS];
+  tmem_ld32<0>(s_addr, v);
+  tmem_ld32<32>(s_addr + 32, v);
+  if (NCOLS == 96) tmem_ld32<64>(s_addr + 64, v);
+  else tmem_ld16<64>(s_addr + 64, v);
+  tmem_ld_wait();
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NVALID; j += 4) {
+    m0 = fmaxf(m0, __uint_as_float(v[j]));
+    if (j + 1 < NVALID) m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+    if (j + 2 < NVALID) m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+    if (j + 3 < NVALID) m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// CLS query row over key block BLK of three (see cls_row_block for the formulation): unnormalised O^T in `o`, the block's
+// own max `m` (log2 units) and row sum `l`.  qb = the B fragments of q.
+template <int BLK>
+__device__ __forceinline__ void cls3_part(const VitAttnParams& p, int i, uint32_t sK, uint32_t sV, uint64_t* k_full,
+                                          uint64_t* k_free, uint64_t* v_full, uint64_t* v_free, float* sc_s, int lane,
+                                          const uint32_t (&qb)[6][2], float (&o)[6][4], float& m, float& l) {
+  constexpr int NT = BLK < 2 ? P3_KB / 16 : P3_KB2 / 16;                   // 16-key tiles: 6 / 6 / 5
+  constexpr int KEY0 = BLK * P3_KB;
+  constexpr int NVALID = BLK < 2 ? P3_KB : P3_VALID2;                      // 96 / 96 / 65
+  const uint32_t ph = i & 1;
+  const int g = lane >> 2, t = lane & 3;
+  const int lrow = lane & 7, lmat = lane >> 3;
+  mbar_wait(&k_full[BLK], ph);
+  auto qk_pair = [&](int mt, bool second) {
+    uint32_t a0[6][4], a1[6][4];
+    const int key = KEY0 + mt * 16 + (lmat & 1) * 8 + lrow;
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) va_ldsm_x4(sK + va_tile_off(key, 2 * ks + (lmat >> 1)), a0[ks]);
+    if (second) {
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks) va_ldsm_x4(sK + va_tile_off(key + 16, 2 * ks + (lmat >> 1)), a1[ks]);
+    }
+    float c0e[4] = {0.f, 0.f, 0.f, 0.f}, c0o[4] = {0.f, 0.f, 0.f, 0.f}, c1e[4] = {0.f, 0.f, 0.f, 0.f}, c1o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 6; ks += 2) {
+      va_mma_16816_nv(c0e, a0[ks], qb[ks][0], qb[ks][1]);
+      va_mma_16816_nv(c0o, a0[ks + 1], qb[ks + 1][0], qb[ks + 1][1]);
+      if (second) {
+        va_mma_16816_nv(c1e, a1[ks], qb[ks][0], qb[ks][1]);
+        va_mma_16816_nv(c1o, a1[ks + 1], qb[ks + 1][0], qb[ks + 1][1]);
+      }
+    }
+    if (t == 0) {
+      sc_s[mt * 16 + g] = c0e[0] + c0o[0];
+      sc_s[mt * 16 + 8 + g] = c0e[2] + c0o[2];
+      if (second) {
+        sc_s[mt * 16 + 16 + g] = c1e[0] + c1o[0];
+        sc_s[mt * 16 + 24 + g] = c1e[2] + c1o[2];
+      }
+    }
+  };
+#pragma unroll 1
+  for (int mt = 0; mt + 1 < NT; mt += 2) qk_pair(mt, true);
+  if (NT & 1) qk_pair(NT - 1, false);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&k_free[BLK]);                      // done reading this K block (second arrival: tcgen05.commit)
+  float x[3];
+  m = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int j = it * 32 + lane;
+    x[it] = (j < NVALID) ? sc_s[j] * p.scale_log2 : -INFINITY;
+    m = fmaxf(m, x[it]);
+  }
+  m = warp_max(m);
+  l = 0.f;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    x[it] = ex2_approx(x[it] - m);                               // exp2(-inf) = 0 for masked keys
+    l += x[it];
+  }
+  l = warp_sum(l);
+  __syncwarp();                                                  // every lane has read its scores before p overwrites them
+  __nv_bfloat16* p_s = reinterpret_cast<__nv_bfloat16*>(sc_s);
+#pragma unroll
+  for (int it = 0; it < 3; ++it)
+    if (it * 32 + lane < NT * 16) p_s[it * 32 + lane] = __float2bfloat16(x[it]);
+  __syncwarp();
+  mbar_wait(&v_full[BLK], ph);
+#pragma unroll
+  for (int mt = 0; mt < 6; ++mt) { o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f; }
+  const uint32_t* p32 = reinterpret_cast<const uint32_t*>(p_s);
+#pragma unroll 1
+  for (int kk = 0; kk < NT; ++kk) {
+    const uint32_t b0 = (g == 0) ? p32[kk * 8 + t] : 0u;
+    const uint32_t b1 = (g == 0) ? p32[kk * 8 + 4 + t] : 0u;
+    const int key = KEY0 + kk * 16 + (lmat >> 1) * 8 + lrow;
+    uint32_t a[6][4];
+#pragma unroll
+    for (int mt = 0; mt < 6; ++mt) va_ldsm_x4_t(sV + va_tile_off(key, 2 * mt + (lmat & 1)), a[mt]);
+#pragma unroll
+    for (int mt = 0; mt < 6; ++mt) va_mma_16816_nv(o[mt], a[mt], b0, b1);
+  }
+  __syncwarp();                                                  // (also: every lane is done with sc_s before its next use)
+  if (lane == 0) mbar_arrive(&v_free[BLK]);                      // done reading this V block
+}
+
+// The CLS row of one item on two warps: HALF 0 takes key blocks 0 and 2 (merged in registers) and writes the result,
+// HALF 1 takes block 1 and hands (O, m, l) over through `xch` (float[100]; two barriers per item guard its reuse).
+template <int HALF>
+__device__ __forceinline__ void cls3_row(const VitAttnParams& p, int w, int i, uint32_t sK, uint32_t sV, uint64_t* k_full,
+                                         uint64_t* k_free, uint64_t* v_full, uint64_t* v_free, float* sc_s, float* xch,
+                                         int lane) {
+  const int b = w / VA_H, h = w - b * VA_H;
+  const long long row0 = (long long)b * VA_S;
+  const int g = lane >> 2, t = lane & 3;
+  // B fragments of q: b0 = d (16ks + 2t, +1), b1 = d (16ks + 8 + 2t, +1), column n = g -> only g == 0 is the real query
+  uint32_t qb[6][2];
+  {
+    const uint32_t* q32 = reinterpret_cast<const uint32_t*>(p.qkv + row0 * p.ld_qkv + h * VA_D);
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) {
+      qb[ks][0] = (g == 0) ? __ldg(q32 + ks * 8 + t) : 0u;
+      qb[ks][1] = (g == 0 && ks < 5) ? __ldg(q32 + ks * 8 + 4 + t) : 0u;      // d 88..95 does not exist
+    }
+  }
+  float o[6][4], m, l;
+  if (HALF == 1) {
+    cls3_part<1>(p, i, sK, sV, k_full, k_free, v_full, v_free, sc_s, lane, qb, o, m, l);
+    if (t == 0) {
+#pragma unroll
+      for (int mt = 0; mt < 6; ++mt) { xch[mt * 16 + g] = o[mt][0]; xch[mt * 16 + 8 + g] = o[mt][2]; }
+    }
+    if (lane == 0) { xch[96] = m; xch[97] = l; }
+    __syncwarp();
+    named_bar_sync(3, 64);                                       // published
+    named_bar_sync(3, 64);                                       // consumed
+  } else {
+    cls3_part<0>(p, i, sK, sV, k_full, k_free, v_full, v_free, sc_s, lane, qb, o, m, l);
+    float o2[6][4], m2, l2;
+    cls3_part<2>(p, i, sK, sV, k_full, k_free, v_full, v_free, sc_s, lane, qb, o2, m2, l2);
+    named_bar_sync(3, 64);
+    const float m1 = xch[96], l1 = xch[97];
+    const float mm = fmaxf(m, fmaxf(m1, m2));
+    const float f0 = ex2_approx(m - mm), f1 = ex2_approx(m1 - mm), f2 = ex2_approx(m2 - mm);
+    const float inv = 1.f / (l * f0 + l1 * f1 + l2 * f2);
+    if (t == 0) {
+      __nv_bfloat16* dst = p.out + row0 * p.ld_out + h * VA_D;
+#pragma unroll
+      for (int mt = 0; mt < 6; ++mt) {
+        dst[mt * 16 + g] = __float2bfloat16((o[mt][0] * f0 + xch[mt * 16 + g] * f1 + o2[mt][0] * f2) * inv);
+        if (mt < 5)
+          dst[mt * 16 + 8 + g] = __float2bfloat16((o[mt][2] * f0 + xch[mt * 16 + 8 + g] * f1 + o2[mt][2] * f2) * inv);
+      }
+    }
+    __syncwarp();
+    named_bar_sync(3, 64);
+  }
+}
+
+__global__ void __launch_bounds__(P3_THREADS, 1)
+vit_attention_p3_kernel(const __grid_constant__ CUtensorMap tmap96, const __grid_constant__ CUtensorMap tmap80,
+                        const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap_out,
+                        const VitAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + P3_SMEM_Q;
+  uint8_t* sK = smem + P3_SMEM_K;
+  uint8_t* sV = smem + P3_SMEM_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P3_SMEM_BAR);
+  uint64_t* q_full = bars + 0;      // [2] per query tile, one completion per item
+  uint64_t* q_free = bars + 2;      // [2]
+  uint64_t* k_full = bars + 4;      // [3] per key block
+  uint64_t* k_free = bars + 7;      // [3] tcgen05.commit + the block's CLS warp
+  uint64_t* v_full = bars + 10;     // [3]
+  uint64_t* v_free = bars + 13;     // [3]
+  uint64_t* s_full = bars + 16;     // [3] per S/P ring buffer, two completions per item
+  uint64_t* p_full = bars + 19;     // [3] 128 arrivals
+  uint64_t* pv_done = bars + 22;    // [2] per tile, one completion per unit (three per item)
+  uint64_t* o_full = bars + 24;     // [2] per tile, one completion per item
+  uint64_t* o_free = bars + 26;     // [2] 128 arrivals (epilogue warpgroup)
+  uint64_t* l_full = bars + 28;     // [2] 128 arrivals: the tile's row sums are in shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  float* cls_scores = reinterpret_cast<float*>(smem + P3_SMEM_CLS);
+  float* l_s = reinterpret_cast<float*>(smem + P3_SMEM_L);
+  uint8_t* stage = smem + P3_SMEM_STAGE;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_my = p.num_items > (int)blockIdx.x ? (p.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmap96);
+    tma_prefetch_desc(&tmap80);
+    tma_prefetch_desc(&tmap128);
+    tma_prefetch_desc(&tmap_out);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1); mbar_init(&q_free[t], 1);
+      mbar_init(&pv_done[t], 1); mbar_init(&o_full[t], 1);
+      mbar_init(&o_free[t], 128); mbar_init(&l_full[t], 128);
+    }
+    for (int k = 0; k < 3; ++k) {
+      mbar_init(&k_full[k], 1); mbar_init(&k_free[k], 2);
+      mbar_init(&v_full[k], 1); mbar_init(&v_free[k], 2);
+      mbar_init(&s_full[k], 1); mbar_init(&p_full[k], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    // Per item, loads are issued in the order the previous item releases their buffers:
+    //   K0 K1 V0 Q0 K2 Q1 V1 V2   (K_kb after S(1,kb), V_kb after P V(1,kb), Q_t after S(t,2); S(u+3) rides behind P V(u))
+    if (lane == 0) {
+      TRACE_DECL
+      for (int i = 0; i < n_my; ++i) {
+        const int w = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = w / VA_H, h = w - b * VA_H;
+        const int row0 = b * VA_S;
+        const uint32_t ph = i & 1;
+        auto load_kv = [&](uint8_t* dst, uint64_t* full, uint64_t* free_, int kb, int col_h) {
+          mbar_wait(&free_[kb], ph ^ 1);
+          mbar_arrive_expect_tx(&full[kb], 2 * (kb < 2 ? P3_BLK_BYTES : P3_BLK2_BYTES));
+#pragma unroll
+          for (int db = 0; db < 2; ++db)
+            tma_load_3d(dst + db * VA_KBLK_BYTES + kb * P3_BLK_BYTES, kb < 2 ? &tmap96 : &tmap80, &full[kb], db * 64, col_h,
+                        row0 + kb * P3_KB);
+        };
+        auto load_q = [&](int t) {
+          mbar_wait(&q_free[t], ph ^ 1);
+          mbar_arrive_expect_tx(&q_full[t], 2 * PP_Q_BYTES);
+#pragma unroll
+          for (int db = 0; db < 2; ++db)
+            tma_load_3d(sQ + (t * 2 + db) * PP_Q_BYTES, &tmap128, &q_full[t], db * 64, h, row0 + 1 + t * 128);
+        };
+        TRACE(0, i * 100 + 1);
+        load_kv(sK, k_full, k_free, 0, VA_H + h);
+        if (i == 0) load_q(0);                                   // the very first item: Q0 next to K0 so that S(0,0) can start
+        load_kv(sK, k_full, k_free, 1, VA_H + h);
+        load_kv(sV, v_full, v_free, 0, 2 * VA_H + h);
+        if (i != 0) load_q(0);
+        TRACE(0, i * 100 + 2);
+        load_kv(sK, k_full, k_free, 2, VA_H + h);
+        load_q(1);
+        load_kv(sV, v_full, v_free, 1, 2 * VA_H + h);
+        load_kv(sV, v_full, v_free, 2, 2 * VA_H + h);
+        TRACE(0, i * 100 + 3);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      TRACE_DECL
+      constexpr uint32_t idesc_s96 = umma_idesc_bf16(128, P3_KB);
+      constexpr uint32_t idesc_s80 = umma_idesc_bf16(128, P3_KB2);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 96) | (1u << 16);     // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const int total = 6 * n_my;
+      // S of unit (item i, r = 2 kb + t) into ring buffer r % 3
+      auto issue_s = [&](int i, int r) {
+        const int t = r & 1, kb = r >> 1;
+        const uint32_t ph = i & 1;
+        if (kb == 0) mbar_wait(&q_full[t], ph);
+        if (t == 0) mbar_wait(&k_full[kb], ph);
+        tc_fence_after();
+        const uint32_t d = tmem_base + P3_COL_S + (r % 3) * P3_S_STRIDE;
+        uint32_t accum = 0;
+#pragma unroll
+        for (int db = 0; db < 2; ++db) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (db == 1 && ks >= 2) break;                       // d = 96..127 is all zero
+            const uint64_t da = umma_desc_sw128(q_addr + (t * 2 + db) * PP_Q_BYTES + ks * 32);
+            const uint64_t dk = umma_desc_sw128(k_addr + db * VA_KBLK_BYTES + kb * P3_BLK_BYTES + ks * 32);
+            umma_bf16_ss(d, da, dk, kb < 2 ? idesc_s96 : idesc_s80, accum);
+            accum = 1;
+          }
+        }
+        umma_commit(&s_full[r % 3]);
+        if (t == 1) umma_commit(&k_free[kb]);
+        if (kb == 2) umma_commit(&q_free[t]);
+      };
+      auto issue_pv = [&](int i, int r) {
+        const int t = r & 1, kb = r >> 1;
+        const uint32_t ph = i & 1;
+        mbar_wait(&p_full[r % 3], r >= 3 ? 1u : 0u);
+        TRACE(1, i * 100 + 10 + r);                              // P(unit) seen
+        if (t == 0) mbar_wait(&v_full[kb], ph);
+        if (kb == 0) mbar_wait(&o_free[t], ph ^ 1);              // the previous item's epilogue has read O_t
+        tc_fence_after();
+        const uint32_t d = tmem_base + P3_COL_O + t * P3_O_STRIDE;
+        const uint32_t a = tmem_base + P3_COL_S + (r % 3) * P3_S_STRIDE;
+        const int nsteps = kb < 2 ? P3_KB / 16 : P3_KB2 / 16;
+        for (int j = 0; j < nsteps; ++j) {
+          const uint64_t db = umma_desc_mn_sw128(v_addr + (kb * (P3_KB / 16) + j) * 2048, VA_KBLK_BYTES, 1024);
+          umma_bf16_ts(d, a + j * 8, db, idesc_pv, (kb > 0 || j > 0) ? 1u : 0u);
+        }
+        umma_commit(&pv_done[t]);
+        if (kb == 2) umma_commit(&o_full[t]);
+        if (t == 1) umma_commit(&v_free[kb]);
+        TRACE(1, i * 100 + 20 + r);                              // P V(unit) issued
+      };
+      for (int u = 0; u < 3 && u < total; ++u) issue_s(0, u);
+      int i = 0, r = 0, i3 = 0, r3 = 3;                          // unit u = (i, r); unit u + 3 = (i3, r3)
+      for (int u = 0; u < total; ++u) {
+        issue_pv(i, r);
+        if (u + 3 < total) issue_s(i3, r3);
+        if (++r == 6) { r = 0; ++i; }
+        if (++r3 == 6) { r3 = 0; ++i3; }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ================================================================ CLS query row: warp 2 key blocks 0 and 2, warp 3 block 1
+    const uint32_t sK32 = smem_u32(sK), sV32 = smem_u32(sV);
+    float* sc_s = cls_scores + (warp - 2) * 96;
+    float* xch = cls_scores + 2 * 96;
+    for (int i = 0; i < n_my; ++i) {
+      const int w = (int)blockIdx.x + i * (int)gridDim.x;
+      if (warp == 2) cls3_row<0>(p, w, i, sK32, sV32, k_full, k_free, v_full, v_free, sc_s, xch, lane);
+      else cls3_row<1>(p, w, i, sK32, sV32, k_full, k_free, v_full, v_free, sc_s, xch, lane);
+    }
+  } else if (warp < 12) {
+    // ================================================================ softmax warpgroups: one thread per query row
+    const int t = (warp - 4) >> 2;               // query tile of this warpgroup
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t o_addr = lane_base + P3_COL_O + t * P3_O_STRIDE;
+    const float sl2 = p.scale_log2;
+    TRACE_DECL
+#ifdef TGB_ATTN_TRACE
+    const bool tr_on = (quarter == 0 && lane == 0);
+#define STRACE3(tag) do { if (tr_on) TRACE(4 + t, tag); } while (0)
+#else
+#define STRACE3(tag) do { } while (0)
+#endif
+    for (int i = 0; i < n_my; ++i) {
+      float mx = 0.f, l = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) {
+        const int r = 2 * kb + t;
+        const int buf = r % 3;
+        const uint32_t s_addr = lane_base + P3_COL_S + buf * P3_S_STRIDE;
+        mbar_wait(&s_full[buf], r >= 3 ? 1u : 0u);
+        STRACE3(i * 100 + 40 + kb * 10);                         // S(t,kb) seen
+        tc_fence_after();
+        if (kb == 0) {
+          mx = p3_row_max<P3_KB, P3_KB>(s_addr) * sl2;
+          l = pp_exp_block<P3_KB / 16 - 1, 16>(s_addr, sl2, -mx);
+        } else {
+          const float m1x = (kb == 1 ? p3_row_max<P3_KB, P3_KB>(s_addr) : p3_row_max<P3_KB2, P3_VALID2>(s_addr)) * sl2;
+          float f = 1.f;
+          const bool need = m1x > mx + PP_RESCALE_THRESHOLD;
+          if (need) {
+            f = ex2_approx(mx - m1x);
+            mx = m1x;
+            l *= f;
+          }
+          if (__any_sync(0xffffffffu, need)) {                   // rare: rescale this warp's 32 rows of O_t in place
+            mbar_wait(&pv_done[t], (uint32_t)(i + kb - 1) & 1u); // P V of the tile's previous block has completed
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 96; c += 8) {
+              uint32_t o[8];
+              tmem_ld8<0>(o_addr + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+              tmem_st8<0>(o_addr + c, o);
+            }
+            tmem_st_wait();
+          }
+          if (kb == 1) l += pp_exp_block<P3_KB / 16 - 1, 16>(s_addr, sl2, -mx);
+          else l += pp_exp_block<P3_VALID2 / 16, P3_VALID2 % 16>(s_addr, sl2, -mx);
+        }
+        STRACE3(i * 100 + 42 + kb * 10);                         // exponentials done
+        if (kb == 2) l_s[t * 128 + row] = l;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[buf]);
+        if (kb == 2) mbar_arrive(&l_full[t]);
+        STRACE3(i * 100 + 43 + kb * 10);                         // P(t,kb) published
+      }
+    }
+  } else {
+    // ================================================================ epilogue warpgroup (warps 12-15), both tiles
+    // O_t / l -> bf16 -> dense [128][88] staging tile (176-byte rows: conflict-free) -> one bulk tensor store per tile.
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const bool leader = (warp == 12 && lane == 0);
+    TRACE_DECL
+    for (int i = 0; i < n_my; ++i) {
+      const int w = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = w / VA_H, h = w - b * VA_H;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&l_full[t], i & 1);
+        const float inv = 1.f / l_s[t * 128 + row];
+        mbar_wait(&o_full[t], i & 1);
+        if (leader) TRACE(2, i * 100 + 60 + t);                  // O_t complete
+        tc_fence_after();
+        uint32_t o[96];
+        const uint32_t o_addr = lane_base + P3_COL_O + t * P3_O_STRIDE;
+        tmem_ld32<0>(o_addr, o);
+        tmem_ld32<32>(o_addr + 32, o);
+        tmem_ld32<64>(o_addr + 64, o);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&o_free[t]);
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the tile
+        named_bar_sync(4, 128);
+        uint4* srow = reinterpret_cast<uint4*>(stage + row * (VA_D * 2));
+#pragma unroll
+        for (int c = 0; c < 11; ++c) {                           // 88 valid d columns = 11 x 16 bytes
+          const float2 i2 = make_float2(inv, inv);
+          const float2 a = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 0]), __uint_as_float(o[8 * c + 1])), i2);
+          const float2 bq = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 2]), __uint_as_float(o[8 * c + 3])), i2);
+          const float2 d = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 4]), __uint_as_float(o[8 * c + 5])), i2);
+          const float2 e = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 6]), __uint_as_float(o[8 * c + 7])), i2);
+          uint4 v;
+          v.x = pack_bf16(a.x, a.y);
+          v.y = pack_bf16(bq.x, bq.y);
+          v.z = pack_bf16(d.x, d.y);
+          v.w = pack_bf16(e.x, e.y);
+          srow[c] = v;
+        }
+        fence_proxy_async();                                     // generic-proxy writes -> visible to the TMA (async proxy)
+        named_bar_sync(4, 128);
+        if (leader) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stage)), "r"(0), "r"(h),
+                         "r"(b * VA_S + 1 + t * 128) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          TRACE(2, i * 100 + 62 + t);                            // store issued
+        }
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every store has landed before the CTA may exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 va_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (fn) return fn;
@@ -1118,10 +1608,10 @@ extern "C" __attribute__((visibility("default"))) int tgb_debug_attn_trace(long 
 }
 #endif
 
-static std::atomic<int> g_vit_attention_variant{0};   // 0 = ping-pong kernel (default), 1 = one-shot kernel (cross-check)
+static std::atomic<int> g_vit_attention_variant{2};   // 0 = three-block kernel (default), 1 = one-shot, 2 = ping-pong (cross-checks)
 
 extern "C" int tgb_vit_attention_set_variant(int variant) {
-  TGB_CHECK_ARG(variant == 0 || variant == 1, "vit_attention_set_variant: 0 (ping-pong) or 1 (one-shot)");
+  TGB_CHECK_ARG(variant >= 0 && variant <= 2, "vit_attention_set_variant: 0 (three-block), 1 (one-shot) or 2 (ping-pong)");
   g_vit_attention_variant = variant;
   return TGB_OK;
 }
@@ -1140,13 +1630,15 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
     return TGB_ECUDA;
   }
-  CUtensorMap map, map144, map128;
+  CUtensorMap map, map144, map128, map96, map80;
   cuuint64_t dims[3] = {VA_D, 3 * VA_H, (cuuint64_t)frames * VA_S};
   cuuint64_t strides[2] = {VA_D * 2, (cuuint64_t)ld_qkv * 2};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUtensorMap* maps[3] = {&map, &map144, &map128};
-  const cuuint32_t box_rows[3] = {VA_BOX_ROWS, PP_KEYS0, 128};
-  for (int i = 0; i < 3; ++i) {
+  const int variant = g_vit_attention_variant.load();
+  CUtensorMap* maps[5] = {&map128, &map96, &map80, &map144, &map};
+  const cuuint32_t box_rows[5] = {128, P3_KB, P3_KB2, PP_KEYS0, VA_BOX_ROWS};
+  for (int i = 0; i < 5; ++i) {
+    if ((variant == 0 && i > 2) || (variant == 1 && i != 4) || (variant == 2 && (i == 1 || i == 2 || i == 4))) continue;
     cuuint32_t box[3] = {64, 1, box_rows[i]};
     CUresult r = fn(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1172,6 +1664,7 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   TGB_ONCE_PER_DEVICE({
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM_TOTAL));
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_TOTAL));
+    TGB_CUDA(cudaFuncSetAttribute(vit_attention_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM_TOTAL));
   });
   VitAttnParams p;
   p.qkv = (const __nv_bfloat16*)qkv;
@@ -1182,10 +1675,12 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   p.num_items = frames * VA_H;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
-  if (g_vit_attention_variant == 1)
+  if (variant == 1)
     vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM_TOTAL, (cudaStream_t)stream>>>(map, p);
-  else
+  else if (variant == 2)
     vit_attention_pp_kernel<<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, map_out, p);
+  else
+    vit_attention_p3_kernel<<<grid, P3_THREADS, P3_SMEM_TOTAL, (cudaStream_t)stream>>>(map96, map80, map128, map_out, p);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

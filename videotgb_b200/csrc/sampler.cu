@@ -199,9 +199,42 @@ __global__ void __launch_bounds__(256) rope_bf16_kernel(__nv_bfloat16* __restric
   }
 }
 
+// A3: additive[b, i] = (1 - mask[b, i]) * value in fp32 (the reference's two statements), and the index of the row's
+// last set position, sum(mask[b, :]) - 1, that TemporalOFEmbedding uses for the eos row.  One warp per row.
+__global__ void __launch_bounds__(256) additive_mask_kernel(const long long* __restrict__ mask, int B, int S, float value,
+                                                            float* __restrict__ out, int* __restrict__ last_index) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const long long* mr = mask + (long long)row * S;
+  long long sum = 0;
+  for (int i = lane; i < S; i += 32) {
+    const long long m = mr[i];
+    sum += m;
+    if (out) out[(long long)row * S + i] = __fmul_rn(__fsub_rn(1.0f, (float)m), value);
+  }
+  if (last_index) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) last_index[row] = (int)(sum - 1);
+  }
+}
+
 }  // namespace tgb
 
 using namespace tgb;
+
+extern "C" int tgb_additive_mask(const int64_t* mask, int B, int S, float value, float* out, int32_t* last_index,
+                                 tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(mask && (out || last_index), "additive_mask: null pointer");
+  TGB_CHECK_ARG(B >= 0 && S > 0, "additive_mask: bad shape B=%d S=%d", B, S);
+  if (B == 0) return TGB_OK;
+  additive_mask_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const long long*)mask, B, S, value, out, last_index);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
 
 static int blocks_for(long long items, int per_block, int per_sm) {
   long long b = (items + per_block - 1) / per_block;

@@ -10,19 +10,26 @@ namespace tgb {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GA_THREADS = 128;
 
-__global__ void __launch_bounds__(GA_THREADS) gumbel_argmax_kernel(const float* __restrict__ logits,
-                                                                  const float* __restrict__ gumbel, float tau, int L,
-                                                                  long long* __restrict__ index) {
+// Rows [0, split) read `logits_a` and write `index_a`, rows [split, R) read `logits_b` / write `index_b` (the start and
+// end logits of the reference's cat(), without the cat).  EXPO: `noise` holds the Exp(1) draws of
+// torch.Tensor.exponential_ and the Gumbel noise is formed here as -log(e), the statement F.gumbel_softmax makes.
+template <bool EXPO>
+__global__ void __launch_bounds__(GA_THREADS) gumbel_argmax_kernel(const float* __restrict__ logits_a,
+                                                                  const float* __restrict__ logits_b, int split,
+                                                                  const float* __restrict__ noise, float tau, int L,
+                                                                  long long* __restrict__ index_a,
+                                                                  long long* __restrict__ index_b) {
   extern __shared__ float xs[];                 // [L]
   __shared__ float red[GA_THREADS / 32];
   __shared__ int redi[GA_THREADS / 32];
   const int r = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* lr = logits + (long long)r * L;
-  const float* gr = gumbel + (long long)r * L;
+  const float* lr = r < split ? logits_a + (long long)r * L : logits_b + (long long)(r - split) * L;
+  const float* gr = noise + (long long)r * L;
   float m = -INFINITY;
   for (int i = tid; i < L; i += GA_THREADS) {
-    const float x = __fdiv_rn(__fadd_rn(lr[i], gr[i]), tau);
+    const float g = EXPO ? -logf(gr[i]) : gr[i];
+    const float x = __fdiv_rn(__fadd_rn(lr[i], g), tau);
     xs[i] = x;
     m = fmaxf(m, x);
   }
@@ -63,7 +70,8 @@ __global__ void __launch_bounds__(GA_THREADS) gumbel_argmax_kernel(const float* 
   if (tid == 0) {
     for (int w = 1; w < GA_THREADS / 32; ++w)
       if (red[w] > best || (red[w] == best && redi[w] < besti)) { best = red[w]; besti = redi[w]; }
-    index[r] = besti;
+    if (r < split) index_a[r] = besti;
+    else index_b[r - split] = besti;
   }
 }
 
@@ -261,9 +269,34 @@ extern "C" int tgb_gumbel_argmax(const float* logits, const float* gumbel, float
   if (R == 0) return TGB_OK;
   const size_t smem = (size_t)L * sizeof(float);
   if (smem > 48 * 1024) {
-    TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(gumbel_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
+    TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(gumbel_argmax_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
   }
-  gumbel_argmax_kernel<<<R, GA_THREADS, smem, (cudaStream_t)stream>>>(logits, gumbel, tau, L, (long long*)index);
+  gumbel_argmax_kernel<false><<<R, GA_THREADS, smem, (cudaStream_t)stream>>>(logits, logits, R, gumbel, tau, L,
+                                                                             (long long*)index, (long long*)index);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
+extern "C" int tgb_span_draw(const float* start_logits, const float* end_logits, const float* noise, int noise_is_exponential,
+                             float tau, int B, int L, int64_t* cand_start, int64_t* cand_end, tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(start_logits && end_logits && noise && cand_start && cand_end, "span_draw: null pointer");
+  TGB_CHECK_ARG(B >= 0 && L > 0 && L <= 40960 && tau > 0.f, "span_draw: bad shape B=%d L=%d tau=%f", B, L, tau);
+  if (B == 0) return TGB_OK;
+  const size_t smem = (size_t)L * sizeof(float);
+  if (smem > 48 * 1024) {
+    TGB_ONCE_PER_DEVICE({
+      TGB_CUDA(cudaFuncSetAttribute(gumbel_argmax_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      TGB_CUDA(cudaFuncSetAttribute(gumbel_argmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    });
+  }
+  if (noise_is_exponential)
+    gumbel_argmax_kernel<true><<<2 * B, GA_THREADS, smem, (cudaStream_t)stream>>>(start_logits, end_logits, B, noise, tau, L,
+                                                                                 (long long*)cand_start, (long long*)cand_end);
+  else
+    gumbel_argmax_kernel<false><<<2 * B, GA_THREADS, smem, (cudaStream_t)stream>>>(start_logits, end_logits, B, noise, tau, L,
+                                                                                  (long long*)cand_start, (long long*)cand_end);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

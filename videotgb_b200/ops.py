@@ -54,6 +54,11 @@ def _need(t: torch.Tensor, dtype, name: str, contiguous: bool = True) -> torch.T
         raise _lib.TgbError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
     if t.dtype != dtype:
         raise _lib.TgbError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's current stream: a tensor living elsewhere would be dereferenced
+        # from the wrong device (wrap the call in `torch.cuda.device(t.device)`)
+        raise _lib.TgbError(f"{name}: tensor is on cuda:{t.device.index} but the current device is "
+                            f"cuda:{torch.cuda.current_device()}")
     if contiguous and not t.is_contiguous():
         raise _lib.TgbError(f"{name}: expected a contiguous tensor")
     return t
@@ -112,6 +117,37 @@ def gumbel_argmax(logits: torch.Tensor, gumbel: torch.Tensor, tau: float = 0.5) 
     idx = torch.empty((lg.shape[0],), dtype=torch.int64, device=lg.device)
     check(_lib.load().tgb_gumbel_argmax(_p(lg), _p(gm), float(tau), lg.shape[0], lg.shape[1], _p(idx), _stream()))
     return idx
+
+
+def additive_mask(mask: torch.Tensor, value: float, want_out: bool = True, want_last_index: bool = False):
+    """0/1 mask [B, S] -> (fp32 additive mask (1 - mask) * value or None, int32 sum(mask) - 1 per row or None), one launch."""
+    if not isinstance(mask, torch.Tensor) or not mask.is_cuda or mask.dim() != 2:
+        raise _lib.TgbError("mask: expected a CUDA tensor [B, S]")
+    m = mask if mask.dtype == torch.int64 else mask.to(torch.int64)
+    m = _need(m.contiguous(), torch.int64, "mask")
+    b, s = m.shape
+    out = torch.empty((b, s), dtype=torch.float32, device=m.device) if want_out else None
+    last = torch.empty((b,), dtype=torch.int32, device=m.device) if want_last_index else None
+    check(_lib.load().tgb_additive_mask(_p(m), b, s, float(value), _p(out), _p(last), _stream()))
+    return out, last
+
+
+def span_draw(start_logits: torch.Tensor, end_logits: torch.Tensor, noise: torch.Tensor, noise_is_exponential: bool,
+              tau: float, cand_start: torch.Tensor, cand_end: torch.Tensor) -> None:
+    """One draw round: start/end logits f32 [B, L], noise f32 [2B, L] -> cand_start / cand_end i64 [B] (written in place,
+    typically rows of the [top_k, B] candidate lists)."""
+    sl = _need(start_logits, torch.float32, "start_logits")
+    el = _need(end_logits, torch.float32, "end_logits")
+    nz = _need(noise, torch.float32, "noise")
+    b, l = sl.shape
+    if el.shape != sl.shape or nz.shape != (2 * b, l):
+        raise _lib.TgbError("start/end logits must be [B, L] and the noise [2B, L]")
+    cs = _need(cand_start, torch.int64, "cand_start")
+    ce = _need(cand_end, torch.int64, "cand_end")
+    if cs.shape != (b,) or ce.shape != (b,):
+        raise _lib.TgbError("cand_start / cand_end must be [B]")
+    check(_lib.load().tgb_span_draw(_p(sl), _p(el), _p(nz), int(bool(noise_is_exponential)), float(tau), b, l, _p(cs), _p(ce),
+                                    _stream()))
 
 
 def spans_to_indices(cand_start: torch.Tensor, cand_end: torch.Tensor, of_lengths: torch.Tensor, num_frames: int,

@@ -167,7 +167,7 @@ class RopeBertModel(_KernelModule):
         return pk
 
     # A1
-    def embed_flow(self, of: torch.Tensor, of_mask: torch.Tensor, flow_group=None):
+    def embed_flow(self, of: torch.Tensor, of_mask: torch.Tensor, flow_group=None, ends: Optional[torch.Tensor] = None):
         """-> (f32, bf16) [B, Lof+2, 768]  (TemporalOFEmbedding.forward, xropebert.py:103-129).
 
         `flow_group`: the flow is sharded by frame over this process group (`of` holds this rank's contiguous slice,
@@ -187,7 +187,8 @@ class RopeBertModel(_KernelModule):
             y = all_gather_frame_rows(y, flow_group)
             if y.shape[1] != l_total:
                 raise ValueError(f"sharded flow covers {y.shape[1]} frames but of_mask describes {l_total}")
-        ends = (of_mask.sum(dim=1) - 1).to(torch.int32).contiguous()
+        if ends is None:
+            ends = ops.additive_mask(of_mask, 0.0, want_out=False, want_last_index=True)[1]
         return ops.sampler_assemble(y.contiguous(), pk.bos, pk.eos, pk.fpos, ends, pk.te_ln[0], pk.te_ln[1], 1e-5)
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, head_mask=None, inputs_embeds=None,
@@ -222,17 +223,18 @@ class RopeBertModel(_KernelModule):
         s = l + 2
         if attention_mask is None:
             attention_mask = torch.ones((b, s), dtype=torch.long, device=encoder_embeds.device)
-        x_f32, x_bf16 = self.embed_flow(encoder_embeds, attention_mask, flow_group)
+        # A3: both additive masks and the eos position in two launches (the reference: ~10 elementwise statements)
+        self_mask, ends = ops.additive_mask(attention_mask, -10000.0, want_last_index=True)
+        x_f32, x_bf16 = self.embed_flow(encoder_embeds, attention_mask, flow_group, ends=ends)
         x_f32, x_bf16 = x_f32.view(-1, d), x_bf16.view(-1, d)
         ids = encoder_hidden_states.to(torch.int64).contiguous()
         tq = ids.shape[1]
         if tq > pk.rope_t.shape[0] or s > pk.rope_f.shape[0]:
             raise ValueError("sequence longer than the rotary position table")
         _, txt = ops.embed_layernorm(ids.view(-1), pk.word, pk.emb_ln[0], pk.emb_ln[1], self.eps, addvec=pk.type0)
-        if encoder_attention_mask is None:
-            encoder_attention_mask = torch.ones((b, tq), dtype=torch.long, device=ids.device)
-        self_mask = ((1.0 - attention_mask.to(torch.float32)) * -10000.0).contiguous()
-        cross_mask = ((1.0 - encoder_attention_mask.to(torch.float32)) * torch.finfo(torch.float32).min).contiguous()
+        # no text mask = all ones = a zero additive mask = none at all (the kernels treat NULL as zeros)
+        cross_mask = None if encoder_attention_mask is None else \
+            ops.additive_mask(encoder_attention_mask, torch.finfo(torch.float32).min)[0]
         scale = 1.0 / math.sqrt(hd)
         for i in range(lo, hi):
             lp = pk.layers[i]

@@ -34,15 +34,18 @@ def draw_spans(start_logits: torch.Tensor, end_logits: torch.Tensor, top_k: int 
     `gumbel[i]` ([2B,L,1] or [2B,L]) overrides the i-th round's noise (parity tests feed the reference's draw).
     """
     b, l = start_logits.shape[:2]
-    logits = torch.cat([start_logits.reshape(b, l), end_logits.reshape(b, l)], dim=0).to(torch.float32).contiguous()
-    starts, ends = [], []
+    sl = start_logits.reshape(b, l).to(torch.float32).contiguous()          # no-ops for the sampler's fp32 logits
+    el = end_logits.reshape(b, l).to(torch.float32).contiguous()
+    cand = torch.empty((2, top_k, b), dtype=torch.int64, device=sl.device)
     for i in range(top_k):
-        g = gumbel[i].reshape(2 * b, l).to(torch.float32).contiguous() if gumbel is not None else \
-            gumbel_noise_like(logits, generator)
-        idx = ops.gumbel_argmax(logits, g, tau)
-        starts.append(idx[:b])
-        ends.append(idx[b:])
-    return torch.stack(starts), torch.stack(ends)
+        if gumbel is not None:
+            ops.span_draw(sl, el, gumbel[i].reshape(2 * b, l).to(torch.float32).contiguous(), False, tau, cand[0, i], cand[1, i])
+        else:
+            # the reference's draw, `-torch.empty_like(logits).exponential_().log()`: the Exp(1) kernel stays torch's (same
+            # generator stream as F.gumbel_softmax), -log and everything after it run inside the one kernel
+            e = torch.empty((2 * b, l), dtype=torch.float32, device=sl.device).exponential_(generator=generator)
+            ops.span_draw(sl, el, e, True, tau, cand[0, i], cand[1, i])
+    return cand[0], cand[1]
 
 
 def select_indices(cand_start: torch.Tensor, cand_end: torch.Tensor, of_lengths, num_frames: int, nframe: int,
