@@ -61,3 +61,32 @@ def test_persistent_schedule_covers_every_tile_once_and_balances():
     _, bal = _walk(clusters, nb, mb, best)
     mean = sum(rr) / clusters
     assert max(rr) > 1.06 * mean and max(bal) < 1.01 * mean
+
+
+def test_row_block_schedule_covers_every_tile_once_and_keeps_row_blocks_private():
+    """Row-block mode of tile_at (csrc/gemm_tcgen05.cu, sched_shift < 0): round r of cluster c is the tile
+    (c + (r // NB) * C) * NB + (r % NB + c % NB) % NB.  Every tile is computed exactly once and every A row block by
+    exactly one cluster; for config 2 (514 row blocks, 74 clusters) the busiest cluster does the same work as under the
+    searched tile-granular schedule."""
+    for clusters, nb, mb in [(74, 6, 514), (74, 17, 514), (74, 24, 514), (74, 6, 74), (3, 2, 7)]:
+        tiles = nb * mb
+        seen = [0] * tiles
+        owner = {}
+        cost = [0.0] * clusters
+        for c in range(clusters):
+            r = 0
+            while True:
+                t = (c + (r // nb) * clusters) * nb + (r % nb + c % nb) % nb
+                if t >= tiles:
+                    break
+                seen[t] += 1
+                owner.setdefault(t // nb, set()).add(c)
+                cost[c] += 0.65 if t % nb == nb - 1 else 1.0
+                r += 1
+        assert all(v == 1 for v in seen), (clusters, nb, mb)
+        assert all(len(v) == 1 for v in owner.values())
+    clusters, nb, mb = 74, 6, 514
+    best = min(range(clusters), key=lambda sh: max(_walk(clusters, nb, mb, sh)[1]))
+    _, bal = _walk(clusters, nb, mb, best)
+    rows = [(7 if c < mb - 6 * clusters else 6) * (nb - 1 + 0.65) for c in range(clusters)]
+    assert abs(max(rows) - max(bal)) < 1e-6 * max(bal) + 0.7      # within one half tile of the searched schedule

@@ -22,11 +22,10 @@ TAGS = {1: "TMA  K0 issued", 2: "TMA  Q0 issued", 3: "TMA  Q1 issued", 4: "TMA  
         60: "WG   O seen", 61: "WG   O loaded", 62: "WG   stored"}
 ROLE = ["tma", "mma", "cls2", "cls3", "wg0", "wg1"]
 
-# three-block kernel (default variant): unit r = 2*kb + t
+# three-block kernel (variant 2): unit r = 2*kb + t
 P3_ROLE = ["tma", "mma", "epi", "-", "wg0", "wg1"]
 P3_TAGS = {"tma": {1: "item loads start (K0)", 2: "Q0 issued", 3: "all loads issued"},
-           "mma": {**{10 + r: f"P(t={r & 1},kb={r >> 1}) seen" for r in range(6)},
-                   **{20 + r: f"PV(t={r & 1},kb={r >> 1}) + next S issued" for r in range(6)}},
+           "mma": {20 + r: f"PV(t={r & 1},kb={r >> 1}) + S(unit+3) issued" for r in range(6)},
            "epi": {60: "O_0 complete", 61: "O_1 complete", 62: "store 0 issued", 63: "store 1 issued"},
            "wg0": {}, "wg1": {}}
 for _kb in range(3):
@@ -69,12 +68,12 @@ def run(frames, variant=0):
     for clk, r, tag in ev:
         item, code = tag // 100, tag % 100
         if item in (0, 1) or last_item // 2 <= item <= last_item // 2 + 1:
-            if variant == 0:
+            if variant == 2:
                 print(f"{clk - t0:9d}  item {item:3d}  {P3_ROLE[r]:5s} {P3_TAGS[P3_ROLE[r]].get(code, code)}")
             else:
                 print(f"{clk - t0:9d}  item {item:3d}  {ROLE[r]:5s} {TAGS.get(code, code)}")
     # steady-state period
-    ks = [clk for clk, r, tag in ev if r == 1 and tag % 100 == (10 if variant == 0 else 12)]
+    ks = [clk for clk, r, tag in ev if r == 1 and tag % 100 == (20 if variant == 2 else 12)]
     if len(ks) > 4:
         print("period (clk/item), items 2..:", (ks[-1] - ks[2]) / (len(ks) - 3))
 

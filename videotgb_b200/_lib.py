@@ -94,8 +94,11 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
         fn.restype = res
     _lib = lib
-    if os.environ.get("TGB_GEMM_SCHEDULE") == "roundrobin" and hasattr(lib, "tgb_gemm_set_schedule"):     # A/B knob
-        lib.tgb_gemm_set_schedule(0)
+    sched = {"roundrobin": 0, "balanced": 1, "rowblocks": 2}.get(os.environ.get("TGB_GEMM_SCHEDULE", ""))   # A/B knob
+    if sched is not None:
+        lib.tgb_gemm_set_schedule(sched)
+    if os.environ.get("TGB_ATTN_VARIANT"):                                                                    # A/B knob
+        lib.tgb_vit_attention_set_variant(int(os.environ["TGB_ATTN_VARIANT"]))
     return lib
 
 

@@ -1094,7 +1094,7 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
 }
 
 // =====================================================================================================================
-// Three-block variant (default).  Same roles as the ping-pong kernel, re-cut so that no warpgroup ever waits for a
+// Three-block variant (cross-check / experiment).  Same roles as the ping-pong kernel, re-cut so that no warpgroup ever waits for a
 // tensor-core round trip it does not depend on:
 //   keys   three blocks of 96 / 96 / 80 rows (65 valid in the last); a "unit" is (query tile t, key block kb), units of
 //          an item run in the order r = 2*kb + t:  (0,0) (1,0) (0,1) (1,1) (0,2) (1,2)
@@ -1126,6 +1126,7 @@ constexpr int P3_SMEM_TOTAL = P3_SMEM_STAGE + PP_STAGE_BYTES + 1024;     // + al
 static_assert(P3_SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 constexpr int P3_BLK_BYTES = P3_KB * 128;                         // one d block of key block 0 / 1 (12288 = 12 swizzle atoms)
 constexpr int P3_BLK2_BYTES = P3_KB2 * 128;
+
 
 template <int NCOLS, int NVALID>
 __device__ __forceinline__ float p3_row_max(uint32_t s_addr) {
@@ -1287,6 +1288,74 @@ __device__ __forceinline__ void cls3_row(const VitAttnParams& p, int w, int i, u
   }
 }
 
+// ---- MMA issuer of the three-block kernel.  ONE thread issues ~70 tcgen05.mma + ~22 tcgen05.commit per item, and a single
+// thread retires a dependent instruction only every ~4-6 clk: with descriptors rebuilt per instruction (64-bit shifts /
+// ors, run-time unit indices) each MMA cost ~150-200 clk of issue time -- more than its 48 clk on the tensor pipe -- and
+// the issuer, not the tensor cores or the softmax warps, set the period of both this kernel's first version (13.8k clk per
+// item) and of the ping-pong kernel (9.4k).  Here every unit index is a template parameter and the shared-memory
+// descriptors are (low word + compile-time constant, constant high word) pairs: ~3 instructions per MMA.
+struct P3Issue {
+  uint32_t tmem_base;
+  uint32_t q_lo, k_lo, v_lo;        // low descriptor words of the Q / K / V buffers' first bytes
+  uint32_t hi_k, hi_mn;             // high descriptor words: K-major SWIZZLE_128B (SBO 1024) / MN-major (SBO 1024), LBO in the low word
+  uint64_t *q_full, *q_free, *k_full, *k_free, *v_full, *v_free, *s_full, *p_full, *pv_done, *o_full, *o_free;
+};
+__device__ __forceinline__ uint64_t p3_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// S of unit R (= 2 kb + t) of item parity `ph` into ring buffer R % 3; waits for the operands it is the first to use.
+template <int R>
+__device__ __forceinline__ void p3_issue_s(const P3Issue& c, uint32_t ph) {
+  constexpr int t = R & 1, kb = R >> 1;
+  constexpr uint32_t idesc = umma_idesc_bf16(128, kb < 2 ? P3_KB : P3_KB2);
+  if (kb == 0) mbar_wait(&c.q_full[t], ph);
+  if (t == 0) mbar_wait(&c.k_full[kb], ph);
+  tc_fence_after();
+  const uint32_t d = c.tmem_base + P3_COL_S + (R % 3) * P3_S_STRIDE;
+#pragma unroll
+  for (int ks6 = 0; ks6 < 6; ++ks6) {                            // d block 0: four k-steps, d block 1: two (d 96..127 is zero)
+    const int db = ks6 >> 2, ks = ks6 & 3;
+    const uint64_t da = p3_desc(c.q_lo + (((t * 2 + db) * PP_Q_BYTES + ks * 32) >> 4), c.hi_k);
+    const uint64_t dk = p3_desc(c.k_lo + ((db * VA_KBLK_BYTES + kb * P3_BLK_BYTES + ks * 32) >> 4), c.hi_k);
+    umma_bf16_ss(d, da, dk, idesc, ks6 > 0 ? 1u : 0u);
+  }
+  umma_commit(&c.s_full[R % 3]);
+  if (t == 1) umma_commit(&c.k_free[kb]);
+  if (kb == 2) umma_commit(&c.q_free[t]);
+}
+// O_t (+)= P V of unit R; waits for P, the V block (first use) and, for the item's first block, the epilogue of O_t.
+template <int R>
+__device__ __forceinline__ void p3_issue_pv(const P3Issue& c, uint32_t ph) {
+  constexpr int t = R & 1, kb = R >> 1;
+  constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 96) | (1u << 16);       // B (= V) is MN-major
+  constexpr int nsteps = kb < 2 ? P3_KB / 16 : P3_KB2 / 16;
+  mbar_wait(&c.p_full[R % 3], R >= 3 ? 1u : 0u);
+  if (t == 0) mbar_wait(&c.v_full[kb], ph);
+  if (kb == 0) mbar_wait(&c.o_free[t], ph ^ 1);                  // the previous item's epilogue has read O_t
+  tc_fence_after();
+  const uint32_t d = c.tmem_base + P3_COL_O + t * P3_O_STRIDE;
+  const uint32_t a = c.tmem_base + P3_COL_S + (R % 3) * P3_S_STRIDE;
+#pragma unroll
+  for (int j = 0; j < nsteps; ++j)
+    umma_bf16_ts(d, a + j * 8, p3_desc(c.v_lo + (((kb * (P3_KB / 16) + j) * 2048) >> 4), c.hi_mn), idesc_pv,
+                 (kb > 0 || j > 0) ? 1u : 0u);
+  umma_commit(&c.pv_done[t]);
+  if (kb == 2) umma_commit(&c.o_full[t]);
+  if (t == 1) umma_commit(&c.v_free[kb]);
+}
+// unit R of item i: P V(R), then S of the unit three places on (same item for R < 3, the next item otherwise)
+template <int R>
+__device__ __forceinline__ void p3_unit(const P3Issue& c, uint32_t ph, bool has_next) {
+  p3_issue_pv<R>(c, ph);
+  if constexpr (R < 3) {
+    p3_issue_s<R + 3>(c, ph);
+  } else {
+    if (has_next) p3_issue_s<R - 3>(c, ph ^ 1);
+  }
+}
+
 __global__ void __launch_bounds__(P3_THREADS, 1)
 vit_attention_p3_kernel(const __grid_constant__ CUtensorMap tmap96, const __grid_constant__ CUtensorMap tmap80,
                         const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap_out,
@@ -1386,62 +1455,36 @@ vit_attention_p3_kernel(const __grid_constant__ CUtensorMap tmap96, const __grid
     // ================================================================ MMA issuer
     if (lane == 0) {
       TRACE_DECL
-      constexpr uint32_t idesc_s96 = umma_idesc_bf16(128, P3_KB);
-      constexpr uint32_t idesc_s80 = umma_idesc_bf16(128, P3_KB2);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 96) | (1u << 16);     // B (= V) is MN-major
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      const int total = 6 * n_my;
-      // S of unit (item i, r = 2 kb + t) into ring buffer r % 3
-      auto issue_s = [&](int i, int r) {
-        const int t = r & 1, kb = r >> 1;
+      P3Issue c;
+      c.tmem_base = tmem_base;
+      c.q_lo = ((smem_u32(sQ) & 0x3FFFFu) >> 4) | (1u << 16);                      // K-major: LBO field unused (1)
+      c.k_lo = ((smem_u32(sK) & 0x3FFFFu) >> 4) | (1u << 16);
+      c.v_lo = ((smem_u32(sV) & 0x3FFFFu) >> 4) | ((uint32_t)(VA_KBLK_BYTES >> 4) << 16);   // MN-major: LBO = next 64-wide d block
+      c.hi_k = (1024u >> 4) | (1u << 14) | (2u << 29);                              // SBO 1024 | version | SWIZZLE_128B
+      c.hi_mn = (1024u >> 4) | (1u << 14) | (2u << 29);
+      c.q_full = q_full; c.q_free = q_free; c.k_full = k_full; c.k_free = k_free; c.v_full = v_full; c.v_free = v_free;
+      c.s_full = s_full; c.p_full = p_full; c.pv_done = pv_done; c.o_full = o_full; c.o_free = o_free;
+      if (n_my > 0) {
+        p3_issue_s<0>(c, 0);
+        p3_issue_s<1>(c, 0);
+        p3_issue_s<2>(c, 0);
+      }
+#pragma unroll 1
+      for (int i = 0; i < n_my; ++i) {
         const uint32_t ph = i & 1;
-        if (kb == 0) mbar_wait(&q_full[t], ph);
-        if (t == 0) mbar_wait(&k_full[kb], ph);
-        tc_fence_after();
-        const uint32_t d = tmem_base + P3_COL_S + (r % 3) * P3_S_STRIDE;
-        uint32_t accum = 0;
-#pragma unroll
-        for (int db = 0; db < 2; ++db) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (db == 1 && ks >= 2) break;                       // d = 96..127 is all zero
-            const uint64_t da = umma_desc_sw128(q_addr + (t * 2 + db) * PP_Q_BYTES + ks * 32);
-            const uint64_t dk = umma_desc_sw128(k_addr + db * VA_KBLK_BYTES + kb * P3_BLK_BYTES + ks * 32);
-            umma_bf16_ss(d, da, dk, kb < 2 ? idesc_s96 : idesc_s80, accum);
-            accum = 1;
-          }
-        }
-        umma_commit(&s_full[r % 3]);
-        if (t == 1) umma_commit(&k_free[kb]);
-        if (kb == 2) umma_commit(&q_free[t]);
-      };
-      auto issue_pv = [&](int i, int r) {
-        const int t = r & 1, kb = r >> 1;
-        const uint32_t ph = i & 1;
-        mbar_wait(&p_full[r % 3], r >= 3 ? 1u : 0u);
-        TRACE(1, i * 100 + 10 + r);                              // P(unit) seen
-        if (t == 0) mbar_wait(&v_full[kb], ph);
-        if (kb == 0) mbar_wait(&o_free[t], ph ^ 1);              // the previous item's epilogue has read O_t
-        tc_fence_after();
-        const uint32_t d = tmem_base + P3_COL_O + t * P3_O_STRIDE;
-        const uint32_t a = tmem_base + P3_COL_S + (r % 3) * P3_S_STRIDE;
-        const int nsteps = kb < 2 ? P3_KB / 16 : P3_KB2 / 16;
-        for (int j = 0; j < nsteps; ++j) {
-          const uint64_t db = umma_desc_mn_sw128(v_addr + (kb * (P3_KB / 16) + j) * 2048, VA_KBLK_BYTES, 1024);
-          umma_bf16_ts(d, a + j * 8, db, idesc_pv, (kb > 0 || j > 0) ? 1u : 0u);
-        }
-        umma_commit(&pv_done[t]);
-        if (kb == 2) umma_commit(&o_full[t]);
-        if (t == 1) umma_commit(&v_free[kb]);
-        TRACE(1, i * 100 + 20 + r);                              // P V(unit) issued
-      };
-      for (int u = 0; u < 3 && u < total; ++u) issue_s(0, u);
-      int i = 0, r = 0, i3 = 0, r3 = 3;                          // unit u = (i, r); unit u + 3 = (i3, r3)
-      for (int u = 0; u < total; ++u) {
-        issue_pv(i, r);
-        if (u + 3 < total) issue_s(i3, r3);
-        if (++r == 6) { r = 0; ++i; }
-        if (++r3 == 6) { r3 = 0; ++i3; }
+        const bool has_next = i + 1 < n_my;
+        p3_unit<0>(c, ph, has_next);
+        TRACE(1, i * 100 + 20);
+        p3_unit<1>(c, ph, has_next);
+        TRACE(1, i * 100 + 21);
+        p3_unit<2>(c, ph, has_next);
+        TRACE(1, i * 100 + 22);
+        p3_unit<3>(c, ph, has_next);
+        TRACE(1, i * 100 + 23);
+        p3_unit<4>(c, ph, has_next);
+        TRACE(1, i * 100 + 24);
+        p3_unit<5>(c, ph, has_next);
+        TRACE(1, i * 100 + 25);
       }
     }
     __syncwarp();
@@ -1608,10 +1651,10 @@ extern "C" __attribute__((visibility("default"))) int tgb_debug_attn_trace(long 
 }
 #endif
 
-static std::atomic<int> g_vit_attention_variant{2};   // 0 = three-block kernel (default), 1 = one-shot, 2 = ping-pong (cross-checks)
+static std::atomic<int> g_vit_attention_variant{0};   // 0 = ping-pong kernel (default), 1 = one-shot, 2 = three-block (cross-checks)
 
 extern "C" int tgb_vit_attention_set_variant(int variant) {
-  TGB_CHECK_ARG(variant >= 0 && variant <= 2, "vit_attention_set_variant: 0 (three-block), 1 (one-shot) or 2 (ping-pong)");
+  TGB_CHECK_ARG(variant >= 0 && variant <= 2, "vit_attention_set_variant: 0 (ping-pong), 1 (one-shot) or 2 (three-block)");
   g_vit_attention_variant = variant;
   return TGB_OK;
 }
@@ -1638,7 +1681,7 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   CUtensorMap* maps[5] = {&map128, &map96, &map80, &map144, &map};
   const cuuint32_t box_rows[5] = {128, P3_KB, P3_KB2, PP_KEYS0, VA_BOX_ROWS};
   for (int i = 0; i < 5; ++i) {
-    if ((variant == 0 && i > 2) || (variant == 1 && i != 4) || (variant == 2 && (i == 1 || i == 2 || i == 4))) continue;
+    if ((variant == 2 && i > 2) || (variant == 1 && i != 4) || (variant == 0 && (i == 1 || i == 2 || i == 4))) continue;
     cuuint32_t box[3] = {64, 1, box_rows[i]};
     CUresult r = fn(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1678,9 +1721,9 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   if (variant == 1)
     vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM_TOTAL, (cudaStream_t)stream>>>(map, p);
   else if (variant == 2)
-    vit_attention_pp_kernel<<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, map_out, p);
-  else
     vit_attention_p3_kernel<<<grid, P3_THREADS, P3_SMEM_TOTAL, (cudaStream_t)stream>>>(map96, map80, map128, map_out, p);
+  else
+    vit_attention_pp_kernel<<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, map_out, p);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

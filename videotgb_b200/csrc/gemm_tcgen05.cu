@@ -205,8 +205,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   // C = 74 (the N = 1408 GEMMs) half of the clusters never see the cheap half-width last N tile and the others see it on
   // a third of their tiles -- the fast half runs ahead by several tiles and the kernel waits for the slow half.  The host
   // searches the shift that minimises the busiest cluster's work (balanced_shift).
+  // Row-block mode (sched_shift < 0; chosen by the host when M is large enough to fill whole rounds of row blocks): a
+  // cluster walks ALL N tiles of one A row block, then the row block `clusters` further down.  Every A row block is then
+  // read by exactly one cluster -- the N tiles after the first hit the L2 -- so no cluster depends on staying in step with
+  // another (the tile-granular schedule let the six clusters sharing a row block of the K = 6144 GEMM drift apart until
+  // the block had left the L2: 1.6-2x the algorithmic A traffic).  Cluster c starts its walk at N tile c mod NB: at any
+  // moment the clusters are spread over all W tiles (all 74 on the same W tile at once measured 6-8 % slower).
   const int sched_shift = p.sched_shift;
+  const int n_blocks = p.num_n_blocks;
+  const int n_start = cluster_id % n_blocks;
   auto tile_at = [&](int round) {
+    if (sched_shift < 0) {
+      const int pass = round / n_blocks;
+      int n = round - pass * n_blocks + n_start;
+      if (n >= n_blocks) n -= n_blocks;
+      return (cluster_id + pass * num_clusters) * n_blocks + n;
+    }
     return round * num_clusters + (cluster_id + round * sched_shift) % num_clusters;
   };
 
@@ -782,7 +796,19 @@ static int balanced_shift(int clusters, int m_blocks, int n_blocks, bool half_la
 static std::atomic<int> g_force_cg{0};     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
 static std::atomic<int> g_force_ew{0};     // 0 = choose per epilogue, 8 / 16 = force
-static std::atomic<int> g_sched_balanced{1};   // 1 = balanced persistent schedule (default), 0 = plain round-robin (A/B knob)
+// 1 = balanced tile schedule (default); 0 = plain round-robin; 2 = row-block schedule when M fills whole rounds of row
+// blocks, else 1 (A/B knob).  Measured (tools/gemm_ab.py, profiles/r2_gemm_ab_rowblocks.txt): the row-block schedule
+// removes the A re-reads between clusters but puts 74 A row blocks (230 MB for K = 6144) in flight at once, more than the
+// L2 holds, so each cluster's own five re-reads of its block miss instead: fc2 -5..8 %, qkv -6 %, proj -2 %.  Not default.
+static std::atomic<int> g_sched_balanced{1};
+
+// Row-block schedule: ceil(m_blocks / clusters) passes of whole row blocks; taken when the last pass leaves at most 3 %
+// of the cluster-passes idle (config 2: 514 row blocks on 74 clusters = 6.95 passes, 99.2 %).
+static bool row_block_schedule_ok(int clusters, int m_blocks) {
+  if (clusters <= 0 || m_blocks < clusters) return false;
+  const long long passes = (m_blocks + clusters - 1) / clusters;
+  return (long long)m_blocks * 100 >= passes * clusters * 97;
+}
 
 template <int BN, int EPI, int CG, int EW>
 static int launch_gemm_ew(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
@@ -815,8 +841,10 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_clusters = sm_count() / CG;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  p.sched_shift = g_sched_balanced.load() ? balanced_shift(clusters, p.num_m_blocks, p.num_n_blocks,
-                                                     BN == 256 && p.N - (p.num_n_blocks - 1) * BN <= BN / 2) : 0;
+  const int sched = g_sched_balanced.load();
+  p.sched_shift = sched ? balanced_shift(clusters, p.num_m_blocks, p.num_n_blocks,
+                                         BN == 256 && p.N - (p.num_n_blocks - 1) * BN <= BN / 2) : 0;
+  if (sched == 2 && row_block_schedule_ok(clusters, p.num_m_blocks)) p.sched_shift = -1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(Cfg::THREADS);
@@ -914,8 +942,12 @@ extern "C" int tgb_gemm_set_epilogue_warps(int warps) {
   return TGB_OK;
 }
 
-extern "C" int tgb_gemm_set_schedule(int balanced) {
-  g_sched_balanced = balanced ? 1 : 0;
+extern "C" int tgb_gemm_set_schedule(int mode) {
+  if (mode < 0 || mode > 2) {
+    set_last_error("schedule must be 0 (round-robin), 1 (balanced tiles, default) or 2 (row blocks when M allows)");
+    return TGB_EINVAL;
+  }
+  g_sched_balanced = mode;
   return TGB_OK;
 }
 

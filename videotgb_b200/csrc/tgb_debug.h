@@ -18,11 +18,12 @@ TGB_API int tgb_resize_set_variant(int variant);
 TGB_API int tgb_patchify_set_variant(int variant);
 /* 0 = choose per problem (default), 1 = single-CTA 128xBN tiles, 2 = CTA-pair 256xBN tiles. */
 TGB_API int tgb_gemm_set_cta_group(int cta_group);
-/* 1 = balanced persistent tile schedule (default), 0 = plain round-robin. */
-TGB_API int tgb_gemm_set_schedule(int balanced);
+/* persistent tile schedule: 1 = balanced tile schedule (default); 0 = plain round-robin; 2 = whole A row blocks per
+ * cluster when M fills whole rounds of them, else 1 (measured slower, kept for A/B). */
+TGB_API int tgb_gemm_set_schedule(int mode);
 /* epilogue warps per CTA, 0 = choose (8; the fp32-residual epilogues always run 8). */
 TGB_API int tgb_gemm_set_epilogue_warps(int warps);
-/* 0 = ping-pong kernel (default), 1 = one-shot kernel (whole score row in tensor memory; cross-check). */
+/* 0 = ping-pong kernel (default), 1 = one-shot kernel (whole score row in tensor memory), 2 = three-block kernel. */
 TGB_API int tgb_vit_attention_set_variant(int variant);
 
 #ifdef __cplusplus

@@ -345,20 +345,35 @@ class Blip2VisionModel(_KernelModule):
     def _fold_monitor(self, dev):
         """Running maximum of |row mean| / row std over EVERY pass since the weights were loaded: one device float that
         `ln_stats_finalize` raises (one atomicMax per warp), mirrored into pinned host memory after each call and read
-        without a synchronisation at the start of the next one."""
+        without a synchronisation at the start of a later one."""
         mon = self._fold_mon
         if mon is None or mon.dev.device != dev:
-            mon = SimpleNamespace(dev=torch.zeros(1, dtype=torch.float32, device=dev),
-                                  host=torch.zeros(1, dtype=torch.float32).pin_memory(), event=None)
+            mon = SimpleNamespace(dev=torch.zeros(1, dtype=torch.float32, device=dev), pending=[],
+                                  free=[torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)])
             self._fold_mon = mon
         return mon
 
+    @staticmethod
+    def _fold_mirror(mon):
+        """Enqueue a copy of the running maximum into a free pinned slot (skipped while both slots are in flight: the
+        value is a running maximum, so the next mirror carries it)."""
+        if not mon.free:
+            return
+        host = mon.free.pop()
+        host.copy_(mon.dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        mon.pending.append((ev, host))
+
     def _fold_poll(self, mon) -> bool:
-        """Reads the mirrored ratio of the calls that have finished; True if the fold had to be switched off."""
-        if mon.event is None or not mon.event.query():
+        """Reads the mirrors that have landed; True if the fold had to be switched off."""
+        seen = None
+        while mon.pending and mon.pending[0][0].query():
+            _, host = mon.pending.pop(0)
+            seen = max(seen or 0.0, float(host.item()))
+            mon.free.append(host)
+        if seen is None:
             return False
-        mon.event = None
-        seen = float(mon.host.item())
         self.fold_ratio_seen = max(self.fold_ratio_seen or 0.0, seen)
         if seen <= self.fold_max_mean_over_std:
             return False
@@ -400,10 +415,8 @@ class Blip2VisionModel(_KernelModule):
                 f1 = min(nf, f0 + step)
                 self._encode(pk, cols[f0 * per: f1 * per], f1 - f0, last[f0 * s: f1 * s], last_bf16[f0 * s: f1 * s],
                              track_ratio=track)
-        if mon is not None and mon.event is None:      # mirror the running maximum; read by a later call, never waited for
-            mon.host.copy_(mon.dev, non_blocking=True)
-            mon.event = torch.cuda.Event()
-            mon.event.record()
+        if mon is not None:                             # mirror the running maximum; read by a later call, never waited for
+            self._fold_mirror(mon)
         return last.view(nf, s, d), last_bf16.view(nf, s, d)
 
     def forward(self, pixel_values: Optional[torch.Tensor] = None, output_attentions: Optional[bool] = None,

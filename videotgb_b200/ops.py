@@ -368,9 +368,10 @@ def gemm_set_cta_group(cta_group: int) -> None:
     check(_lib.load().tgb_gemm_set_cta_group(int(cta_group)))
 
 
-def gemm_set_schedule(balanced: bool) -> None:
-    """True = balanced persistent tile schedule (default), False = plain round-robin; A/B knob."""
-    check(_lib.load().tgb_gemm_set_schedule(1 if balanced else 0))
+def gemm_set_schedule(mode) -> None:
+    """1 / True = balanced persistent tile schedule (default); 0 / False = plain round-robin; 2 = whole A row blocks per
+    cluster when M allows (measured slower).  A/B knob."""
+    check(_lib.load().tgb_gemm_set_schedule(1 if mode is True else int(mode)))
 
 
 def gemm_set_epilogue_warps(warps: int) -> None:
