@@ -560,12 +560,12 @@ def test_attention(b, h, sq, sk, d, masked):
     assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("frames,scale_in,late_peak", [(1, 1.0, False), (3, 1.0, False), (19, 2.5, False), (2, 1.0, True),
                                                        (150, 1.0, False), (300, 1.0, True)])
 def test_vit_attention_tcgen05(frames, scale_in, late_peak, variant):
     """The tensor-memory attention kernels (0: ping-pong, two key blocks, online softmax; 1: one-shot; 2: three key blocks
-    over a ring of score buffers) vs torch and vs the mma.sync kernel.  `late_peak` plants dominant keys in the later key
+    over a ring of score buffers; 3: CTA pair, cta_group::2 with both query tiles in one MMA) vs torch and vs the mma.sync kernel.  `late_peak` plants dominant keys in the later key
     blocks (rows 150-160 and 200) for half of the queries, which forces the online-softmax kernels through their
     accumulator-rescale path (300 frames: more than two items per CTA, so every barrier wraps with rescales in flight)."""
     g = torch.Generator().manual_seed(frames)

@@ -52,7 +52,8 @@ def bench(f, iters=10):
             ops.vit_attention(qkv, f, 88 ** -0.5, out=out)
             ops.vit_attention_set_variant(0)
         return run
-    for name, fn in (("tcgen05 three-block", variant(2)),
+    for name, fn in (("tcgen05 CTA pair", variant(3)),
+                     ("tcgen05 three-block", variant(2)),
                      ("tcgen05 ping-pong", variant(0)),
                      ("tcgen05 one-shot", variant(1)),
                      ("mma.sync", lambda: ops.attention(qkv[:, :1408], qkv[:, 1408:2816], qkv[:, 2816:], f, 16, 257, 257, 88, 88 ** -0.5, out=out))):

@@ -32,6 +32,16 @@ for _kb in range(3):
     for _wg in ("wg0", "wg1"):
         P3_TAGS[_wg].update({40 + 10 * _kb: f"S(t,{_kb}) seen", 42 + 10 * _kb: f"exp({_kb}) done", 43 + 10 * _kb: f"P(t,{_kb}) published"})
 
+# CTA-pair kernel (variant 3), leader CTA of cluster 0
+C2_ROLE = ["tma", "mma", "epi", "cls", "smA", "smB"]
+C2_TAGS = {"tma": {1: "Q/K buffers free -> loads issued", 2: "V buffer free -> loads issued"},
+           "mma": {10: "P(0) seen", 11: "O free", 12: "PV(0) issued", 13: "next item landed", 14: "next S(0) issued",
+                   15: "P(1) seen", 16: "PV(1) issued", 17: "next S(1) issued"},
+           "epi": {60: "O complete", 62: "store issued", 63: "CLS row done"},
+           "cls": {30: "K landed", 31: "local scores sent", 32: "peer scores here", 33: "probabilities published"},
+           "smA": {40: "S(0) seen", 41: "row max known", 42: "exp done", 43: "P(0) published", 50: "S(1) seen", 53: "P(1) published"},
+           "smB": {40: "S(0) seen", 41: "row max known", 42: "exp done", 43: "P(0) published", 50: "S(1) seen", 53: "P(1) published"}}
+
 
 def build():
     os.makedirs(DBG, exist_ok=True)
@@ -68,12 +78,14 @@ def run(frames, variant=0):
     for clk, r, tag in ev:
         item, code = tag // 100, tag % 100
         if item in (0, 1) or last_item // 2 <= item <= last_item // 2 + 1:
-            if variant == 2:
+            if variant == 3:
+                print(f"{clk - t0:9d}  item {item:3d}  {C2_ROLE[r]:5s} {C2_TAGS[C2_ROLE[r]].get(code, code)}")
+            elif variant == 2:
                 print(f"{clk - t0:9d}  item {item:3d}  {P3_ROLE[r]:5s} {P3_TAGS[P3_ROLE[r]].get(code, code)}")
             else:
                 print(f"{clk - t0:9d}  item {item:3d}  {ROLE[r]:5s} {TAGS.get(code, code)}")
     # steady-state period
-    ks = [clk for clk, r, tag in ev if r == 1 and tag % 100 == (20 if variant == 2 else 12)]
+    ks = [clk for clk, r, tag in ev if r == 1 and tag % 100 == {2: 20, 3: 12}.get(variant, 12)]
     if len(ks) > 4:
         print("period (clk/item), items 2..:", (ks[-1] - ks[2]) / (len(ks) - 3))
 

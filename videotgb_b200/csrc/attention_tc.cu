@@ -1626,6 +1626,740 @@ vit_attention_p3_kernel(const __grid_constant__ CUtensorMap tmap96, const __grid
   }
 }
 
+// =====================================================================================================================
+// CTA-pair variant (default): one (frame, head) item per 2-CTA cluster, `tcgen05.mma.cta_group::2` with M = 256.
+//
+// Why: a tcgen05.mma with M = 128 costs 60-110 clk on the tensor pipe whatever its N (profiles/r2_mma_chain_microbench.txt:
+// the A read of 4 KB from shared / tensor memory, not the math, sets the time), and one item needs 58-70 of them on one
+// SM: 6-7k clk per item, above the item's HBM time.  With the pair, ONE instruction covers both query tiles (CTA r owns
+// tile r), each CTA stages only half of K (B rows = keys, split across the pair) and a 64-column half of V (B rows = d),
+// and an item needs 29 instructions: 12 for S (6 k-steps x key blocks of 144 + 128) and 17 for P V.
+//   smem   per CTA and item 100 KB: Q tile [2 d blocks][128 x 128 B] | K halves [2 d blocks][72 + 64 rows x 128 B] |
+//          V d-half [272 keys x 128 B] -- DOUBLE BUFFERED over items, so the loads run a whole item ahead
+//   TMEM   per CTA: S0 fp32 [0,144) | S1 [144,272) | O fp32 [272,400) | row sums [400,404).  P (bf16) aliases the first
+//          half of the columns each softmax thread reads (two threads per query row: A keys [0,80) / [0,64) of the block,
+//          B the rest; P of thread B's keys sits at the start of B's own columns, each P V k-step has its own address)
+//   sync   full[stage] local (TMA bytes) + peer_full[stage] on the leader (forwarded by the peer's idle MMA warp);
+//          tcgen05.commit multicast -> s_full / pv_done / o_full / empty in both CTAs; the softmax and epilogue warps of
+//          both CTAs arrive (one lane per warp) on the LEADER's p_full / o_free.
+//   warps  0 TMA producer (+ TMEM alloc) | 1 MMA issuer (leader) / full-barrier forwarder (peer) | 2, 3 CLS query row of
+//          key block 0 / 1 | 4-7, 8-11 softmax threads A / B | 12-15 epilogue (O / l -> bf16 -> staging tile -> bulk store)
+//   CLS    the CLS query row needs every key's score but K is split across the pair: each CTA's CLS warps compute the
+//          scores of their local keys (mma.sync, transposed formulation as in the ping-pong kernel), write them into BOTH
+//          CTAs' score buffers (st.shared::cluster), and each CTA then runs softmax + P V for its own d-half.
+// =====================================================================================================================
+constexpr int C2_THREADS = 512;
+constexpr int C2_KEYS0 = 144, C2_KEYS1 = 128;                      // key blocks (272 padded keys, 257 valid)
+constexpr int C2_HALF0 = C2_KEYS0 / 2, C2_HALF1 = C2_KEYS1 / 2;    // 72 / 64 keys of a block held by one CTA
+constexpr int C2_SPLIT0 = 80, C2_SPLIT1 = 64;                      // softmax thread A takes the first SPLIT columns of the block
+constexpr int C2_VALID1 = VA_S - C2_KEYS0;                         // 113 valid keys in block 1
+constexpr uint32_t C2_COL_S0 = 0, C2_COL_S1 = 144, C2_COL_O = 272, C2_COL_L = 400;
+constexpr int C2_Q_BYTES = 2 * PP_Q_BYTES;                         // 32768
+constexpr int C2_KD_BYTES = (C2_HALF0 + C2_HALF1) * 128;           // 17408: one d block of this CTA's K rows
+constexpr int C2_K_BYTES = 2 * C2_KD_BYTES;
+constexpr int C2_V_BYTES = 272 * 128;                              // 34816
+constexpr int C2_STAGE_BYTES = C2_Q_BYTES + C2_K_BYTES + C2_V_BYTES;   // 102400
+constexpr int C2_SMEM_BAR = 2 * C2_STAGE_BYTES;                    // 204800
+constexpr int C2_SMEM_CLS = C2_SMEM_BAR + 256;                     // CLS row: float [2 item parities][2 blocks][144] scores |
+                                                                   // bf16 [2 blocks][144] probabilities | float [2 blocks][2] (max, sum)
+constexpr int C2_SMEM_XMAX = C2_SMEM_CLS + 2 * 2 * 144 * 4 + 2 * 144 * 2 + 32;   // float [2 halves][128] row maxima of the thread pairs
+constexpr int C2_SMEM_STAGE = (C2_SMEM_XMAX + 2 * 128 * 4 + 127) / 128 * 128;
+constexpr int C2_SMEM_LAYOUT = C2_SMEM_STAGE + PP_STAGE_BYTES;
+// The layout is laid down from the first 1024-byte boundary of the dynamic window.  The window starts on such a boundary on
+// sm_100 (no static shared memory in this kernel), so the slack below is normally unused; the kernel checks and traps if a
+// misaligned base would push the layout past the allocation.
+constexpr int C2_SMEM_TOTAL = C2_SMEM_LAYOUT + 1024 <= 227 * 1024 ? C2_SMEM_LAYOUT + 1024 : 227 * 1024;
+static_assert(C2_SMEM_LAYOUT <= C2_SMEM_TOTAL, "shared memory budget");
+
+__device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, const uint32_t (&v)[NREG]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v[OFF]) : "memory");
+}
+template <int OFF, int NREG>
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&v)[NREG]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[OFF]), "=r"(v[OFF + 1]) : "r"(taddr));
+}
+__device__ __forceinline__ void st_shared_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+
+// ---- code-size diet.  The first version of this kernel instantiated the score-row routines per (key block, thread half)
+// and inlined every barrier wait's time-out path: 76 KB of SASS whose roles run concurrently on one SM, and ncu showed
+// 7.8 "no instruction" stall cycles per issued instruction (the ping-pong kernel: 0.7).  The routines below take their
+// column counts at run time (one copy for every caller) and keep the rare paths out of line.
+__device__ __noinline__ void c2_wait_slow(uint64_t* bar, uint32_t parity) { mbar_wait_impl<true>(bar, parity); }
+__device__ __forceinline__ void c2_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) c2_wait_slow(bar, parity);
+}
+// row max of the first NVALID of NCOLS (80 / 64) fp32 score columns at s_addr: every tcgen05.ld in flight at once (a rolled
+// 16-column loop with one chunk of lookahead took 1.1k clk per block instead of 0.45k: it sits on the softmax chain)
+template <int NCOLS, int NVALID>
+__device__ __forceinline__ float c2_row_max(uint32_t s_addr) {
+  static_assert(NCOLS == 80 || NCOLS == 64, "column split widths");
+  uint32_t v[NCOLS];
+  tmem_ld32<0>(s_addr, v);
+  tmem_ld32<32>(s_addr + 32, v);
+  if (NCOLS == 80) tmem_ld16<64>(s_addr + 64, v);
+  tmem_ld_wait();
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NVALID; j += 4) {
+    m0 = fmaxf(m0, __uint_as_float(v[j]));
+    if (j + 1 < NVALID) m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+    if (j + 2 < NVALID) m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+    if (j + 3 < NVALID) m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// (rolled alternative, kept for reference / tiny code: max over the first `nvalid` columns, 16-column chunks)
+__device__ __forceinline__ float c2_row_max_rt(uint32_t s_addr, int nvalid) {
+  const int nfull = nvalid >> 4, ntail = nvalid & 15;
+  const int nchunk = nfull + (ntail ? 1 : 0);
+  uint32_t cur[16], nxt[16];
+  tmem_ld16<0>(s_addr, cur);
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < nfull; ++c) {
+    tmem_ld_wait();
+    if (c + 1 < nchunk) tmem_ld16<0>(s_addr + (c + 1) * 16, nxt);
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      m0 = fmaxf(m0, __uint_as_float(cur[j]));
+      m1 = fmaxf(m1, __uint_as_float(cur[j + 1]));
+      m2 = fmaxf(m2, __uint_as_float(cur[j + 2]));
+      m3 = fmaxf(m3, __uint_as_float(cur[j + 3]));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+  }
+  if (ntail) {
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) m0 = fmaxf(m0, j < ntail ? __uint_as_float(cur[j]) : -INFINITY);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// exp pass over `nfull` all-valid 16-column chunks plus (ntail > 0) one chunk with ntail valid columns (the rest give p = 0);
+// P chunk c (8 bf16x2 columns) is stored behind the read position.  Returns the row sum.
+__device__ __forceinline__ float c2_exp_rt(uint32_t s_addr, int nfull, int ntail, float sl2, float negm) {
+  float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+  uint32_t cur[16], nxt[16];
+  tmem_ld16<0>(s_addr, cur);
+#pragma unroll 1
+  for (int c = 0; c < nfull; ++c) {
+    tmem_ld_wait();
+    if (ntail > 0 || c + 1 < nfull) tmem_ld16<0>(s_addr + (c + 1) * 16, nxt);
+    pp_exp16<16>(cur, sl2, negm, la, lb);
+    tmem_st8<0>(s_addr + c * 8, cur);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+  }
+  if (ntail > 0) {
+    tmem_ld_wait();
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const float x0 = j < ntail ? ex2_approx(fmaf(__uint_as_float(cur[j]), sl2, negm)) : 0.f;
+      const float x1 = j + 1 < ntail ? ex2_approx(fmaf(__uint_as_float(cur[j + 1]), sl2, negm)) : 0.f;
+      l += x0 + x1;
+      cur[j >> 1] = pack_bf16(x0, x1);
+    }
+    la.x += l;
+    tmem_st8<0>(s_addr + nfull * 8, cur);
+  }
+  return (la.x + la.y) + (lb.x + lb.y);
+}
+
+// byte offset of the 16-byte chunk holding d [8*chunk, 8*chunk+8) of local K row r (d block stride C2_KD_BYTES) / V row r
+__device__ __forceinline__ uint32_t c2_k_off(int r, int chunk) {
+  return (uint32_t)((chunk >> 3) * C2_KD_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((((chunk & 7) ^ (r & 7))) << 4));
+}
+__device__ __forceinline__ uint32_t c2_v_off(int r, int chunk) {      // chunk 0..7 of this CTA's 64-column d half
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((chunk ^ (r & 7))) << 4));
+}
+
+// MMA issuer state of the pair kernel (see P3Issue): descriptor low words of stage 0, constant high words
+struct C2Issue {
+  uint32_t tmem_base, q_lo, k_lo, v_lo, hi;
+  uint64_t* s_full;
+};
+// S of key block kb of the item in `stage` into its score buffer (one out-of-line copy for its three call sites)
+__device__ __noinline__ void c2_issue_s(const C2Issue& c, int stage, int kb) {
+  const uint32_t idesc = kb == 0 ? umma_idesc_bf16(256, C2_KEYS0) : umma_idesc_bf16(256, C2_KEYS1);
+  const uint32_t d = c.tmem_base + (kb == 0 ? C2_COL_S0 : C2_COL_S1);
+  const uint32_t qo = c.q_lo + (uint32_t)stage * (C2_STAGE_BYTES >> 4);
+  const uint32_t ko = c.k_lo + (uint32_t)stage * (C2_STAGE_BYTES >> 4) + (uint32_t)kb * ((C2_HALF0 * 128) >> 4);
+#pragma unroll
+  for (int ks6 = 0; ks6 < 6; ++ks6) {                            // d block 0: four k-steps, d block 1: two (d 96..127 is zero)
+    const int db = ks6 >> 2, ks = ks6 & 3;
+    const uint64_t da = p3_desc(qo + ((db * PP_Q_BYTES + ks * 32) >> 4), c.hi);
+    const uint64_t dk = p3_desc(ko + ((db * C2_KD_BYTES + ks * 32) >> 4), c.hi);
+    umma_bf16_ss_cg<2>(d, da, dk, idesc, ks6 > 0 ? 1u : 0u);
+  }
+  umma_commit_cg<2>(&c.s_full[kb]);
+}
+// O (+)= P V over key block KB.  P of softmax thread A's keys starts at the block's first column, P of thread B's keys at
+// B's first column (SPLIT); V rows are the item's keys in order.
+template <int KB>
+__device__ __forceinline__ void c2_issue_pv(const C2Issue& c, int stage) {
+  constexpr uint32_t idesc_pv = umma_idesc_bf16(256, 128) | (1u << 16);      // B (= V) is MN-major
+  constexpr int NSTEP = (KB == 0 ? C2_KEYS0 : C2_KEYS1) / 16;                // 9 / 8
+  constexpr int ASTEP = (KB == 0 ? C2_SPLIT0 : C2_SPLIT1) / 16;              // k-steps over thread A's keys: 5 / 4
+  constexpr int SPLIT = KB == 0 ? C2_SPLIT0 : C2_SPLIT1;
+  constexpr int KK0 = KB == 0 ? 0 : C2_KEYS0 / 16;
+  const uint32_t d = c.tmem_base + C2_COL_O;
+  const uint32_t a = c.tmem_base + (KB == 0 ? C2_COL_S0 : C2_COL_S1);
+  const uint32_t so = (uint32_t)stage * (C2_STAGE_BYTES >> 4);
+#pragma unroll
+  for (int j = 0; j < NSTEP; ++j) {
+    const uint32_t pa = j < ASTEP ? a + j * 8 : a + SPLIT + (j - ASTEP) * 8;
+    umma_bf16_ts_cg2(d, pa, p3_desc(c.v_lo + so + (((KK0 + j) * 2048) >> 4), c.hi), idesc_pv, (KB > 0 || j > 0) ? 1u : 0u);
+  }
+}
+
+// CLS query row, key block KB: scores of this CTA's keys -> both CTAs' score buffers; then (every key's score present)
+// softmax of the block and O^T = V^T p for this CTA's 64-column d half.  Returns the block's (max, sum, O).
+__device__ __forceinline__ void st_async_f32(uint32_t cluster_addr, float v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(cluster_addr), "r"(__float_as_uint(v)), "r"(cluster_mbar) : "memory");
+}
+// The scores travel to the peer with st.async: every 4-byte store completes on the PEER's cls_ready barrier (transaction
+// bytes), so no cluster-scope release fence is needed (an mbarrier.arrive.release.cluster here cost ~2k clk per item).
+// CLS row scores on the FP32 pipe.  (A first version used mma.sync in the transposed formulation of the ping-pong kernel:
+// warp-level MMAs queue behind the tcgen05.mma stream on the tensor pipe -- 30 of them took 1.9k clk, the 17 of the P V
+// 4.8k -- which made the CLS row the bottleneck of the whole kernel.  The FP32 pipe is idle next to the MUFU-bound softmax.)
+// Lane = (key = lane & 7 of the round's eight keys, quarter qd = lane >> 3 of the d chunks: 16-byte chunks qd, qd+4, qd+8);
+// a phase of eight lanes reads eight different K rows at the same chunk index: conflict-free under the 128-byte swizzle.
+__device__ __forceinline__ void c2_cls_block(const VitAttnParams& p, int i, int kb, uint32_t rank, uint32_t sK, float* sc_local,
+                                             uint32_t sc_peer, uint64_t* cls_ready, uint32_t cls_ready_peer, uint64_t* kq_empty,
+                                             uint64_t* clsp_free, uint64_t* clsp_ready, __nv_bfloat16* p_s, float* ml,
+                                             int lane, const float (&qf)[24], int& tr_n) {
+  const int half = kb == 0 ? C2_HALF0 : C2_HALF1;              // local keys of the block: 72 / 64
+  const int row0 = kb == 0 ? 0 : C2_HALF0;                     // first local K row of the block
+  const int nkey = kb == 0 ? C2_KEYS0 : C2_KEYS1;
+  const int nvalid = kb == 0 ? C2_KEYS0 : C2_VALID1;
+  const int kl = lane & 7, qd = lane >> 3;
+  // per-lane byte offsets of its three chunks within an 8-row group (row kl): the round only adds 1024 bytes
+  uint32_t coff[3];
+#pragma unroll
+  for (int c3 = 0; c3 < 3; ++c3) {
+    const int chunk = qd + 4 * c3;                             // 0..10 hold d 0..87; chunk 11 (qd == 3, c3 == 2) does not exist
+    coff[c3] = sK + (uint32_t)((chunk >> 3) * C2_KD_BYTES + (row0 >> 3) * 1024 + kl * 128 + (((chunk & 7) ^ kl) << 4));
+  }
+  const bool has3 = qd < 3;
+  // all rounds first, the stores afterwards: a st.async between two rounds is a scheduling barrier (volatile + memory
+  // clobber) that exposed every round's load and shuffle latency -- 3.7k clk for 520 instructions
+  float scs[9];
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    if (r == 8 && kb != 0) { scs[8] = 0.f; break; }            // 9 rounds of eight keys (72) / 8 rounds (64)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int c3 = 0; c3 < 3; ++c3) {
+      if (c3 == 2 && !has3) break;
+      uint32_t w[4];
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                   : "r"(coff[c3] + r * 1024));
+      a0 = fmaf(__uint_as_float(w[0] << 16), qf[c3 * 8 + 0], a0);
+      a1 = fmaf(__uint_as_float(w[0] & 0xffff0000u), qf[c3 * 8 + 1], a1);
+      a2 = fmaf(__uint_as_float(w[1] << 16), qf[c3 * 8 + 2], a2);
+      a3 = fmaf(__uint_as_float(w[1] & 0xffff0000u), qf[c3 * 8 + 3], a3);
+      a0 = fmaf(__uint_as_float(w[2] << 16), qf[c3 * 8 + 4], a0);
+      a1 = fmaf(__uint_as_float(w[2] & 0xffff0000u), qf[c3 * 8 + 5], a1);
+      a2 = fmaf(__uint_as_float(w[3] << 16), qf[c3 * 8 + 6], a2);
+      a3 = fmaf(__uint_as_float(w[3] & 0xffff0000u), qf[c3 * 8 + 7], a3);
+    }
+    scs[r] = (a0 + a1) + (a2 + a3);
+  }
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    scs[r] += __shfl_xor_sync(0xffffffffu, scs[r], 8);
+    scs[r] += __shfl_xor_sync(0xffffffffu, scs[r], 16);
+  }
+  // every lane now holds the scores of keys 8 r + kl; lane quarter qd stores rounds qd, qd + 4, qd + 8
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    if ((r & 3) == qd && r * 8 < half) {
+      const int j = r * 8 + kl;
+      sc_local[rank * half + j] = scs[r];
+      st_async_f32(sc_peer + (rank * half + j) * 4, scs[r], cls_ready_peer);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    mbar_arrive(kq_empty);                                       // done reading this stage's K rows
+    mbar_arrive_expect_tx(cls_ready, half * 4);                  // my half is written; the peer's scores arrive as bytes
+  }
+  if (lane == 0 && kb == 0) TRACE(3, i * 100 + 31);              // scores of the local keys sent
+  c2_wait(cls_ready, i & 1);                                     // both halves of the block's scores are here
+  if (lane == 0 && kb == 0) TRACE(3, i * 100 + 32);              // peer's scores here
+  // ---- softmax over the block's valid keys, 5 per lane
+  float x[5];
+  float m = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < 5; ++it) {
+    const int j = it * 32 + lane;
+    x[it] = (j < nvalid) ? sc_local[j] * p.scale_log2 : -INFINITY;
+    m = fmaxf(m, x[it]);
+  }
+  m = warp_max(m);
+  float l = 0.f;
+#pragma unroll
+  for (int it = 0; it < 5; ++it) {
+    x[it] = ex2_approx(x[it] - m);                               // exp2(-inf) = 0 for masked keys
+    l += x[it];
+  }
+  l = warp_sum(l);
+  // ---- hand the block's probabilities (bf16) and (max, sum) to the epilogue warps, which run O = p V
+  c2_wait(clsp_free, (i & 1) ^ 1);                               // they are done with the previous item's
+#pragma unroll
+  for (int it = 0; it < 5; ++it)
+    if (it * 32 + lane < nkey) p_s[it * 32 + lane] = __float2bfloat16(x[it]);
+  if (lane == 0) { ml[0] = m; ml[1] = l; }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(clsp_ready);
+  if (lane == 0 && kb == 0) TRACE(3, i * 100 + 33);              // probabilities published
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1)
+vit_attention_c2_kernel(const __grid_constant__ CUtensorMap tmap72, const __grid_constant__ CUtensorMap tmap64,
+                        const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap136,
+                        const __grid_constant__ CUtensorMap tmap_out, const VitAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0 && (smem - smem_raw) + C2_SMEM_LAYOUT > C2_SMEM_TOTAL) {
+    printf("tgb: vit_attention_c2: dynamic shared memory base %p is not aligned as expected\n", (void*)smem_raw);
+    __trap();
+  }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C2_SMEM_BAR);
+  // Q + K and V of an item have separate barriers: Q / K are released as soon as the item's S MMAs have completed (they are
+  // issued during the PREVIOUS item), so the producer runs Q / K two items and V one item ahead.
+  uint64_t* kq_full = bars + 0;     // [2 stages] this CTA's TMA bytes of an item's Q tile and K rows
+  uint64_t* v_full = bars + 2;      // [2] ... and of its V half
+  uint64_t* peer_kq = bars + 4;     // [2] leader only: the peer CTA's kq_full has completed (forwarded)
+  uint64_t* peer_v = bars + 6;      // [2] leader only: ... v_full
+  uint64_t* kq_empty = bars + 8;    // [2] tcgen05.commit (multicast) + this CTA's two CLS warps
+  uint64_t* v_empty = bars + 10;    // [2] same
+  uint64_t* s_full = bars + 12;     // [2 key blocks] multicast commit, one completion per item
+  uint64_t* p_full = bars + 14;     // [2] leader only: 16 arrivals (8 softmax warps x 2 CTAs)
+  uint64_t* pv_done = bars + 16;    // P V of key block 0 has completed (multicast; the rare accumulator rescale waits for it)
+  uint64_t* o_full = bars + 17;     // multicast commit, one completion per item
+  uint64_t* o_free = bars + 18;     // leader only: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint64_t* cls_ready = bars + 19;  // [2 key blocks] 1 arrival (this CTA's CLS warp) + the peer's scores as transaction bytes
+  uint64_t* clsp_ready = bars + 21; // the CLS row's probabilities of both key blocks are in shared memory (2 CLS warps)
+  uint64_t* clsp_free = bars + 22;  // ... have been consumed (4 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  float* cls_sc = reinterpret_cast<float*>(smem + C2_SMEM_CLS);             // [2 item parities][2 key blocks][144] scores
+  __nv_bfloat16* cls_p = reinterpret_cast<__nv_bfloat16*>(cls_sc + 2 * 2 * 144);   // [2 key blocks][144] probabilities
+  float* cls_ml = reinterpret_cast<float*>(cls_p + 2 * 144);                // [2 key blocks][2] block max (log2 units), block sum
+  float* xmax = reinterpret_cast<float*>(smem + C2_SMEM_XMAX);              // [2][128]
+  uint8_t* stage_out = smem + C2_SMEM_STAGE;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int n_my = p.num_items > cluster_id ? (p.num_items - cluster_id + num_clusters - 1) / num_clusters : 0;
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmap72);
+    tma_prefetch_desc(&tmap64);
+    tma_prefetch_desc(&tmap128);
+    tma_prefetch_desc(&tmap136);
+    tma_prefetch_desc(&tmap_out);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kq_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&peer_kq[s], 1); mbar_init(&peer_v[s], 1);
+      mbar_init(&kq_empty[s], 3); mbar_init(&v_empty[s], 5);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 16); mbar_init(&cls_ready[s], 1);
+    }
+    mbar_init(pv_done, 1); mbar_init(o_full, 1); mbar_init(o_free, 8);
+    mbar_init(clsp_ready, 2); mbar_init(clsp_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_cg<2>(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer: this CTA's share of every item
+    // order K/Q(0) K/Q(1) V(0) K/Q(2) V(1) K/Q(3) ...: each load is issued as soon as its buffer can be free
+    if (lane == 0) {
+      TRACE_DECL
+      auto load_kq = [&](int i) {
+        const int w = cluster_id + i * num_clusters;
+        const int b = w / VA_H, h = w - b * VA_H;
+        const int row0 = b * VA_S;
+        const int s = i & 1;
+        uint8_t* sQ = smem + s * C2_STAGE_BYTES;
+        uint8_t* sK = sQ + C2_Q_BYTES;
+        c2_wait(&kq_empty[s], ((i >> 1) & 1) ^ 1);
+        TRACE(0, i * 100 + 1);                                   // Q / K buffers free -> loads issued
+        mbar_arrive_expect_tx(&kq_full[s], C2_Q_BYTES + C2_K_BYTES);
+#pragma unroll
+        for (int db = 0; db < 2; ++db) {                         // K rows of block 0, Q tile, K rows of block 1
+          tma_load_3d(sK + db * C2_KD_BYTES, &tmap72, &kq_full[s], db * 64, VA_H + h, row0 + (int)rank * C2_HALF0);
+          tma_load_3d(sQ + db * PP_Q_BYTES, &tmap128, &kq_full[s], db * 64, h, row0 + 1 + (int)rank * 128);
+          tma_load_3d(sK + db * C2_KD_BYTES + C2_HALF0 * 128, &tmap64, &kq_full[s], db * 64, VA_H + h,
+                      row0 + C2_KEYS0 + (int)rank * C2_HALF1);
+        }
+      };
+      auto load_v = [&](int i) {
+        const int w = cluster_id + i * num_clusters;
+        const int b = w / VA_H, h = w - b * VA_H;
+        const int row0 = b * VA_S;
+        const int s = i & 1;
+        uint8_t* sV = smem + s * C2_STAGE_BYTES + C2_Q_BYTES + C2_K_BYTES;
+        c2_wait(&v_empty[s], ((i >> 1) & 1) ^ 1);
+        TRACE(0, i * 100 + 2);                                   // V buffer free -> loads issued
+        mbar_arrive_expect_tx(&v_full[s], C2_V_BYTES);
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb)                           // every key, this CTA's 64-column d half (88.. zero-filled)
+          tma_load_3d(sV + hb * VA_BOX_BYTES, &tmap136, &v_full[s], (int)rank * 64, 2 * VA_H + h, row0 + hb * VA_BOX_ROWS);
+      };
+      if (n_my > 0) load_kq(0);
+      if (n_my > 1) load_kq(1);
+      for (int i = 0; i < n_my; ++i) {
+        load_v(i);
+        if (i + 2 < n_my) load_kq(i + 2);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && !leader) {
+      // ============================================================== peer: forward "my loads have landed" to the leader
+      // (same order as the producer issues them; the bytes are TMA (async-proxy) writes, complete once the barrier fires)
+      const uint32_t pkq0 = mapa_u32(smem_u32(&peer_kq[0]), 0), pv0 = mapa_u32(smem_u32(&peer_v[0]), 0);
+      auto fwd_kq = [&](int i) { c2_wait(&kq_full[i & 1], (i >> 1) & 1); mbar_arrive_cluster_relaxed(pkq0 + (i & 1) * 8); };
+      auto fwd_v = [&](int i) { c2_wait(&v_full[i & 1], (i >> 1) & 1); mbar_arrive_cluster_relaxed(pv0 + (i & 1) * 8); };
+      if (n_my > 0) fwd_kq(0);
+      if (n_my > 1) fwd_kq(1);
+      for (int i = 0; i < n_my; ++i) {
+        fwd_v(i);
+        if (i + 2 < n_my) fwd_kq(i + 2);
+      }
+    } else if (lane == 0) {
+      // ============================================================== MMA issuer (leader CTA, for the pair)
+      TRACE_DECL
+      C2Issue c;
+      c.tmem_base = tmem_base;
+      c.q_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);
+      c.k_lo = ((smem_u32(smem + C2_Q_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+      c.v_lo = ((smem_u32(smem + C2_Q_BYTES + C2_K_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+      c.hi = (1024u >> 4) | (1u << 14) | (2u << 29);               // SBO 1024 | version | SWIZZLE_128B (K-major and MN-major alike)
+      c.s_full = s_full;
+      auto kq_landed = [&](int i) {                              // non-blocking
+        return mbar_try_wait(&kq_full[i & 1], (i >> 1) & 1) && mbar_try_wait(&peer_kq[i & 1], (i >> 1) & 1);
+      };
+      auto wait_kq = [&](int i) {
+        c2_wait(&kq_full[i & 1], (i >> 1) & 1);
+        c2_wait(&peer_kq[i & 1], (i >> 1) & 1);
+        tc_fence_after();
+      };
+      if (n_my > 0) {
+        wait_kq(0);
+        c2_issue_s(c, 0, 0);
+        c2_issue_s(c, 0, 1);
+        umma_commit_cg<2>(&kq_empty[0]);
+      }
+#pragma unroll 1
+      for (int i = 0; i < n_my; ++i) {
+        const uint32_t ph = i & 1;
+        const int s = i & 1;
+        const bool has_next = i + 1 < n_my;
+        c2_wait(&p_full[0], ph);
+        TRACE(1, i * 100 + 10);                                  // P(0) seen
+        c2_wait(o_free, ph ^ 1);                               // both CTAs' epilogues have read the previous item's O
+        c2_wait(&v_full[s], (i >> 1) & 1);
+        c2_wait(&peer_v[s], (i >> 1) & 1);
+        tc_fence_after();
+        TRACE(1, i * 100 + 11);                                  // O free, V landed
+        c2_issue_pv<0>(c, s);
+        umma_commit_cg<2>(pv_done);
+        TRACE(1, i * 100 + 12);                                  // P V(0) issued
+        // S(0) of the next item goes in here when its operands are already there; otherwise P V(1) must not wait for them
+        bool s0_done = false;
+        if (has_next && kq_landed(i + 1)) {
+          tc_fence_after();
+          c2_issue_s(c, s ^ 1, 0);
+          s0_done = true;
+          TRACE(1, i * 100 + 14);                                // next S(0) issued (early)
+        }
+        c2_wait(&p_full[1], ph);
+        TRACE(1, i * 100 + 15);                                  // P(1) seen
+        tc_fence_after();
+        c2_issue_pv<1>(c, s);
+        umma_commit_cg<2>(o_full);
+        umma_commit_cg<2>(&v_empty[s]);                          // every MMA reading this stage's V has completed
+        TRACE(1, i * 100 + 16);                                  // P V(1) issued
+        if (has_next) {
+          if (!s0_done) {
+            wait_kq(i + 1);
+            TRACE(1, i * 100 + 13);                              // next item's Q / K landed (late)
+            c2_issue_s(c, s ^ 1, 0);
+          }
+          c2_issue_s(c, s ^ 1, 1);
+          umma_commit_cg<2>(&kq_empty[s ^ 1]);                   // ... Q / K of the next item
+          TRACE(1, i * 100 + 17);                                // next S(1) issued
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ================================================================ CLS query row, scores + softmax: warp 2 key block 0, warp 3 block 1
+    const int kb = warp - 2;
+    const uint32_t peer = rank ^ 1u;
+    int tr_n = 0;
+    // the CLS query: this lane's d chunks (16 bytes each: qd, qd + 4, qd + 8), fetched one item ahead as packed bf16
+    // (global-memory latency off the per-item chain) and widened to fp32 at the top of the item
+    const int qd = lane >> 3;
+    uint4 qn[3];
+    auto load_q = [&](int i) {
+      const int w = cluster_id + i * num_clusters;
+      const int b = w / VA_H, h = w - b * VA_H;
+      const uint4* q4 = reinterpret_cast<const uint4*>(p.qkv + (long long)b * VA_S * p.ld_qkv + h * VA_D);
+#pragma unroll
+      for (int c3 = 0; c3 < 3; ++c3) qn[c3] = (qd + 4 * c3 < 11) ? __ldg(q4 + qd + 4 * c3) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    if (n_my > 0) load_q(0);
+    for (int i = 0; i < n_my; ++i) {
+      const int s = i & 1;
+      const uint32_t sK32 = smem_u32(smem + s * C2_STAGE_BYTES + C2_Q_BYTES);
+      float qf[24];
+#pragma unroll
+      for (int c3 = 0; c3 < 3; ++c3) {
+        const uint32_t w4[4] = {qn[c3].x, qn[c3].y, qn[c3].z, qn[c3].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          qf[c3 * 8 + 2 * e] = __uint_as_float(w4[e] << 16);
+          qf[c3 * 8 + 2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u);
+        }
+      }
+      if (i + 1 < n_my) load_q(i + 1);
+      float* sc_local = cls_sc + ((i & 1) * 2 + kb) * 144;
+      const uint32_t sc_peer = mapa_u32(smem_u32(sc_local), peer);
+      const uint32_t ready_peer = mapa_u32(smem_u32(&cls_ready[kb]), peer);
+      c2_wait(&kq_full[s], (i >> 1) & 1);
+      if (lane == 0 && kb == 0) TRACE(3, i * 100 + 30);          // K landed
+      c2_cls_block(p, i, kb, rank, sK32, sc_local, sc_peer, &cls_ready[kb], ready_peer, &kq_empty[s], clsp_free, clsp_ready,
+                   cls_p + kb * 144, cls_ml + kb * 2, lane, qf, tr_n);
+    }
+  } else if (warp < 12) {
+    // ================================================================ softmax: two threads per query row (A: warps 4-7, B: 8-11)
+    const int hf = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t o_addr = lane_base + C2_COL_O + hf * 64;      // this thread's half of the accumulator columns (rescale)
+    const float sl2 = p.scale_log2;
+    const uint32_t p_full0 = mapa_u32(smem_u32(&p_full[0]), 0), p_full1 = mapa_u32(smem_u32(&p_full[1]), 0);
+    TRACE_DECL
+#ifdef TGB_ATTN_TRACE
+    const bool tr_on = (quarter == 0 && lane == 0);
+#define CTRACE(tag) do { if (tr_on) TRACE(4 + hf, tag); } while (0)
+#else
+#define CTRACE(tag) do { } while (0)
+#endif
+    for (int i = 0; i < n_my; ++i) {
+      const uint32_t ph = i & 1;
+      float mx, l;
+      {
+        // ------------------------------------------------------------ key block 0: keys [0,144), all valid
+        const uint32_t s_addr = lane_base + C2_COL_S0 + hf * C2_SPLIT0;
+        c2_wait(&s_full[0], ph);
+        CTRACE(i * 100 + 40);                                    // S(0) seen
+        tc_fence_after();
+        const float mine = hf == 0 ? c2_row_max<80, 80>(s_addr) : c2_row_max<64, 64>(s_addr);
+        xmax[hf * 128 + row] = mine;
+        named_bar_sync(4 + quarter, 64);
+        mx = fmaxf(mine, xmax[(hf ^ 1) * 128 + row]) * sl2;
+        named_bar_sync(4 + quarter, 64);                         // both have read before the next block's maxima are written
+        CTRACE(i * 100 + 41);                                    // row max known
+        l = c2_exp_rt(s_addr, hf == 0 ? C2_SPLIT0 / 16 : (C2_KEYS0 - C2_SPLIT0) / 16, 0, sl2, -mx);
+        CTRACE(i * 100 + 42);                                    // exponentials done
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(p_full0);   // P is in tensor memory (tcgen05.wait::st above): no generic-memory release needed
+        CTRACE(i * 100 + 43);                                    // P(0) published
+      }
+      {
+        // ------------------------------------------------------------ key block 1: keys [144,272), 113 valid
+        const uint32_t s_addr = lane_base + C2_COL_S1 + hf * C2_SPLIT1;
+        c2_wait(&s_full[1], ph);
+        CTRACE(i * 100 + 50);                                    // S(1) seen
+        tc_fence_after();
+        const int nv1 = hf == 0 ? C2_SPLIT1 : C2_VALID1 - C2_SPLIT1;      // valid keys among this thread's 64 columns: 64 / 49
+        const float mine = hf == 0 ? c2_row_max<64, 64>(s_addr) : c2_row_max<64, C2_VALID1 - C2_SPLIT1>(s_addr);
+        xmax[hf * 128 + row] = mine;
+        named_bar_sync(4 + quarter, 64);
+        const float m1x = fmaxf(mine, xmax[(hf ^ 1) * 128 + row]) * sl2;
+        named_bar_sync(4 + quarter, 64);
+        float f = 1.f;
+        const bool need = m1x > mx + PP_RESCALE_THRESHOLD;       // the same decision in both threads of the row
+        if (need) {
+          f = ex2_approx(mx - m1x);
+          mx = m1x;
+          l *= f;
+        }
+        if (__any_sync(0xffffffffu, need)) {                     // rare: rescale this warp's rows of its O columns in place
+          c2_wait(pv_done, ph);                                 // P V of key block 0 has completed
+          tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < (hf == 0 ? 64 : 32); cc += 8) {  // d 0..63 / 64..95 (88.. are zero)
+            uint32_t ov[8];
+            tmem_ld8<0>(o_addr + cc, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
+            tmem_st8<0>(o_addr + cc, ov);
+          }
+          tmem_st_wait();
+        }
+        l += c2_exp_rt(s_addr, nv1 >> 4, nv1 & 15, sl2, -mx);
+        uint32_t lv[1] = {__float_as_uint(l)};                   // this thread's part of the row sum, for the epilogue
+        tmem_st1<0>(lane_base + C2_COL_L + (i & 1) * 2 + hf, lv);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(p_full1);
+        CTRACE(i * 100 + 53);                                    // P(1) published
+      }
+    }
+  } else {
+    // ================================================================ epilogue warpgroup (warps 12-15)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const bool store_thread = (warp == 12 && lane == 0);
+    const uint32_t o_free0 = mapa_u32(smem_u32(o_free), 0);
+    TRACE_DECL
+    for (int i = 0; i < n_my; ++i) {
+      const int w = cluster_id + i * num_clusters;
+      const int b = w / VA_H, h = w - b * VA_H;
+      c2_wait(o_full, i & 1);
+      if (store_thread) TRACE(2, i * 100 + 60);                  // O complete
+      tc_fence_after();
+      uint32_t o[96], lv[2];
+      tmem_ld32<0>(lane_base + C2_COL_O, o);
+      tmem_ld32<32>(lane_base + C2_COL_O + 32, o);
+      tmem_ld32<64>(lane_base + C2_COL_O + 64, o);
+      tmem_ld2<0>(lane_base + C2_COL_L + (i & 1) * 2, lv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(o_free0);   // the accumulator has been READ (tcgen05.wait::ld above)
+      const float inv = 1.f / (__uint_as_float(lv[0]) + __uint_as_float(lv[1]));
+      if (store_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the tile
+      named_bar_sync(2, 128);
+      uint4* srow = reinterpret_cast<uint4*>(stage_out + row * (VA_D * 2));
+#pragma unroll
+      for (int cc = 0; cc < 11; ++cc) {                          // 88 valid d columns = 11 x 16 bytes
+        const float2 i2 = make_float2(inv, inv);
+        const float2 a = __fmul2_rn(make_float2(__uint_as_float(o[8 * cc + 0]), __uint_as_float(o[8 * cc + 1])), i2);
+        const float2 bq = __fmul2_rn(make_float2(__uint_as_float(o[8 * cc + 2]), __uint_as_float(o[8 * cc + 3])), i2);
+        const float2 d = __fmul2_rn(make_float2(__uint_as_float(o[8 * cc + 4]), __uint_as_float(o[8 * cc + 5])), i2);
+        const float2 e = __fmul2_rn(make_float2(__uint_as_float(o[8 * cc + 6]), __uint_as_float(o[8 * cc + 7])), i2);
+        uint4 v;
+        v.x = pack_bf16(a.x, a.y);
+        v.y = pack_bf16(bq.x, bq.y);
+        v.z = pack_bf16(d.x, d.y);
+        v.w = pack_bf16(e.x, e.y);
+        srow[cc] = v;
+      }
+      fence_proxy_async();                                       // generic-proxy writes -> visible to the TMA (async proxy)
+      named_bar_sync(2, 128);
+      if (store_thread) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stage_out)), "r"(0), "r"(h),
+                       "r"(b * VA_S + 1 + (int)rank * 128) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        TRACE(2, i * 100 + 62);                                  // store issued
+      }
+      // ---- CLS query row, O = p V for this CTA's d half on the FP32 pipe: warp q takes d [16q, 16q+16); lane = (key group
+      // kg = lane >> 3, d pair dp = lane & 7); key = 4 j + kg, so a phase of eight lanes reads 32 contiguous bytes of one V row
+      // and the four rows of an instruction sit at four different swizzle phases (conflict-free).  Keys 0..143 (j < 36) are
+      // block 0, the rest block 1: one accumulator pair per block (each block's p is relative to its own max).
+      {
+        const int s = i & 1;
+        const uint32_t sV32 = smem_u32(smem + s * C2_STAGE_BYTES + C2_Q_BYTES + C2_K_BYTES);
+        const int kg = lane >> 3, dp = lane & 7;
+        c2_wait(clsp_ready, i & 1);
+        const int chunk = 2 * quarter + (dp >> 2);              // 16-byte chunk of the row holding this lane's d pair
+        // key = 8 jj + kg (row kg of 8-row group jj) and 8 jj + 4 + kg (row kg + 4): two fixed byte offsets per lane, the
+        // group only adds 1024 bytes; the probabilities sit at element == key (block 1's key 144 is element 144 of cls_p)
+        const uint32_t voff0 = sV32 + (uint32_t)(kg * 128 + ((chunk ^ kg) << 4) + (dp & 3) * 4);
+        const uint32_t voff1 = sV32 + (uint32_t)((kg + 4) * 128 + ((chunk ^ (kg + 4)) << 4) + (dp & 3) * 4);
+        const uint32_t poff = smem_u32(cls_p) + kg * 2;
+        float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        float2 accb[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          const int g0 = blk == 0 ? 0 : 18, g1 = blk == 0 ? 18 : 34;      // 8-row groups: keys [0,144) / [144,272)
+#pragma unroll 6
+          for (int jj = g0; jj < g1; ++jj) {
+            uint32_t v0, v1;
+            uint16_t p0, p1;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0) : "r"(voff0 + jj * 1024));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v1) : "r"(voff1 + jj * 1024));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p0) : "r"(poff + jj * 16));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(p1) : "r"(poff + jj * 16 + 8));
+            const float pk0 = __uint_as_float(static_cast<uint32_t>(p0) << 16);
+            const float pk1 = __uint_as_float(static_cast<uint32_t>(p1) << 16);
+            acc[blk].x = fmaf(pk0, __uint_as_float(v0 << 16), acc[blk].x);
+            acc[blk].y = fmaf(pk0, __uint_as_float(v0 & 0xffff0000u), acc[blk].y);
+            accb[blk].x = fmaf(pk1, __uint_as_float(v1 << 16), accb[blk].x);
+            accb[blk].y = fmaf(pk1, __uint_as_float(v1 & 0xffff0000u), accb[blk].y);
+          }
+          acc[blk].x += accb[blk].x;
+          acc[blk].y += accb[blk].y;
+        }
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          acc[blk].x += __shfl_xor_sync(0xffffffffu, acc[blk].x, 8);
+          acc[blk].y += __shfl_xor_sync(0xffffffffu, acc[blk].y, 8);
+          acc[blk].x += __shfl_xor_sync(0xffffffffu, acc[blk].x, 16);
+          acc[blk].y += __shfl_xor_sync(0xffffffffu, acc[blk].y, 16);
+        }
+        const float m0 = cls_ml[0], l0 = cls_ml[1], m1 = cls_ml[2], l1 = cls_ml[3];
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(clsp_free);                                // p and (m, l) of this item have been read
+          mbar_arrive(&v_empty[s]);                              // ... and this stage's V
+        }
+        const float mm = fmaxf(m0, m1);
+        const float f0 = ex2_approx(m0 - mm), f1 = ex2_approx(m1 - mm);
+        const float inv = 1.f / (l0 * f0 + l1 * f1);
+        if (kg == 0) {
+          const int d0 = (int)rank * 64 + quarter * 16 + 2 * dp;
+          if (d0 < VA_D) {
+            __nv_bfloat16* dst = p.out + (long long)b * VA_S * p.ld_out + h * VA_D + d0;
+            *reinterpret_cast<uint32_t*>(dst) = pack_bf16((acc[0].x * f0 + acc[1].x * f1) * inv, (acc[0].y * f0 + acc[1].y * f1) * inv);
+          }
+        }
+        if (store_thread) TRACE(2, i * 100 + 63);                // CLS row done
+      }
+    }
+    if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every store has landed before the CTA may exit
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                            // no CTA leaves while its pair may still touch its smem / barriers
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_cg<2>(tmem_base, 512);
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 va_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (fn) return fn;
@@ -1654,7 +2388,7 @@ extern "C" __attribute__((visibility("default"))) int tgb_debug_attn_trace(long 
 static std::atomic<int> g_vit_attention_variant{0};   // 0 = ping-pong kernel (default), 1 = one-shot, 2 = three-block (cross-checks)
 
 extern "C" int tgb_vit_attention_set_variant(int variant) {
-  TGB_CHECK_ARG(variant >= 0 && variant <= 2, "vit_attention_set_variant: 0 (ping-pong), 1 (one-shot) or 2 (three-block)");
+  TGB_CHECK_ARG(variant >= 0 && variant <= 3, "vit_attention_set_variant: 0 (ping-pong), 1 (one-shot), 2 (three-block) or 3 (CTA pair)");
   g_vit_attention_variant = variant;
   return TGB_OK;
 }
@@ -1673,15 +2407,17 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
     return TGB_ECUDA;
   }
-  CUtensorMap map, map144, map128, map96, map80;
+  CUtensorMap map, map144, map128, map96, map80, map72, map64;
   cuuint64_t dims[3] = {VA_D, 3 * VA_H, (cuuint64_t)frames * VA_S};
   cuuint64_t strides[2] = {VA_D * 2, (cuuint64_t)ld_qkv * 2};
   cuuint32_t estr[3] = {1, 1, 1};
   const int variant = g_vit_attention_variant.load();
-  CUtensorMap* maps[5] = {&map128, &map96, &map80, &map144, &map};
-  const cuuint32_t box_rows[5] = {128, P3_KB, P3_KB2, PP_KEYS0, VA_BOX_ROWS};
-  for (int i = 0; i < 5; ++i) {
-    if ((variant == 2 && i > 2) || (variant == 1 && i != 4) || (variant == 0 && (i == 1 || i == 2 || i == 4))) continue;
+  CUtensorMap* maps[7] = {&map128, &map96, &map80, &map144, &map, &map72, &map64};
+  const cuuint32_t box_rows[7] = {128, P3_KB, P3_KB2, PP_KEYS0, VA_BOX_ROWS, C2_HALF0, C2_HALF1};
+  // tensor maps each variant reads: ping-pong 128 144 | one-shot 136 | three-block 128 96 80 | pair 128 136 72 64
+  static const unsigned char needs[4][7] = {{1, 0, 0, 1, 0, 0, 0}, {0, 0, 0, 0, 1, 0, 0}, {1, 1, 1, 0, 0, 0, 0}, {1, 0, 0, 0, 1, 1, 1}};
+  for (int i = 0; i < 7; ++i) {
+    if (!needs[variant][i]) continue;
     cuuint32_t box[3] = {64, 1, box_rows[i]};
     CUresult r = fn(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1708,6 +2444,7 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM_TOTAL));
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_TOTAL));
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM_TOTAL));
+    TGB_CUDA(cudaFuncSetAttribute(vit_attention_c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_TOTAL));
   });
   VitAttnParams p;
   p.qkv = (const __nv_bfloat16*)qkv;
@@ -1718,7 +2455,11 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   p.num_items = frames * VA_H;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
-  if (variant == 1)
+  if (variant == 3) {
+    const int pairs = sm_count() / 2;
+    const int clusters = p.num_items < pairs ? p.num_items : pairs;
+    vit_attention_c2_kernel<<<2 * clusters, C2_THREADS, C2_SMEM_TOTAL, (cudaStream_t)stream>>>(map72, map64, map128, map, map_out, p);
+  } else if (variant == 1)
     vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM_TOTAL, (cudaStream_t)stream>>>(map, p);
   else if (variant == 2)
     vit_attention_p3_kernel<<<grid, P3_THREADS, P3_SMEM_TOTAL, (cudaStream_t)stream>>>(map96, map80, map128, map_out, p);

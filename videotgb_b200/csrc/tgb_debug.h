@@ -23,7 +23,8 @@ TGB_API int tgb_gemm_set_cta_group(int cta_group);
 TGB_API int tgb_gemm_set_schedule(int mode);
 /* epilogue warps per CTA, 0 = choose (8; the fp32-residual epilogues always run 8). */
 TGB_API int tgb_gemm_set_epilogue_warps(int warps);
-/* 0 = ping-pong kernel (default), 1 = one-shot kernel (whole score row in tensor memory), 2 = three-block kernel. */
+/* 0 = ping-pong kernel (default), 1 = one-shot kernel (whole score row in tensor memory), 2 = three-block kernel,
+ * 3 = CTA-pair kernel (cta_group::2). */
 TGB_API int tgb_vit_attention_set_variant(int variant);
 
 #ifdef __cplusplus
