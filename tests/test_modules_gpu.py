@@ -378,7 +378,7 @@ def test_ragged_widths_mean_assembly():
 def test_cuda_graph_replay_matches_eager(vit2):
     """Small batches replay a captured CUDA graph of the ~270-launch ViT pass; results must equal the eager launches."""
     sd, m, px, out = vit2                       # the fixture ran with graphs enabled (2 frames <= graph_max_rows)
-    assert ("vit", 2, 592) in m._graphs.entries
+    assert ("vit", 2, 592, True) in m._graphs.entries      # key = (kind, frames, K, LayerNorm fold on)
     m.graph_max_rows = 0
     eager = m(pixel_values=px).last_hidden_state
     m.graph_max_rows = 64
