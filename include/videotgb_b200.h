@@ -172,6 +172,14 @@ TGB_API int tgb_layernorm_f32(const float* x, int64_t ldx, const float* gamma, c
 TGB_API int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                        void* out, int64_t ldo, const float* mask, int B, int H, int Sq, int Sk, int D, float scale,
                        tgb_stream_t stream);
+/* Self-attention over the concatenation of two separately stored row groups, without the concatenation: the
+ * InstructBLIP Q-Former attends over cat(query rows, instruction rows) (xinstructblip.py:1168-1176, :836-851), whose two
+ * halves go through different feed-forward blocks afterwards (:858-876).  qkv1: bf16 [B*n1, ld_qkv] fused q|k|v of the
+ * first n1 sequence rows of every batch element, qkv2: [B*n2, ld_qkv] of the remaining n2; out1 [B*n1, ldo], out2
+ * [B*n2, ldo]; mask f32 additive [B, n1+n2] or NULL.  Same arithmetic as tgb_attention_bf16 on the concatenated rows.  */
+TGB_API int tgb_self_attention_2seg_bf16(const void* qkv1, const void* qkv2, int64_t ld_qkv, void* out1, void* out2,
+                                 int64_t ldo, const float* mask, int B, int H, int n1, int n2, int D, float scale,
+                                 tgb_stream_t stream);
 
 /* ViT self-attention on tcgen05 (xblip2.py:156-192), specialised for the EVA-ViT-g shape: 257 tokens, 16 heads x 88.
  * qkv: bf16 [frames*257, ld_qkv] fused projection, q|k|v of head h at columns {0,1408,2816}+88h (the tensor is read

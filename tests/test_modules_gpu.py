@@ -246,6 +246,26 @@ def test_sampler(gold, mode):
         m(encoder_embeds=of.to(DEV), attention_mask=of_mask.to(DEV), encoder_hidden_states=qids.to(DEV), mode="bogus")
 
 
+@pytest.mark.parametrize("mode", ["fusion", "multi_modal"])
+def test_sampler_sinusoidal_rope_tables(mode):
+    """the rotary tables are opaque weights -- N(0, 0.02) draws after the reference's `_init_weights`, or the
+    true sin | cos table the class builds first (xropebert.py:149-164).  Same kernels, table-agnostic: checked against the
+    fp32 oracle with the sinusoidal tables (large, structured rotations instead of small random ones)."""
+    sd = dict(syn.sampler_state_dict())
+    for key in ("encoder.embed_positions.weight", "encoder.c_embed_positions.weight"):
+        n_pos, dim = sd[key].shape
+        sd[key] = syn.sinusoidal_table(n_pos, dim)
+    m = RopeBertModel(NS(fusion_layer=6, encoder_width=768)).to(DEV)
+    m.load_state_dict(sd)
+    of, of_mask, of_len, qids, qmask = cases.sampler_inputs()
+    seq, logits = m(encoder_embeds=of.to(DEV), attention_mask=of_mask.to(DEV), encoder_hidden_states=qids.to(DEV),
+                    encoder_attention_mask=qmask.to(DEV), mode=mode)
+    with torch.no_grad():
+        rseq, rlogits = torch_ref.sampler_forward(to_dev(sd), of.to(DEV), of_mask.to(DEV), qids.to(DEV), qmask.to(DEV), mode=mode)
+    assert_parity(seq, rseq, f"sinusoidal tables, {mode}: sequence output")
+    assert_parity(logits, rlogits, f"sinusoidal tables, {mode}: logits")
+
+
 def test_sampler_long_video():
     """cfg 4 shape: 1024 candidate flow frames (needs max_position_embeddings >= 1026)."""
     cfg = syn.SamplerCfg(max_pos=1040)

@@ -43,6 +43,8 @@ SIGNATURES = {
     "tgb_layernorm_f32": ([c_vp, c_i64, c_vp, c_vp, c_f32, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp], c_int),
     "tgb_attention_bf16": ([c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int,
                             c_int, c_f32, c_vp], c_int),
+    "tgb_self_attention_2seg_bf16": ([c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32,
+                                      c_vp], c_int),
     "tgb_of_patch_reduce": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp], c_int),
     "tgb_sampler_assemble": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "tgb_embed_layernorm": ([c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_f32, c_i64, c_int, c_vp, c_i64, c_vp,

@@ -20,7 +20,20 @@ struct AttnParams {
   long long ldq, ldk, ldv, ldo;
   int B, H, Sq, Sk;
   float scale_log2;           // scale * log2(e)
+  // optional second row segment (self-attention over the concatenation of two separately stored row groups, e.g. the
+  // Q-Former's 32 query rows and Tt instruction rows): sequence row r < n1 is row b*n1 + r of q/k/v/out, row r >= n1 is
+  // row b*(S - n1) + (r - n1) of q2/k2/v2/out2 (same leading dimensions).  q2 == nullptr: one segment.
+  const __nv_bfloat16* q2; const __nv_bfloat16* k2; const __nv_bfloat16* v2;
+  __nv_bfloat16* out2;
+  int n1;
 };
+
+// address of sequence row r of batch b in a (possibly two-segment) operand with S rows per batch
+template <typename T>
+__device__ __forceinline__ T* attn_row(T* a, T* a2, long long ld, int b, int r, int S, int n1) {
+  if (a2 == nullptr) return a + ((long long)b * S + r) * ld;
+  return r < n1 ? a + ((long long)b * n1 + r) * ld : a2 + ((long long)b * (S - n1) + (r - n1)) * ld;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
@@ -158,14 +171,14 @@ __global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
   for (int i = tid; i < SkPad * KCH; i += blockDim.x) {
     const int r = i / KCH, c = i - r * KCH;
     __nv_bfloat16* dst = sKp + (size_t)r * C::KP + c * 8;
-    if (r < p.Sk && c < CH) cp_async16(dst, p.k + ((long long)b * p.Sk + r) * p.ldk + h * D + c * 8);
+    if (r < p.Sk && c < CH) cp_async16(dst, attn_row(p.k, p.k2, p.ldk, b, r, p.Sk, p.n1) + h * D + c * 8);
     else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
   constexpr int VCH = C::VP / 8;
   for (int i = tid; i < SkPad * VCH; i += blockDim.x) {
     const int r = i / VCH, c = i - r * VCH;
     __nv_bfloat16* dst = sVp + (size_t)r * C::VP + c * 8;
-    if (r < p.Sk && c < CH) cp_async16(dst, p.v + ((long long)b * p.Sk + r) * p.ldv + h * D + c * 8);
+    if (r < p.Sk && c < CH) cp_async16(dst, attn_row(p.v, p.v2, p.ldv, b, r, p.Sk, p.n1) + h * D + c * 8);
     else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
   if (p.mask)
@@ -182,8 +195,9 @@ __global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
     // ---- Q fragments straight from global (row-major A layout of m16n8k16)
     uint32_t qf[C::KS][4];
     const int r0 = mt * 16 + g, r1 = r0 + 8;
-    const __nv_bfloat16* q0 = p.q + ((long long)b * p.Sq + r0) * p.ldq + h * D;
-    const __nv_bfloat16* q1 = p.q + ((long long)b * p.Sq + r1) * p.ldq + h * D;
+    // (rows >= Sq are never dereferenced: clamp them so that the two-segment address stays inside its segment)
+    const __nv_bfloat16* q0 = attn_row(p.q, p.q2, p.ldq, b, r0 < p.Sq ? r0 : 0, p.Sq, p.n1) + h * D;
+    const __nv_bfloat16* q1 = attn_row(p.q, p.q2, p.ldq, b, r1 < p.Sq ? r1 : 0, p.Sq, p.n1) + h * D;
 #pragma unroll
     for (int ks = 0; ks < C::KS; ++ks) {
       const int c0 = ks * 16 + t2, c1 = c0 + 8;
@@ -208,8 +222,8 @@ __global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
-    __nv_bfloat16* o0 = p.out + ((long long)b * p.Sq + r0) * p.ldo + h * D;
-    __nv_bfloat16* o1 = p.out + ((long long)b * p.Sq + r1) * p.ldo + h * D;
+    __nv_bfloat16* o0 = attn_row(p.out, p.out2, p.ldo, b, r0 < p.Sq ? r0 : 0, p.Sq, p.n1) + h * D;
+    __nv_bfloat16* o1 = attn_row(p.out, p.out2, p.ldo, b, r1 < p.Sq ? r1 : 0, p.Sq, p.n1) + h * D;
 #pragma unroll
     for (int nd = 0; nd < C::ND; ++nd) {
       if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(o0 + nd * 8 + t2) = pack_bf16(o[nd][0] * inv0, o[nd][1] * inv0);
@@ -346,6 +360,38 @@ extern "C" int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int
   p.out = (__nv_bfloat16*)out; p.mask = mask;
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.q2 = p.k2 = p.v2 = nullptr; p.out2 = nullptr; p.n1 = 0;
+  if (D == 88) return launch_attention<88>(p, (cudaStream_t)stream);
+  return launch_attention<64>(p, (cudaStream_t)stream);
+}
+
+extern "C" int tgb_self_attention_2seg_bf16(const void* qkv1, const void* qkv2, int64_t ld_qkv, void* out1, void* out2,
+                                            int64_t ldo, const float* mask, int B, int H, int n1, int n2, int D, float scale,
+                                            tgb_stream_t stream) {
+  int st = check_device();
+  if (st != TGB_OK) return st;
+  TGB_CHECK_ARG(qkv1 && qkv2 && out1 && out2, "self_attention_2seg: null pointer");
+  TGB_CHECK_ARG(B >= 0 && H > 0 && n1 > 0 && n2 > 0 && (long long)B * H <= 2147483647, "self_attention_2seg: bad shape B=%d H=%d n1=%d n2=%d", B, H, n1, n2);
+  TGB_CHECK_ARG(D == 64 || D == 88, "self_attention_2seg: head dim %d not supported (64, 88)", D);
+  TGB_CHECK_ARG(ld_qkv % 8 == 0 && ld_qkv >= 3 * (int64_t)H * D && ldo % 2 == 0 && ldo >= (int64_t)H * D,
+                "self_attention_2seg: leading dims must cover 3*H*D / H*D columns (multiples of 8 / 2)");
+  TGB_CHECK_ARG(((uintptr_t)qkv1 % 16) == 0 && ((uintptr_t)qkv2 % 16) == 0 && ((uintptr_t)out1 % 4) == 0 && ((uintptr_t)out2 % 4) == 0,
+                "self_attention_2seg: buffers must be 16-byte aligned");
+  using C64 = AttnCfg<64>;
+  const int S = n1 + n2, SkPad = (S + 15) & ~15;
+  TGB_CHECK_ARG((size_t)SkPad * (C64::KP + C64::VP + 16) * 2 + (size_t)SkPad * 4 <= 112 * 1024,
+                "self_attention_2seg: %d rows do not fit the single-pass kernel", S);
+  if (B == 0) return TGB_OK;
+  const __nv_bfloat16* a = (const __nv_bfloat16*)qkv1;
+  const __nv_bfloat16* b2 = (const __nv_bfloat16*)qkv2;
+  const int hd = H * D;
+  AttnParams p;
+  p.q = a; p.k = a + hd; p.v = a + 2 * hd;
+  p.q2 = b2; p.k2 = b2 + hd; p.v2 = b2 + 2 * hd;
+  p.out = (__nv_bfloat16*)out1; p.out2 = (__nv_bfloat16*)out2; p.mask = mask;
+  p.ldq = p.ldk = p.ldv = ld_qkv; p.ldo = ldo;
+  p.B = B; p.H = H; p.Sq = S; p.Sk = S; p.n1 = n1;
   p.scale_log2 = scale * 1.4426950408889634f;
   if (D == 88) return launch_attention<88>(p, (cudaStream_t)stream);
   return launch_attention<64>(p, (cudaStream_t)stream);

@@ -556,23 +556,33 @@ class _QFormerBase(_KernelModule):
             return None
         return ops.additive_mask(mask, value)[0]
 
-    def _run_layers(self, layers, x_f32, x_bf16, nf, seq, nq, img, s_img, self_mask, cross_mask, final_bf16_out=None):
-        """-> (fp32, bf16) [nf*seq, d].  `final_bf16_out` (bf16 [nf*nq, d], contiguous): the LAST LayerNorm of the query
-        rows writes its bf16 result there -- e.g. straight into this rank's slot of the NCCL all-gather buffer."""
+    def _run_layers(self, layers, x_f32, x_bf16, nf, seq, nq, img, s_img, self_mask, cross_mask, final_bf16_out=None,
+                    text=None):
+        """-> (fp32, bf16) [nf*nq, d] query rows (and, with `text`, the instruction rows).  `final_bf16_out` (bf16
+        [nf*nq, d], contiguous): the LAST LayerNorm of the query rows writes its bf16 result there -- e.g. straight into
+        this rank's slot of the NCCL all-gather buffer.
+
+        `text` = (fp32, bf16) [nf*tt, d] instruction rows (InstructBLIP).  Query rows and instruction rows live in SEPARATE
+        buffers for the whole stack: they only meet in the self-attention, which reads both row groups in place
+        (`ops.self_attention_2seg`); every other block runs per group, as the reference's feed_forward_chunk_query /
+        feed_forward_chunk split does (xinstructblip.py:858-876) -- no per-layer split copies or torch.cat."""
         d, h, hd = self.hidden, self.heads, self.head_dim
         scale = 1.0 / math.sqrt(hd)
+        q_f32, q_bf16 = x_f32, x_bf16
+        t_f32, t_bf16 = text if text is not None else (None, None)
+        tt = seq - nq
         for li, lp in enumerate(layers):
             # self-attention over all `seq` rows (queries + instruction tokens)
-            qkv = ops.gemm(x_bf16, lp.qkv_w, lp.qkv_b, ops.EPI_BF16)
-            ctx = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nf, h, seq, seq, hd, scale, self_mask)
-            acc = ops.gemm(ctx, lp.ao_w, lp.ao_b, ops.EPI_F32_RESID, resid=x_f32)
-            a_f32, a_bf16 = self._post_ln(acc, lp.ao_ln, self.eps)
-            if seq > nq:       # InstructBLIP: split query rows / text rows (plain strided copies)
-                a3f, a3b = a_f32.view(nf, seq, d), a_bf16.view(nf, seq, d)
-                q_f32, q_bf16 = a3f[:, :nq].reshape(-1, d), a3b[:, :nq].reshape(-1, d)
-                t_f32, t_bf16 = a3f[:, nq:].reshape(-1, d), a3b[:, nq:].reshape(-1, d)
+            qkv = ops.gemm(q_bf16, lp.qkv_w, lp.qkv_b, ops.EPI_BF16)
+            if tt:
+                qkv_t = ops.gemm(t_bf16, lp.qkv_w, lp.qkv_b, ops.EPI_BF16)
+                ctx, ctx_t = ops.self_attention_2seg(qkv, qkv_t, nf, h, nq, tt, hd, scale, self_mask)
+                acc_t = ops.gemm(ctx_t, lp.ao_w, lp.ao_b, ops.EPI_F32_RESID, resid=t_f32)
+                t_f32, t_bf16 = self._post_ln(acc_t, lp.ao_ln, self.eps)
             else:
-                q_f32, q_bf16 = a_f32, a_bf16
+                ctx = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nf, h, nq, nq, hd, scale, self_mask)
+            acc = ops.gemm(ctx, lp.ao_w, lp.ao_b, ops.EPI_F32_RESID, resid=q_f32)
+            q_f32, q_bf16 = self._post_ln(acc, lp.ao_ln, self.eps)
             if lp.cross is not None:
                 c = lp.cross
                 if img is None:
@@ -588,15 +598,13 @@ class _QFormerBase(_KernelModule):
                 q_bf16, q_f32 = ops.layernorm(acc, lp.oq_ln[0], lp.oq_ln[1], self.eps, out_bf16=final_bf16_out, want_f32=True)
             else:
                 q_f32, q_bf16 = self._post_ln(acc, lp.oq_ln, self.eps)
-            if seq > nq:
+            if tt:
                 inter = ops.gemm(t_bf16, lp.it_w, lp.it_b, ops.EPI_BF16_GELU)
                 acc = ops.gemm(inter, lp.ot_w, lp.ot_b, ops.EPI_F32_RESID, resid=t_f32)
                 t_f32, t_bf16 = self._post_ln(acc, lp.ot_ln, self.eps)
-                x_f32 = torch.cat([q_f32.view(nf, nq, d), t_f32.view(nf, seq - nq, d)], 1).view(-1, d)
-                x_bf16 = torch.cat([q_bf16.view(nf, nq, d), t_bf16.view(nf, seq - nq, d)], 1).view(-1, d)
-            else:
-                x_f32, x_bf16 = q_f32, q_bf16
-        return x_f32, x_bf16
+        if tt:
+            return q_f32, q_bf16, t_f32, t_bf16
+        return q_f32, q_bf16
 
     def _finish(self, x_f32, nf, seq, return_dict, x_bf16=None):
         seq_out = x_f32.view(nf, seq, self.hidden)
@@ -702,27 +710,28 @@ class InstructBlipQFormerModel(_QFormerBase):
         nf, nq, d = query_embeds.shape
         tt = 0 if input_ids is None else input_ids.shape[1]
         seq = nq + tt
-        x_f32 = torch.empty((nf, seq, d), dtype=torch.float32, device=query_embeds.device)
-        x_bf16 = torch.empty((nf, seq, d), dtype=torch.bfloat16, device=query_embeds.device)
         # query rows: LayerNorm(query_embeds); identical for every frame when query_embeds is an expand() of query_tokens
         qn_b, qn_f = ops.layernorm(query_embeds.to(torch.float32).contiguous().view(-1, d), pk.ln[0], pk.ln[1], self.eps,
                                    want_bf16=True, want_f32=True)
-        x_f32[:, :nq] = qn_f.view(nf, nq, d)
-        x_bf16[:, :nq] = qn_b.view(nf, nq, d)
+        text = None
         if tt:
             if tt > pk.pos.shape[0]:
                 raise ValueError(f"instruction length {tt} exceeds max_position_embeddings {pk.pos.shape[0]}")
-            t_f = torch.empty((nf * tt, d), dtype=torch.float32, device=x_f32.device)
-            t_b = torch.empty((nf * tt, d), dtype=torch.bfloat16, device=x_f32.device)
+            t_f = torch.empty((nf * tt, d), dtype=torch.float32, device=qn_f.device)
+            t_b = torch.empty((nf * tt, d), dtype=torch.bfloat16, device=qn_f.device)
             ops.embed_layernorm(input_ids.to(torch.int64).contiguous().view(-1), pk.word, pk.ln[0], pk.ln[1], self.eps,
                                 pos=pk.pos, period=tt, out_f32=t_f, out_bf16=t_b)
-            x_f32[:, nq:] = t_f.view(nf, tt, d)
-            x_bf16[:, nq:] = t_b.view(nf, tt, d)
+            text = (t_f, t_b)
         img, s_img = None, 0
         if encoder_hidden_states is not None:
             img = self._image_operand(encoder_hidden_states)
             s_img = encoder_hidden_states.shape[1]
         self_mask = self._additive(attention_mask, -10000.0)
         cross_mask = self._additive(encoder_attention_mask, torch.finfo(torch.float32).min)
-        x, _ = self._run_layers(pk.layers, x_f32.view(-1, d), x_bf16.view(-1, d), nf, seq, nq, img, s_img, self_mask, cross_mask)
+        res = self._run_layers(pk.layers, qn_f, qn_b, nf, seq, nq, img, s_img, self_mask, cross_mask, text=text)
+        if tt:
+            # the reference returns the whole sequence (callers keep [:, :num_query]): one concatenation at the very end
+            x = torch.cat([res[0].view(nf, nq, d), res[2].view(nf, tt, d)], dim=1).view(-1, d)
+        else:
+            x = res[0]
         return self._finish(x, nf, seq, return_dict)

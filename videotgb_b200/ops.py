@@ -405,6 +405,26 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 # ------------------------------------------------------------------------------------------------ attention
+def self_attention_2seg(qkv1: torch.Tensor, qkv2: torch.Tensor, batch: int, heads: int, n1: int, n2: int, head_dim: int,
+                        scale: float, mask: Optional[torch.Tensor] = None):
+    """Self-attention over cat(rows of qkv1, rows of qkv2) per batch element without materialising the concatenation.
+    qkv1 bf16 [batch*n1, 3*heads*head_dim], qkv2 [batch*n2, ...] -> (out1 [batch*n1, heads*head_dim], out2 [batch*n2, ...])."""
+    hd = heads * head_dim
+    for t, nm, n in ((qkv1, "qkv1", n1), (qkv2, "qkv2", n2)):
+        _need(t, torch.bfloat16, nm)
+        if t.dim() != 2 or t.shape != (batch * n, 3 * hd):
+            raise _lib.TgbError(f"self_attention_2seg: {nm} must be [batch*n, 3*heads*head_dim]")
+    if mask is not None:
+        _need(mask, torch.float32, "mask")
+        if mask.shape != (batch, n1 + n2):
+            raise _lib.TgbError("self_attention_2seg: mask must be [batch, n1+n2]")
+    out1 = torch.empty((batch * n1, hd), dtype=torch.bfloat16, device=qkv1.device)
+    out2 = torch.empty((batch * n2, hd), dtype=torch.bfloat16, device=qkv1.device)
+    check(_lib.load().tgb_self_attention_2seg_bf16(_p(qkv1), _p(qkv2), 3 * hd, _p(out1), _p(out2), hd, _p(mask), batch, heads,
+                                                   n1, n2, head_dim, float(scale), _stream()))
+    return out1, out2
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, heads: int, sq: int, sk: int,
               head_dim: int, scale: float, mask: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:

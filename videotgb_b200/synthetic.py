@@ -263,3 +263,13 @@ def raft_state_dict(seed: int = 1234, device="cpu") -> dict:
     conv(u + "mask.0", 256, 128, 3, 3)
     conv(u + "mask.2", 576, 256, 1, 1)
     return dict(sd)
+
+
+def sinusoidal_table(n_pos: int, dim: int) -> torch.Tensor:
+    """The rotary table the reference class constructs before `_init_weights` overwrites it with N(0, 0.02) draws
+    (BertSinusoidalPositionalEmbedding, xropebert.py:149-164): sin of pos / 10000^(2j/dim) in the first half of a row,
+    cos in the second half (not interleaved).  float64 arithmetic rounded to float32, as numpy -> FloatTensor does."""
+    pos = torch.arange(n_pos, dtype=torch.float64)[:, None]
+    j = torch.arange(dim // 2, dtype=torch.float64)[None, :]
+    angle = pos / torch.pow(torch.tensor(10000.0, dtype=torch.float64), 2.0 * j / dim)
+    return torch.cat([torch.sin(angle), torch.cos(angle)], dim=1).to(torch.float32)
