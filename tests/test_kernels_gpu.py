@@ -560,7 +560,7 @@ def test_attention(b, h, sq, sk, d, masked):
     assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("frames,scale_in,late_peak", [(1, 1.0, False), (3, 1.0, False), (19, 2.5, False), (2, 1.0, True),
                                                        (150, 1.0, False), (300, 1.0, True)])
 def test_vit_attention_tcgen05(frames, scale_in, late_peak, variant):

@@ -52,7 +52,9 @@ def bench(f, iters=10):
             ops.vit_attention(qkv, f, 88 ** -0.5, out=out)
             ops.vit_attention_set_variant(0)
         return run
-    for name, fn in (("tcgen05 CTA pair", variant(3)),
+    for name, fn in (("tcgen05 ping-pong + pipelined softmax", variant(5)),
+                     ("tcgen05 split-row ping-pong", variant(4)),
+                     ("tcgen05 CTA pair", variant(3)),
                      ("tcgen05 three-block", variant(2)),
                      ("tcgen05 ping-pong", variant(0)),
                      ("tcgen05 one-shot", variant(1)),

@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DBG = os.path.join(ROOT, "tools", "_dbg")
-LIB = os.path.join(DBG, "libtgb_trace.so")
+LIB = os.path.join(DBG, os.environ.get("TGB_TRACE_LIB", "libtgb_trace.so"))
 CSRC = os.path.join(ROOT, "videotgb_b200", "csrc")
 
 TAGS = {1: "TMA  K0 issued", 2: "TMA  Q0 issued", 3: "TMA  Q1 issued", 4: "TMA  V0 issued", 5: "TMA  K1 issued", 6: "TMA  V1 issued",
@@ -47,7 +47,7 @@ def build():
     os.makedirs(DBG, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
     cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-DTGB_ATTN_TRACE", "-shared", "-cudart", "static", "-o", LIB, *srcs]
+           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-DTGB_ATTN_TRACE", *os.environ.get("TGB_TRACE_DEFS", "").split(), "-shared", "-cudart", "static", "-o", LIB, *srcs]
     subprocess.run(cmd, check=True)
     print(LIB)
 
@@ -56,6 +56,10 @@ def run(frames, variant=0):
     import torch
     lib = ctypes.CDLL(LIB)
     lib.tgb_vit_attention_set_variant(variant)
+    if os.environ.get("TGB_ATTN_PREFETCH"):
+        lib.tgb_vit_attention_set_prefetch(int(os.environ["TGB_ATTN_PREFETCH"]))
+    if os.environ.get("TGB_ATTN_DBG"):
+        lib.tgb_debug_vit_attention_dbg(int(os.environ["TGB_ATTN_DBG"]))
     qkv = torch.randn(frames * 257, 4224, device="cuda").to(torch.bfloat16)
     out = torch.empty(frames * 257, 1408, dtype=torch.bfloat16, device="cuda")
     fn = lib.tgb_vit_attention_bf16

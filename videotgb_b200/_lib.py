@@ -75,6 +75,7 @@ DEBUG_SIGNATURES = {
     "tgb_gemm_set_schedule": ([c_int], c_int),
     "tgb_gemm_set_epilogue_warps": ([c_int], c_int),
     "tgb_vit_attention_set_variant": ([c_int], c_int),
+    "tgb_vit_attention_set_prefetch": ([c_int], c_int),
 }
 
 _lib = None
@@ -101,6 +102,8 @@ def load() -> ctypes.CDLL:
         lib.tgb_gemm_set_schedule(sched)
     if os.environ.get("TGB_ATTN_VARIANT"):                                                                    # A/B knob
         lib.tgb_vit_attention_set_variant(int(os.environ["TGB_ATTN_VARIANT"]))
+    if os.environ.get("TGB_ATTN_PREFETCH"):                                                                   # A/B knob
+        lib.tgb_vit_attention_set_prefetch(int(os.environ["TGB_ATTN_PREFETCH"]))
     return lib
 
 

@@ -47,6 +47,8 @@ struct VitAttnParams {
   int frames;
   int num_items;            // frames * 16
   float scale_log2;
+  int l2_prefetch;          // split-row kernel: L2 prefetch of the next item's operands (A/B knob, default off: slower)
+  int dbg;                  // timing experiments only (results are wrong): 1 = operands are loaded for the first item only
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -54,6 +56,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uin
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// L2 prefetch of a box (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const void* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // MN-major SWIZZLE_128B operand: 64 MN elements (128 B) per K row, 8-row groups every `sbo` bytes, 64-wide MN blocks
@@ -516,6 +524,24 @@ constexpr int PP_STAGE_BYTES = 128 * VA_D * 2;                 // 22528
 constexpr int PP_SMEM_TOTAL = PP_SMEM_STAGE + PP_STAGE_BYTES + 1024;   // + alignment slack
 constexpr int PP_BLK0_BYTES = PP_KEYS0 * 128;                  // one d block of key block 0
 constexpr int PP_BLK1_BYTES = (272 - PP_KEYS0) * 128;
+// Split-row form (HALVES = 2, the default): every query row is shared by TWO threads of two different warpgroups (same
+// TMEM lane quarter), half A owning the low score columns of a key block and half B the high ones, so each softmax phase
+// of the serial S -> softmax -> P V chain takes about half as long:
+//   key block 0 (144 columns): A [0,80)  -> P columns [0,40)     B [80,144) -> P columns [80,112)
+//   key block 1 (128 columns): A [0,64)  -> P columns [0,32)     B [64,128) -> P columns [64,96)   (keys 113.. masked)
+// (every half writes its bf16 P behind its own read position, so the two halves never touch each other's columns; the
+// MMA issuer picks the P column of each 16-key step accordingly).  Row maxima are exchanged through shared memory
+// (float [tile][half][128], one named barrier per tile), the two partial row sums through two spare TMEM columns per tile
+// (ordered by the P-published -> P V committed mbarrier chain), the epilogue is split by d columns (A [0,40), B [40,88)).
+constexpr int PP_SPLIT0 = 80, PP_SPLIT1 = 64;
+constexpr uint32_t PP_COL_L = 480;                             // fp32 partial row sums: column 480 + 2*tile + half
+constexpr int PP2_THREADS = 640;                               // 4 service warps + 4 softmax warpgroups
+constexpr int PP2_SMEM_XMAX = PP_SMEM_BAR + 192;               // float [2 tiles][2 halves][128]
+constexpr int PP2_SMEM_CLS = PP2_SMEM_XMAX + 2048;             // float [2][144] scores + [2][100] exchange = 1952 B
+constexpr int PP2_SMEM_STAGE = (PP2_SMEM_CLS + 1952 + 127) / 128 * 128;
+// the dynamic shared memory base is 1024-byte aligned in practice; the kernel traps if it is not even 128-byte aligned
+constexpr int PP2_SMEM_TOTAL = PP2_SMEM_STAGE + PP_STAGE_BYTES + 896;
+static_assert(PP2_SMEM_TOTAL <= 227 * 1024, "shared memory budget (split-row ping-pong kernel)");
 
 template <int OFF, int NREG>
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[NREG]) {
@@ -548,6 +574,50 @@ __device__ __forceinline__ float pp_row_max(uint32_t s_addr) {
     if (j + 3 < NVALID) m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// Row max of the first NVALID of NCOLS (64 or 80) fp32 score columns at `s_addr` (split-row form: at most 64 score
+// registers live, the thread budget is 96).
+template <int NCOLS, int NVALID>
+__device__ __forceinline__ float pp_row_max_part(uint32_t s_addr) {
+  static_assert(NCOLS == 64 || NCOLS == 80, "column counts of the row halves");
+  uint32_t v[32], w[32];
+  tmem_ld32<0>(s_addr, v);
+  tmem_ld32<0>(s_addr + 32, w);
+  tmem_ld_wait();
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    if (j < NVALID) m0 = fmaxf(m0, __uint_as_float(v[j]));
+    if (j + 1 < NVALID) m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+    if (j + 2 < NVALID) m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+    if (j + 3 < NVALID) m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+  }
+  if (NCOLS == 80) tmem_ld16<0>(s_addr + 64, v);
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    if (32 + j < NVALID) m0 = fmaxf(m0, __uint_as_float(w[j]));
+    if (32 + j + 1 < NVALID) m1 = fmaxf(m1, __uint_as_float(w[j + 1]));
+    if (32 + j + 2 < NVALID) m2 = fmaxf(m2, __uint_as_float(w[j + 2]));
+    if (32 + j + 3 < NVALID) m3 = fmaxf(m3, __uint_as_float(w[j + 3]));
+  }
+  if (NCOLS == 80) {
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      if (64 + j < NVALID) m0 = fmaxf(m0, __uint_as_float(v[j]));
+      if (64 + j + 1 < NVALID) m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+      if (64 + j + 2 < NVALID) m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+      if (64 + j + 3 < NVALID) m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr));
 }
 
 // 16 score columns -> 8 packed bf16 probability registers; staged (fma, ex2, add/pack) so the MUFU pipe is fed back to
@@ -597,6 +667,94 @@ __device__ __forceinline__ float pp_exp_block(uint32_t s_addr, float sl2, float 
     tmem_ld_wait();
     pp_exp16<TAIL>(cur, sl2, negm, la, lb);
     tmem_st8<0>(s_addr + NFULL * 8, cur);
+  }
+  return (la.x + la.y) + (lb.x + lb.y);
+}
+
+// ---- software-pipelined form of pass 2.  In pp_exp_block a chunk's 16 MUFU.EX2 (8 issue cycles each on the SMSP: 128
+// clk) are followed by its adds / packs / TMEM store and the next chunk's scaling, all of which depend on -- or feed --
+// them, and the warp is alone on its SMSP during its softmax phase: measured 217-240 clk per chunk, MUFU idle 45 % of
+// the phase.  Here the three stages of three different chunks sit in ONE basic block, mutually independent:
+//   pack + store of chunk c-1   |   ex2 of chunk c   |   wait + scale of chunk c+1, load of chunk c+2
+// so the scheduler can keep the MUFU pipe fed.  Chunks alternate between two register sets (rolled loop over pairs).
+__device__ __forceinline__ void pp_scale16(const uint32_t (&raw)[16], float2 (&x)[8], float sl2, float negm) {
+  const float2 s2 = make_float2(sl2, sl2), m2 = make_float2(negm, negm);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = __ffma2_rn(make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1])), s2, m2);
+}
+#ifndef TGB_EXP_EXPERIMENT
+#define TGB_EXP_EXPERIMENT 0
+#endif
+template <int NV>
+__device__ __forceinline__ void pp_ex2_16(float2 (&x)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#if TGB_EXP_EXPERIMENT == 1      // timing experiment: no MUFU
+    x[j].x = (2 * j < NV) ? x[j].x * 0.001f : 0.f;
+    x[j].y = (2 * j + 1 < NV) ? x[j].y * 0.001f : 0.f;
+#else
+    x[j].x = (2 * j < NV) ? ex2_approx(x[j].x) : 0.f;
+    x[j].y = (2 * j + 1 < NV) ? ex2_approx(x[j].y) : 0.f;
+#endif
+  }
+}
+__device__ __forceinline__ uint32_t pp_pack2(float lo, float hi) {
+#if TGB_EXP_EXPERIMENT == 2      // timing experiment: truncating pack on the ALU pipe (PRMT) instead of F2FP
+  return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+#else
+  return pack_bf16(lo, hi);
+#endif
+}
+__device__ __forceinline__ void pp_pack_store16(const float2 (&e)[8], uint32_t p_addr, float2& la, float2& lb) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {                 // same summation order as pp_exp16
+    la = __fadd2_rn(la, e[j]);
+    lb = __fadd2_rn(lb, e[j + 1]);
+    pk[j] = pp_pack2(e[j].x, e[j].y);
+    pk[j + 1] = pp_pack2(e[j + 1].x, e[j + 1].y);
+  }
+  tmem_st8<0>(p_addr, pk);
+}
+// one pipeline step: chunk c is scaled in `cur`; `prev` holds the exponentials of chunk c-1 (HAVE_PREV) and receives the
+// scaled chunk c+1 (have_next); `raw` is the in-flight load of chunk c+1, re-issued for chunk c+2 (have_next2).
+template <int NV, bool HAVE_PREV>
+__device__ __forceinline__ void pp_sp_step(uint32_t s_addr, int c, float2 (&cur)[8], float2 (&prev)[8], uint32_t (&raw)[16],
+                                           bool have_next, bool have_next2, float sl2, float negm, float2& la, float2& lb) {
+  if (HAVE_PREV) pp_pack_store16(prev, s_addr + (c - 1) * 8, la, lb);
+  pp_ex2_16<NV>(cur);
+  if (have_next) {
+    tmem_ld_wait_dep(raw);
+    pp_scale16(raw, prev, sl2, negm);
+    if (have_next2) tmem_ld16<0>(s_addr + (c + 2) * 16, raw);
+  }
+}
+// NCHUNK 16-column chunks, the last one with TAILV (1..16) valid columns.  Returns the row sum.
+template <int NCHUNK, int TAILV>
+__device__ __forceinline__ float pp_exp_block_sp(uint32_t s_addr, float sl2, float negm) {
+  static_assert(NCHUNK >= 3 && TAILV >= 1 && TAILV <= 16, "pipeline shape");
+  float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+  uint32_t raw[16];
+  float2 xa[8], xb[8];
+  tmem_ld16<0>(s_addr, raw);
+  tmem_ld_wait_dep(raw);
+  pp_scale16(raw, xa, sl2, negm);
+  tmem_ld16<0>(s_addr + 16, raw);
+  pp_sp_step<16, false>(s_addr, 0, xa, xb, raw, true, true, sl2, negm, la, lb);        // chunk 0 (xa); chunk 1 -> xb
+  constexpr int MID = NCHUNK - 2;                                                      // chunks 1 .. NCHUNK-2, all full
+  int c = 1;
+#pragma unroll 1
+  for (int k = 0; k < MID / 2; ++k, c += 2) {
+    pp_sp_step<16, true>(s_addr, c, xb, xa, raw, true, true, sl2, negm, la, lb);
+    pp_sp_step<16, true>(s_addr, c + 1, xa, xb, raw, true, c + 3 < NCHUNK, sl2, negm, la, lb);
+  }
+  if (MID & 1) {
+    pp_sp_step<16, true>(s_addr, NCHUNK - 2, xb, xa, raw, true, false, sl2, negm, la, lb);
+    pp_sp_step<TAILV, true>(s_addr, NCHUNK - 1, xa, xb, raw, false, false, sl2, negm, la, lb);
+    pp_pack_store16(xa, s_addr + (NCHUNK - 1) * 8, la, lb);
+  } else {
+    pp_sp_step<TAILV, true>(s_addr, NCHUNK - 1, xb, xa, raw, false, false, sl2, negm, la, lb);
+    pp_pack_store16(xb, s_addr + (NCHUNK - 1) * 8, la, lb);
   }
   return (la.x + la.y) + (lb.x + lb.y);
 }
@@ -767,10 +925,13 @@ __device__ __forceinline__ void cls_row_block(const VitAttnParams& p, int w, int
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(VA_THREADS, 1)
+template <int HALVES, bool SP>
+__global__ void __launch_bounds__(HALVES == 1 ? VA_THREADS : PP2_THREADS, 1)
 vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __grid_constant__ CUtensorMap tmap128,
                         const __grid_constant__ CUtensorMap tmap_out, const VitAttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  static_assert(HALVES == 1 || HALVES == 2, "threads per query row");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (HALVES == 2 && (smem_u32(smem_raw) & 127u) != 0) __trap();      // PP2_SMEM_TOTAL carries 896 bytes of alignment slack
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + PP_SMEM_Q;
   uint8_t* sK = smem + PP_SMEM_K;
@@ -789,8 +950,9 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
   uint64_t* stage_free = bars + 20; // the output staging tile has been read by its TMA store (one completion per use)
   uint64_t* stage_ready = bars + 21; // ... has been written by a softmax warpgroup (128 arrivals per use)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-  float* cls_scores = reinterpret_cast<float*>(smem + PP_SMEM_CLS);
-  uint8_t* stage = smem + PP_SMEM_STAGE;
+  float* cls_scores = reinterpret_cast<float*>(smem + (HALVES == 1 ? PP_SMEM_CLS : PP2_SMEM_CLS));
+  uint8_t* stage = smem + (HALVES == 1 ? PP_SMEM_STAGE : PP2_SMEM_STAGE);
+  float* xmax = reinterpret_cast<float*>(smem + PP2_SMEM_XMAX);   // (HALVES == 2 only) [tile][half][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -800,13 +962,13 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
     tma_prefetch_desc(&tmap128);
     tma_prefetch_desc(&tmap_out);
     mbar_init(stage_free, 1);
-    mbar_init(stage_ready, 128);
+    mbar_init(stage_ready, 128 * HALVES);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1); mbar_init(&q_free[t], 1);
       mbar_init(&k_full[t], 1); mbar_init(&k_free[t], 2);      // tcgen05.commit + the CLS warp of the item
       mbar_init(&v_full[t], 1); mbar_init(&v_free[t], 2);
-      mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128);
-      mbar_init(&o_full[t], 1); mbar_init(&o_free[t], 128);
+      mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 128 * HALVES);
+      mbar_init(&o_full[t], 1); mbar_init(&o_free[t], 128 * HALVES);
     }
     fence_mbar_init();
   }
@@ -840,7 +1002,9 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         const int b = w / VA_H, h = w - b * VA_H;
         const int row0 = b * VA_S;
         const uint32_t ph = i & 1;
+        const bool skip_loads = (p.dbg & 1) && i > 1;
         auto load_kv = [&](uint8_t* dst, uint64_t* full, int blk, int col_h) {
+          if (skip_loads) { mbar_arrive(full); return; }
           mbar_arrive_expect_tx(full, 2 * (blk == 0 ? PP_BLK0_BYTES : PP_BLK1_BYTES));
 #pragma unroll
           for (int db = 0; db < 2; ++db)
@@ -850,6 +1014,7 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         auto load_q = [&](int t) {
           mbar_wait(&q_free[t], ph ^ 1);
           TRACE(0, i * 100 + 2 + t);                             // Q_t load issued
+          if (skip_loads) { mbar_arrive(&q_full[t]); return; }
           mbar_arrive_expect_tx(&q_full[t], 2 * PP_Q_BYTES);
 #pragma unroll
           for (int db = 0; db < 2; ++db)
@@ -859,6 +1024,22 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         TRACE(0, i * 100 + 1);                                   // K block 0 load issued
         load_kv(sK, &k_full[0], 0, VA_H + h);
         load_q(0);
+        if (HALVES == 2 && p.l2_prefetch && w + (int)gridDim.x < p.num_items) {
+          // The loads of an item are issued as the previous item frees their buffers, i.e. at most one softmax phase
+          // before they are needed, and a load from DRAM takes 3-6k clk (176-byte pieces at an 8 448-byte stride): pull
+          // the NEXT item's operands into the L2 now, so that its loads are L2 hits.
+          const int wn = w + (int)gridDim.x;
+          const int bn = wn / VA_H, hn = wn - bn * VA_H, rown = bn * VA_S;
+#pragma unroll
+          for (int db = 0; db < 2; ++db) {
+            tma_prefetch_3d(&tmap144, db * 64, VA_H + hn, rown);
+            tma_prefetch_3d(&tmap128, db * 64, hn, rown + 1);
+            tma_prefetch_3d(&tmap128, db * 64, hn, rown + 129);
+            tma_prefetch_3d(&tmap144, db * 64, 2 * VA_H + hn, rown);
+            tma_prefetch_3d(&tmap128, db * 64, VA_H + hn, rown + PP_KEYS0);
+            tma_prefetch_3d(&tmap128, db * 64, 2 * VA_H + hn, rown + PP_KEYS0);
+          }
+        }
         mbar_wait(&v_free[0], ph ^ 1);
         TRACE(0, i * 100 + 4);                                   // V block 0 load issued
         load_kv(sV, &v_full[0], 0, 2 * VA_H + h);
@@ -910,7 +1091,12 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         const int kk0 = blk == 0 ? 0 : PP_KEYS0 / 16, kk1 = blk == 0 ? PP_KEYS0 / 16 : 17;
         for (int kk = kk0; kk < kk1; ++kk) {
           const uint64_t db = umma_desc_mn_sw128(v_addr + kk * 2048, VA_KBLK_BYTES, 1024);
-          umma_bf16_ts(d, a + (kk - kk0) * 8, db, idesc_pv, (blk > 0 || kk > kk0) ? 1u : 0u);
+          uint32_t pcol = (kk - kk0) * 8;                        // bf16 P of 16 keys = 8 columns
+          if (HALVES == 2) {                                     // half B's P sits behind ITS score columns
+            const int split = (blk == 0 ? PP_SPLIT0 : PP_SPLIT1) / 16;
+            if (kk - kk0 >= split) pcol = (blk == 0 ? PP_SPLIT0 : PP_SPLIT1) + (kk - kk0 - split) * 8;
+          }
+          umma_bf16_ts(d, a + pcol, db, idesc_pv, (blk > 0 || kk > kk0) ? 1u : 0u);
         }
       };
       int i = 0;
@@ -979,20 +1165,32 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
     // memory reads are cheap: ~68 B/clk per warp), exponentiates and writes the packed bf16 P chunk behind the read
     // position (P aliases the first half of S).  Each tcgen05.ld is issued one chunk ahead of its use; at most two
     // chunks are live, so nothing spills.
-    const int t = (warp - 4) >> 2;               // query tile of this warpgroup
+    const int half = (HALVES == 2 && warp >= 12) ? 1 : 0;   // which columns of the row this thread owns (split-row form)
+    const int t = ((warp - 4) & 7) >> 2;         // query tile of this warpgroup (warps 4-7 / 12-15: tile 0, 8-11 / 16-19: tile 1)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t s_addr = lane_base + PP_COL_S + t * PP_S_STRIDE;
     const uint32_t o_addr = lane_base + PP_COL_O + t * PP_O_STRIDE;
+    const uint32_t l_addr = lane_base + PP_COL_L + 2 * t;
+    float* xm_mine = xmax + t * 256 + half * 128 + row;
+    const float* xm_other = xmax + t * 256 + (half ^ 1) * 128 + row;
     const float sl2 = p.scale_log2;
     TRACE_DECL
 #ifdef TGB_ATTN_TRACE
-    const bool tr_on = (quarter == 0 && lane == 0);
+    const bool tr_on = (quarter == 0 && lane == 0 && half == 0);
 #define STRACE(tag) do { if (tr_on) TRACE(4 + t, tag); } while (0)
 #else
 #define STRACE(tag) do { } while (0)
 #endif
+    // row max over both halves of the row: own part -> shared memory -> the tile's named barrier -> the other part.
+    // One slot per (tile, half, row) is enough: between two uses of a slot lies an mbarrier chain through the MMA
+    // thread (the reader's P-published arrival -> the next S of this tile -> the writer's wait on it).
+    auto merged_max = [&](float part) -> float {
+      *xm_mine = part;
+      named_bar_sync(4 + t, 256);
+      return fmaxf(part, *xm_other);
+    };
     int i = 0;
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
       float mx, l;
@@ -1001,9 +1199,19 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         mbar_wait(&s_full[t], 0);
         STRACE(i * 100 + 40);                                    // S(t,0) seen
         tc_fence_after();
-        mx = pp_row_max<PP_KEYS0, PP_KEYS0>(s_addr) * sl2;
+        if (HALVES == 1) mx = pp_row_max<PP_KEYS0, PP_KEYS0>(s_addr) * sl2;
+        else if (half == 0) mx = merged_max(pp_row_max_part<PP_SPLIT0, PP_SPLIT0>(s_addr)) * sl2;
+        else mx = merged_max(pp_row_max_part<PP_KEYS0 - PP_SPLIT0, PP_KEYS0 - PP_SPLIT0>(s_addr + PP_SPLIT0)) * sl2;
         STRACE(i * 100 + 41);                                    // row max known
-        l = pp_exp_block<PP_KEYS0 / 16 - 1, 16>(s_addr, sl2, -mx);
+        if constexpr (SP) {
+          if (HALVES == 1) l = pp_exp_block_sp<PP_KEYS0 / 16, 16>(s_addr, sl2, -mx);
+          else if (half == 0) l = pp_exp_block_sp<PP_SPLIT0 / 16, 16>(s_addr, sl2, -mx);
+          else l = pp_exp_block_sp<(PP_KEYS0 - PP_SPLIT0) / 16, 16>(s_addr + PP_SPLIT0, sl2, -mx);
+        } else {
+          if (HALVES == 1) l = pp_exp_block<PP_KEYS0 / 16 - 1, 16>(s_addr, sl2, -mx);
+          else if (half == 0) l = pp_exp_block<PP_SPLIT0 / 16 - 1, 16>(s_addr, sl2, -mx);
+          else l = pp_exp_block<(PP_KEYS0 - PP_SPLIT0) / 16 - 1, 16>(s_addr + PP_SPLIT0, sl2, -mx);
+        }
         STRACE(i * 100 + 42);                                    // exponentials done
         tmem_st_wait();
         tc_fence_before();
@@ -1015,18 +1223,22 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         mbar_wait(&s_full[t], 1);                                 // also implies P V of block 0 has completed
         STRACE(i * 100 + 50);                                    // S(t,1) seen
         tc_fence_after();
-        const float m1x = pp_row_max<128, PP_VALID1>(s_addr) * sl2;
+        float m1x;
+        if (HALVES == 1) m1x = pp_row_max<128, PP_VALID1>(s_addr) * sl2;
+        else if (half == 0) m1x = merged_max(pp_row_max_part<PP_SPLIT1, PP_SPLIT1>(s_addr)) * sl2;
+        else m1x = merged_max(pp_row_max_part<128 - PP_SPLIT1, PP_VALID1 - PP_SPLIT1>(s_addr + PP_SPLIT1)) * sl2;
         STRACE(i * 100 + 51);
         float f = 1.f;
-        const bool need = m1x > mx + PP_RESCALE_THRESHOLD;
+        const bool need = m1x > mx + PP_RESCALE_THRESHOLD;       // (same decision in both halves of a row: same operands)
         if (need) {
           f = ex2_approx(mx - m1x);
           mx = m1x;
           l *= f;
         }
         if (__any_sync(0xffffffffu, need)) {                     // rare: rescale this warp's 32 rows of O_t in place
+          const int c0 = (HALVES == 2 && half == 1) ? 48 : 0, c1 = (HALVES == 2 && half == 0) ? 48 : 96;
 #pragma unroll 1
-          for (int c = 0; c < 96; c += 8) {
+          for (int c = c0; c < c1; c += 8) {
             uint32_t o[8];
             tmem_ld8<0>(o_addr + c, o);
             tmem_ld_wait();
@@ -1036,7 +1248,17 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
           }
           tmem_st_wait();
         }
-        l += pp_exp_block<PP_VALID1 / 16, PP_VALID1 % 16>(s_addr, sl2, -mx);
+        static_assert(PP_VALID1 % 16 != 0 && (PP_VALID1 - PP_SPLIT1) % 16 != 0, "the last chunk of key block 1 is partial");
+        if constexpr (SP) {
+          if (HALVES == 1) l += pp_exp_block_sp<PP_VALID1 / 16 + 1, PP_VALID1 % 16>(s_addr, sl2, -mx);
+          else if (half == 0) l += pp_exp_block_sp<PP_SPLIT1 / 16, 16>(s_addr, sl2, -mx);
+          else l += pp_exp_block_sp<(PP_VALID1 - PP_SPLIT1) / 16 + 1, (PP_VALID1 - PP_SPLIT1) % 16>(s_addr + PP_SPLIT1, sl2, -mx);
+        } else {
+          if (HALVES == 1) l += pp_exp_block<PP_VALID1 / 16, PP_VALID1 % 16>(s_addr, sl2, -mx);
+          else if (half == 0) l += pp_exp_block<PP_SPLIT1 / 16 - 1, 16>(s_addr, sl2, -mx);
+          else l += pp_exp_block<(PP_VALID1 - PP_SPLIT1) / 16, (PP_VALID1 - PP_SPLIT1) % 16>(s_addr + PP_SPLIT1, sl2, -mx);
+        }
+        if (HALVES == 2) tmem_st1(l_addr + half, __float_as_uint(l));   // this half's partial row sum
         STRACE(i * 100 + 52);
         tmem_st_wait();
         tc_fence_before();
@@ -1049,34 +1271,54 @@ vit_attention_pp_kernel(const __grid_constant__ CUtensorMap tmap144, const __gri
         // memory traffic of the other warpgroup) busy for ~3k cycles; instead each thread writes its row into a dense
         // [128][88] shared tile (conflict-free: 176-byte rows) and the TMA producer thread issues an asynchronous bulk
         // tensor store (waiting for the store to drain inside this warpgroup would sit on the critical chain).
-        const float inv = 1.f / l;
         mbar_wait(&o_full[t], i & 1);
         STRACE(i * 100 + 60);                                    // O_t complete
         tc_fence_after();
-        uint32_t o[96];
-        tmem_ld32<0>(o_addr, o);
-        tmem_ld32<32>(o_addr + 32, o);
-        tmem_ld32<64>(o_addr + 64, o);
+        constexpr int NO = HALVES == 1 ? 96 : 48;                // O columns held by one thread
+        uint32_t o[NO];
+        uint32_t la = 0, lb = 0;
+        int c_first, c_count;                                    // 16-byte d chunks of the row this thread writes
+        if constexpr (HALVES == 1) {
+          tmem_ld32<0>(o_addr, o);
+          tmem_ld32<32>(o_addr + 32, o);
+          tmem_ld32<64>(o_addr + 64, o);
+          c_first = 0; c_count = 11;
+        } else {
+          tmem_ld2(l_addr, la, lb);
+          if (half == 0) {                                       // d [0,40)
+            tmem_ld32<0>(o_addr, o);
+            tmem_ld8<32>(o_addr + 32, o);
+            c_first = 0; c_count = 5;
+          } else {                                               // d [40,88)
+            tmem_ld32<0>(o_addr + 40, o);
+            tmem_ld16<32>(o_addr + 72, o);
+            c_first = 5; c_count = 6;
+          }
+        }
         tmem_ld_wait();
         STRACE(i * 100 + 61);                                    // O_t in registers
         tc_fence_before();
         mbar_arrive(&o_free[t]);
-        const int use = 2 * i + t;                               // uses of the staging tile alternate between the warpgroups
+        if (HALVES == 2) l = __uint_as_float(la) + __uint_as_float(lb);   // (A's part + B's part in both halves)
+        const float inv = 1.f / l;
+        const int use = 2 * i + t;                               // uses of the staging tile alternate between the tiles
         mbar_wait(stage_free, (use & 1) ^ 1);                    // use - 1 has been read out
-        uint4* srow = reinterpret_cast<uint4*>(stage + row * (VA_D * 2));
+        uint4* srow = reinterpret_cast<uint4*>(stage + row * (VA_D * 2)) + c_first;
 #pragma unroll
-        for (int c = 0; c < 11; ++c) {                           // 88 valid d columns = 11 x 16 bytes
-          const float2 i2 = make_float2(inv, inv);              // packed fp32 multiplies (FMUL2)
-          const float2 a = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 0]), __uint_as_float(o[8 * c + 1])), i2);
-          const float2 b = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 2]), __uint_as_float(o[8 * c + 3])), i2);
-          const float2 d = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 4]), __uint_as_float(o[8 * c + 5])), i2);
-          const float2 e = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 6]), __uint_as_float(o[8 * c + 7])), i2);
-          uint4 v;
-          v.x = pack_bf16(a.x, a.y);
-          v.y = pack_bf16(b.x, b.y);
-          v.z = pack_bf16(d.x, d.y);
-          v.w = pack_bf16(e.x, e.y);
-          srow[c] = v;
+        for (int c = 0; c < (HALVES == 1 ? 11 : 6); ++c) {       // 88 valid d columns = 11 x 16 bytes
+          if (c < c_count) {
+            const float2 i2 = make_float2(inv, inv);            // packed fp32 multiplies (FMUL2)
+            const float2 a = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 0]), __uint_as_float(o[8 * c + 1])), i2);
+            const float2 b = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 2]), __uint_as_float(o[8 * c + 3])), i2);
+            const float2 d = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 4]), __uint_as_float(o[8 * c + 5])), i2);
+            const float2 e = __fmul2_rn(make_float2(__uint_as_float(o[8 * c + 6]), __uint_as_float(o[8 * c + 7])), i2);
+            uint4 v;
+            v.x = pack_bf16(a.x, a.y);
+            v.y = pack_bf16(b.x, b.y);
+            v.z = pack_bf16(d.x, d.y);
+            v.w = pack_bf16(e.x, e.y);
+            srow[c] = v;
+          }
         }
         fence_proxy_async();                                     // generic-proxy writes -> visible to the TMA (async proxy)
         mbar_arrive(stage_ready);                                // the TMA producer thread issues the bulk store
@@ -2387,8 +2629,19 @@ extern "C" __attribute__((visibility("default"))) int tgb_debug_attn_trace(long 
 
 static std::atomic<int> g_vit_attention_variant{0};   // 0 = ping-pong kernel (default), 1 = one-shot, 2 = three-block (cross-checks)
 
+static std::atomic<int> g_vit_attention_dbg{0};
+extern "C" __attribute__((visibility("default"))) int tgb_debug_vit_attention_dbg(int bits) {
+  g_vit_attention_dbg = bits;
+  return TGB_OK;
+}
+static std::atomic<int> g_vit_attention_prefetch{0};   // measured 30 % slower with it (profiles/r2_attention_experiments.txt)
+extern "C" int tgb_vit_attention_set_prefetch(int on) {
+  g_vit_attention_prefetch = on ? 1 : 0;
+  return TGB_OK;
+}
+
 extern "C" int tgb_vit_attention_set_variant(int variant) {
-  TGB_CHECK_ARG(variant >= 0 && variant <= 3, "vit_attention_set_variant: 0 (ping-pong), 1 (one-shot), 2 (three-block) or 3 (CTA pair)");
+  TGB_CHECK_ARG(variant >= 0 && variant <= 5, "vit_attention_set_variant: 0 (ping-pong), 1 (one-shot), 2 (three-block), 3 (CTA pair), 4 (split-row ping-pong) or 5 (ping-pong, pipelined softmax)");
   g_vit_attention_variant = variant;
   return TGB_OK;
 }
@@ -2415,7 +2668,8 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   CUtensorMap* maps[7] = {&map128, &map96, &map80, &map144, &map, &map72, &map64};
   const cuuint32_t box_rows[7] = {128, P3_KB, P3_KB2, PP_KEYS0, VA_BOX_ROWS, C2_HALF0, C2_HALF1};
   // tensor maps each variant reads: ping-pong 128 144 | one-shot 136 | three-block 128 96 80 | pair 128 136 72 64
-  static const unsigned char needs[4][7] = {{1, 0, 0, 1, 0, 0, 0}, {0, 0, 0, 0, 1, 0, 0}, {1, 1, 1, 0, 0, 0, 0}, {1, 0, 0, 0, 1, 1, 1}};
+  static const unsigned char needs[6][7] = {{1, 0, 0, 1, 0, 0, 0}, {0, 0, 0, 0, 1, 0, 0}, {1, 1, 1, 0, 0, 0, 0}, {1, 0, 0, 0, 1, 1, 1},
+                                            {1, 0, 0, 1, 0, 0, 0}, {1, 0, 0, 1, 0, 0, 0}};
   for (int i = 0; i < 7; ++i) {
     if (!needs[variant][i]) continue;
     cuuint32_t box[3] = {64, 1, box_rows[i]};
@@ -2442,7 +2696,9 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   }
   TGB_ONCE_PER_DEVICE({
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM_TOTAL));
-    TGB_CUDA(cudaFuncSetAttribute(vit_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_TOTAL));
+    TGB_CUDA(cudaFuncSetAttribute(vit_attention_pp_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_TOTAL));
+    TGB_CUDA(cudaFuncSetAttribute(vit_attention_pp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_TOTAL));
+    TGB_CUDA(cudaFuncSetAttribute(vit_attention_pp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP2_SMEM_TOTAL));
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM_TOTAL));
     TGB_CUDA(cudaFuncSetAttribute(vit_attention_c2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_TOTAL));
   });
@@ -2454,6 +2710,8 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
   p.frames = frames;
   p.num_items = frames * VA_H;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.l2_prefetch = g_vit_attention_prefetch.load();
+  p.dbg = g_vit_attention_dbg.load();
   const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
   if (variant == 3) {
     const int pairs = sm_count() / 2;
@@ -2463,8 +2721,12 @@ extern "C" int tgb_vit_attention_bf16(const void* qkv, int64_t ld_qkv, void* out
     vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM_TOTAL, (cudaStream_t)stream>>>(map, p);
   else if (variant == 2)
     vit_attention_p3_kernel<<<grid, P3_THREADS, P3_SMEM_TOTAL, (cudaStream_t)stream>>>(map96, map80, map128, map_out, p);
+  else if (variant == 4)
+    vit_attention_pp_kernel<2, true><<<grid, PP2_THREADS, PP2_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, map_out, p);
+  else if (variant == 5)
+    vit_attention_pp_kernel<1, true><<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, map_out, p);
   else
-    vit_attention_pp_kernel<<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, map_out, p);
+    vit_attention_pp_kernel<1, false><<<grid, VA_THREADS, PP_SMEM_TOTAL, (cudaStream_t)stream>>>(map144, map128, map_out, p);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }

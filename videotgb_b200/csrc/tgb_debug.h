@@ -24,8 +24,11 @@ TGB_API int tgb_gemm_set_schedule(int mode);
 /* epilogue warps per CTA, 0 = choose (8; the fp32-residual epilogues always run 8). */
 TGB_API int tgb_gemm_set_epilogue_warps(int warps);
 /* 0 = ping-pong kernel (default), 1 = one-shot kernel (whole score row in tensor memory), 2 = three-block kernel,
- * 3 = CTA-pair kernel (cta_group::2). */
+ * 3 = CTA-pair kernel (cta_group::2), 4 = split-row ping-pong kernel (two threads per query row), 5 = ping-pong kernel
+ * with the software-pipelined exp pass.  Measurements: profiles/r2_attention_experiments.txt. */
 TGB_API int tgb_vit_attention_set_variant(int variant);
+/* split-row kernel: 1 = prefetch the next item's operands into the L2 (measured 30 % slower), 0 = off (default). */
+TGB_API int tgb_vit_attention_set_prefetch(int on);
 
 #ifdef __cplusplus
 }
