@@ -317,7 +317,7 @@ def test_gemm_bias_bf16(m, n, k, bn, cta_group):
     assert _cos(got, want) > 0.9999
 
 
-def test_gemm_epilogues(cta_group):
+def test_gemm_epilogues(cta_group, resid_piece):
     g = torch.Generator().manual_seed(99)
     m, n, k = 777, 1408, 1408
     a = torch.randn(m, k, generator=g).to(torch.bfloat16)
@@ -360,8 +360,16 @@ def test_gemm_epilogues(cta_group):
 
 # LayerNorm folded into the GEMMs (tgb_gemm_bf16_ln): producer statistics, finalize, consumer epilogues, and the chain
 # residual-GEMM -> LN -> GEMM against torch's layer_norm in float64.
+@pytest.fixture(params=[0, 16, 32])
+def resid_piece(request):
+    """Column width of the fp32-residual epilogue's pieces: 0 = the library's choice (32 when K <= 2048), 16 / 32 forced."""
+    ops.gemm_set_resid_piece(request.param)
+    yield request.param
+    ops.gemm_set_resid_piece(0)
+
+
 @pytest.mark.parametrize("m,n,k", [(777, 1408, 1408), (257 * 2, 1408, 6144), (130, 768, 256), (64, 136, 64)])
-def test_gemm_ln_statistics_producer(m, n, k, cta_group):
+def test_gemm_ln_statistics_producer(m, n, k, cta_group, resid_piece):
     g = torch.Generator().manual_seed(m + n + k)
     a = torch.randn(m, k, generator=g).to(torch.bfloat16)
     w = (torch.randn(n, k, generator=g) * 0.03).to(torch.bfloat16)

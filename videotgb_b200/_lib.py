@@ -74,6 +74,7 @@ DEBUG_SIGNATURES = {
     "tgb_gemm_set_cta_group": ([c_int], c_int),
     "tgb_gemm_set_schedule": ([c_int], c_int),
     "tgb_gemm_set_epilogue_warps": ([c_int], c_int),
+    "tgb_gemm_set_resid_piece": ([c_int], c_int),
     "tgb_vit_attention_set_variant": ([c_int], c_int),
     "tgb_vit_attention_set_prefetch": ([c_int], c_int),
 }
@@ -100,6 +101,8 @@ def load() -> ctypes.CDLL:
     sched = {"roundrobin": 0, "balanced": 1, "rowblocks": 2}.get(os.environ.get("TGB_GEMM_SCHEDULE", ""))   # A/B knob
     if sched is not None:
         lib.tgb_gemm_set_schedule(sched)
+    if os.environ.get("TGB_GEMM_RESID_PIECE"):                                                                # A/B knob
+        lib.tgb_gemm_set_resid_piece(int(os.environ["TGB_GEMM_RESID_PIECE"]))
     if os.environ.get("TGB_ATTN_VARIANT"):                                                                    # A/B knob
         lib.tgb_vit_attention_set_variant(int(os.environ["TGB_ATTN_VARIANT"]))
     if os.environ.get("TGB_ATTN_PREFETCH"):                                                                   # A/B knob

@@ -70,17 +70,27 @@ template <int EPI> struct EpiTraits {
 //            [32 x 16] fp32 box (ring of three: loads run two pieces ahead), is updated in place and leaves by bulk
 //            tensor store, plus a bf16 copy box for the statistics-producing variant
 constexpr int FAM_BF16 = 1, FAM_RES = 2;           // (0 = FAM_T)
-constexpr int RES_BOX_BYTES = 32 * 16 * 4, RES_COPY_BYTES = 32 * 16 * 2;
+// Piece width PW (template): 16 columns = 64-byte row pieces in SWIZZLE_64B boxes, ring of three (the default), or
+// 32 columns = whole 128-byte lines per row in SWIZZLE_128B boxes, ring of two (bf16 copy: 64-byte rows, SWIZZLE_64B).
+// The wide form halves the number of bulk operations and doubles the contiguous bytes per row in DRAM; it costs one
+// operand stage (4 instead of 5).  Used for short main loops (K <= 2048: the attention projection), whose epilogue
+// traffic -- not the tensor pipe -- sets the kernel's time.
+template <int PW> struct ResCfg {
+  static_assert(PW == 16 || PW == 32, "residual piece width");
+  static constexpr int NBOX = PW == 16 ? 3 : 2;
+  static constexpr int BOX_BYTES = 32 * PW * 4;
+  static constexpr int COPY_BYTES = 32 * PW * 2;
+  static constexpr int WARP_BYTES = NBOX * BOX_BYTES + 2 * COPY_BYTES;
+};
 // residual boxes per warp: loads run RES_NBOX-1 pieces ahead.  Measured (tools/gemm_ab.py, profiles/r1_gemm_ab_nbox.txt):
 // rings of 2 / 3 / 4 boxes and an extra L2 prefetch of the tile's residual by the TMA producer all land within 2 % of
 // each other -- the residual GEMMs are bound by the power their DRAM traffic takes from the tensor cores, not by latency.
-constexpr int RES_NBOX = 3;
-constexpr int RES_WARP_BYTES = RES_NBOX * RES_BOX_BYTES + 2 * RES_COPY_BYTES;
+constexpr int RES_MAX_NBOX = 3;
 
-template <int BN, int CG, int EW, int FAM>
+template <int BN, int CG, int EW, int FAM, int PW = 16>
 struct GemmCfg {
   static constexpr int THREADS = 128 + EW * 32;
-  static constexpr int STG_BYTES = FAM == FAM_BF16 ? EW * 4096 : (FAM == FAM_RES ? EW * RES_WARP_BYTES : EW * 32 * STG_PITCH * 4);
+  static constexpr int STG_BYTES = FAM == FAM_BF16 ? EW * 4096 : (FAM == FAM_RES ? EW * ResCfg<PW>::WARP_BYTES : EW * 32 * STG_PITCH * 4);
   static constexpr int B_ROWS = BN / CG;                 // W rows staged per CTA
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
@@ -172,14 +182,17 @@ __device__ __forceinline__ void bf16_half(const GemmParams& p, const uint32_t (&
   }
 }
 
-template <int BN, int EPI, int CG, int EW>
+template <int BN, int EPI, int CG, int EW, int PW = 16>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
                          const __grid_constant__ CUtensorMap tma_c2, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::FAM>;
+  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::FAM, PW>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int STG_BYTES = Cfg::STG_BYTES;
+  constexpr int RES_NBOX = ResCfg<PW>::NBOX, RES_BOX_BYTES = ResCfg<PW>::BOX_BYTES, RES_COPY_BYTES = ResCfg<PW>::COPY_BYTES;
+  constexpr int RES_WARP_BYTES = ResCfg<PW>::WARP_BYTES;
+  static_assert(EpiTraits<EPI>::FAM == FAM_RES || PW == 16, "the piece width only exists in the fp32-residual epilogues");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -238,7 +251,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       mbar_init(&tmem_empty[s], CG * EW);  // lane 0 of every epilogue warp of every CTA of the pair
     }
     if (EpiTraits<EPI>::FAM == FAM_RES)
-      for (int s = 0; s < RES_NBOX * EW; ++s) mbar_init(&res_full[s], 1);
+      for (int s = 0; s < RES_MAX_NBOX * EW; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == W_ALLOC) tmem_alloc_cg<CG>(tmem_slot, TMEM_COLS);
@@ -407,11 +420,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     const int quarter = warp & 3;
     const int sub = warp >> 2;
     constexpr int NSUB = EW / 4;
-    constexpr int NCHUNK = BN / 16;
+    constexpr int NCHUNK = BN / PW;
     uint8_t* wbase = reinterpret_cast<uint8_t*>(staging) + warp * RES_WARP_BYTES;
     const uint32_t box0 = smem_u32(wbase);
     const uint32_t copy0 = box0 + RES_NBOX * RES_BOX_BYTES;
-    const uint32_t sw = (lane >> 1) & 3;
+    // 16-byte unit u of the lane's row sits at unit (u ^ sw): SWIZZLE_64B (64-byte rows) xors address bits [4,6) with
+    // [7,9), SWIZZLE_128B (128-byte rows) bits [4,7) with [7,10)
+    const uint32_t sw = PW == 16 ? ((lane >> 1) & 3) : (lane & 7);
+    const uint32_t sw_copy = (lane >> 1) & 3;          // PW == 32: the bf16 copy box has 64-byte rows (SWIZZLE_64B)
     uint64_t* my_full = res_full + RES_NBOX * warp;
     const bool has_bias = p.bias != nullptr;
     const uint32_t empty0 = (CG == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
@@ -423,7 +439,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
     // piece iterator: (tile, j) with j = sub, sub+NSUB, ... while the piece starts inside N
     auto piece_rows = [&](int tile) { return ((tile / p.num_n_blocks) * CG + (int)rank) * BM + quarter * 32; };
-    auto piece_col = [&](int tile, int j) { return (tile % p.num_n_blocks) * BN + j * 16; };
+    auto piece_col = [&](int tile, int j) { return (tile % p.num_n_blocks) * BN + j * PW; };
     auto next_piece = [&](int& round, int& tile, int& j) {       // advance; returns false past the end
       j += NSUB;
       if (j >= NCHUNK || piece_col(tile, j) >= p.N) {
@@ -469,11 +485,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           tc_fence_after();
         }
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
-        uint32_t v[16];
-        tmem_ld_32x32b_x16_nomem(t_row + j * 16, v);
+        uint32_t v[PW];
+        if constexpr (PW == 16) tmem_ld_32x32b_x16_nomem(t_row + j * 16, v);
+        else tmem_ld_32x32b_x32_nomem(t_row + j * 32, v);
         mbar_wait(&my_full[b], (box_phase >> b) & 1u);
         box_phase ^= 1u << b;
-        tmem_ld_wait_dep(v);
+        if constexpr (PW == 16) tmem_ld_wait_dep(v);
+        else tmem_ld_wait_dep32(v);
         const bool tile_done = !more || ntile != tile;
         if (tile_done) {     // that was this warp's last read of the accumulator: hand it back before the math and the stores
           tc_fence_before();
@@ -483,10 +501,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
             else mbar_arrive_cluster_relaxed(acc == 0 ? empty0 : empty1);
           }
         }
-        const uint32_t my_box = box0 + b * RES_BOX_BYTES + lane * 64;
-        uint32_t pk[8];
+        const uint32_t my_box = box0 + b * RES_BOX_BYTES + lane * (PW * 4);
+        uint32_t pk[PW / 2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < PW / 4; ++u) {
           const uint32_t addr = my_box + ((u ^ sw) << 4);
           float4 r;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
@@ -508,9 +526,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           }
         }
         if (T::STATS) {
-          const uint32_t my_copy = copy0 + (n & 1) * RES_COPY_BYTES + lane * 32;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_copy), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_copy + 16), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+          const uint32_t my_copy = copy0 + (n & 1) * RES_COPY_BYTES + lane * (PW * 2);
+#pragma unroll
+          for (int w = 0; w < PW / 8; ++w) {            // 16-byte units of the bf16 row (32-byte rows are not swizzled)
+            const uint32_t addr = my_copy + ((PW == 16 ? (uint32_t)w : ((uint32_t)w ^ sw_copy)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * w]), "r"(pk[4 * w + 1]), "r"(pk[4 * w + 2]), "r"(pk[4 * w + 3]) : "memory");
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -732,7 +753,7 @@ static int make_tmap_out(CUtensorMap* map, const void* base, long long rows, lon
 }
 
 // the fp32 residual epilogue's boxes: [32 rows x 16 columns], fp32 (SWIZZLE_64B) or bf16 copy (32-byte rows, no swizzle)
-static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, bool f32) {
+static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, bool f32, int pw = 16) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
@@ -740,11 +761,13 @@ static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, l
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (f32 ? 4 : 2)};
-  cuuint32_t box[2] = {16u, 32u};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(pw), 32u};
   cuuint32_t estr[2] = {1, 1};
+  const int row_bytes = pw * (f32 ? 4 : 2);           // 32 -> no swizzle, 64 -> SWIZZLE_64B, 128 -> SWIZZLE_128B
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
   CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
-                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled (residual box) failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
@@ -796,6 +819,7 @@ static int balanced_shift(int clusters, int m_blocks, int n_blocks, bool half_la
 static std::atomic<int> g_force_cg{0};     // 0 = choose, 1 / 2 = force (tests exercise both paths)
 
 static std::atomic<int> g_force_ew{0};     // 0 = choose per epilogue, 8 / 16 = force
+static std::atomic<int> g_force_resid_piece{0};   // 0 = choose by K, 16 / 32 = force the residual piece width (A/B knob)
 // 1 = balanced tile schedule (default); 0 = plain round-robin; 2 = row-block schedule when M fills whole rounds of row
 // blocks, else 1 (A/B knob).  Measured (tools/gemm_ab.py, profiles/r2_gemm_ab_rowblocks.txt): the row-block schedule
 // removes the A re-reads between clusters but puts 74 A row blocks (230 MB for K = 6144) in flight at once, more than the
@@ -810,9 +834,9 @@ static bool row_block_schedule_ok(int clusters, int m_blocks) {
   return (long long)m_blocks * 100 >= passes * clusters * 97;
 }
 
-template <int BN, int EPI, int CG, int EW>
+template <int BN, int EPI, int CG, int EW, int PW = 16>
 static int launch_gemm_ew(const void* A, long long lda, const void* W, long long ldw, GemmParams p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::FAM>;
+  using Cfg = GemmCfg<BN, CG, EW, EpiTraits<EPI>::FAM, PW>;
   p.num_m_blocks = (p.M + BM * CG - 1) / (BM * CG);
   p.num_n_blocks = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
@@ -827,16 +851,16 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
     if (st != TGB_OK) return st;
   }
   if (EpiTraits<EPI>::RESID) {
-    st = make_tmap_box16(&tc, p.out, p.M, p.N, p.ldo, true);
+    st = make_tmap_box16(&tc, p.out, p.M, p.N, p.ldo, true, PW);
     if (st != TGB_OK) return st;
-    st = make_tmap_box16(&tr, p.resid, p.M, p.N, p.ldr, true);
+    st = make_tmap_box16(&tr, p.resid, p.M, p.N, p.ldr, true, PW);
     if (st != TGB_OK) return st;
     if (EpiTraits<EPI>::STATS) {
-      st = make_tmap_box16(&tc2, p.out2, p.M, p.N, p.ldo2, false);
+      st = make_tmap_box16(&tc2, p.out2, p.M, p.N, p.ldo2, false, PW);
       if (st != TGB_OK) return st;
     }
   }
-  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, EW>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, EW, PW>;
   TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_clusters = sm_count() / CG;
@@ -867,10 +891,18 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
   // warps and the extra pipeline stage than with 16)
   const int force_ew = g_force_ew.load();
   int ew = force_ew ? force_ew : 8;
-  if (EpiTraits<EPI>::RESID) ew = 8;           // two double-buffered residual boxes per warp; the statistics slot layout
-                                               // (2 per 256-column tile) is fixed
-  if (ew == 16) return launch_gemm_ew<BN, EPI, CG, 16>(A, lda, W, ldw, p, stream);
-  return launch_gemm_ew<BN, EPI, CG, 8>(A, lda, W, ldw, p, stream);
+  if constexpr (EpiTraits<EPI>::RESID) {       // 8 epilogue warps: the statistics slot layout (2 per 256-column tile) is fixed
+    // wide residual pieces (whole 128-byte lines) for short main loops, where the epilogue traffic sets the time
+    const int force_pw = g_force_resid_piece.load();
+    const int pw = force_pw ? force_pw : (p.K <= 2048 ? 32 : 16);
+    if constexpr (BN == 256) {
+      if (pw == 32) return launch_gemm_ew<BN, EPI, CG, 8, 32>(A, lda, W, ldw, p, stream);
+    }
+    return launch_gemm_ew<BN, EPI, CG, 8, 16>(A, lda, W, ldw, p, stream);
+  } else {
+    if (ew == 16) return launch_gemm_ew<BN, EPI, CG, 16>(A, lda, W, ldw, p, stream);
+    return launch_gemm_ew<BN, EPI, CG, 8>(A, lda, W, ldw, p, stream);
+  }
 }
 
 template <int BN, int CG>
@@ -932,6 +964,15 @@ static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
 }  // namespace tgb
 
 using namespace tgb;
+
+extern "C" int tgb_gemm_set_resid_piece(int width) {
+  if (width != 0 && width != 16 && width != 32) {
+    set_last_error("residual piece width must be 0 (auto), 16 or 32");
+    return TGB_EINVAL;
+  }
+  g_force_resid_piece = width;
+  return TGB_OK;
+}
 
 extern "C" int tgb_gemm_set_epilogue_warps(int warps) {
   if (warps != 0 && warps != 8 && warps != 16) {

@@ -23,6 +23,9 @@ TGB_API int tgb_gemm_set_cta_group(int cta_group);
 TGB_API int tgb_gemm_set_schedule(int mode);
 /* epilogue warps per CTA, 0 = choose (8; the fp32-residual epilogues always run 8). */
 TGB_API int tgb_gemm_set_epilogue_warps(int warps);
+/* column width of the fp32-residual epilogue's pieces: 0 = choose (32 when K <= 2048 and N tiles are 256 wide, else 16),
+ * 16 / 32 = force (32 needs 256-wide N tiles; other tile widths keep 16). */
+TGB_API int tgb_gemm_set_resid_piece(int width);
 /* 0 = ping-pong kernel (default), 1 = one-shot kernel (whole score row in tensor memory), 2 = three-block kernel,
  * 3 = CTA-pair kernel (cta_group::2), 4 = split-row ping-pong kernel (two threads per query row), 5 = ping-pong kernel
  * with the software-pipelined exp pass.  Measurements: profiles/r2_attention_experiments.txt. */

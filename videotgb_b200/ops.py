@@ -379,6 +379,11 @@ def gemm_set_epilogue_warps(warps: int) -> None:
     check(_lib.load().tgb_gemm_set_epilogue_warps(int(warps)))
 
 
+def gemm_set_resid_piece(width: int) -> None:
+    """0 = auto (32-column pieces when K <= 2048, else 16), 16 or 32; test / A-B knob of the fp32-residual epilogues."""
+    check(_lib.load().tgb_gemm_set_resid_piece(int(width)))
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, want_bf16: bool = True,
               want_f32: bool = False, out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
