@@ -76,7 +76,8 @@ TGB_API int tgb_span_draw(const float* start_logits, const float* end_logits, co
 /* ---------------------------------------------------------------- A8  spans -> frame indices ----------
  * src/models/LSTP_SF_blip2_module.py:433-459 (eval), :284-312 (train, inclusive end),
  * src/models/LSTP_module.py:233-261 and eval/utils/model.py:119-147 (ratio mapping).
- * cand_start / cand_end: i64 [top_k, B] argmax draws.  of_lengths: i32 [B] true flow lengths (>= 2).
+ * cand_start / cand_end: i64 [top_k, B] argmax draws.  of_lengths: i32 [B] true flow lengths (>= 2: the reference divides
+ * by length - 1 and raises below that; a device-side value below 2 is treated as 2).
  * mapping: 0 = int(s*(N-1)/(L-1)), 1 = int(s/L*N).  inclusive: range(start,end+1) instead of range(start,end).
  * host_ints: the draws are Python ints in the reference (float64 arithmetic) instead of 0-dim tensors (float32).
  * indices: i64 [B, nframe], sorted.  Returns TGB_EINVAL when num_frames > 4096 (bitmap limit).             */
@@ -207,7 +208,8 @@ TGB_API int tgb_sampler_assemble(const float* y, const float* bos, const float* 
                                  const float* gamma, const float* beta, float eps, int B, int L, int N, float* out_f32,
                                  void* out_bf16, tgb_stream_t stream);
 /* LayerNorm(table[ids[r]] + pos[r % period] + addvec): RopeBertEmbeddings (xropebert.py:190-208: word + token_type[0],
- * no position) and InstructBlipQFormerEmbeddings (xinstructblip.py:1018-1046: word + position).  pos/addvec may be NULL. */
+ * no position) and InstructBlipQFormerEmbeddings (xinstructblip.py:1018-1046: word + position).  pos/addvec may be NULL.
+ * An id outside [0, vocab) -- where nn.Embedding raises / trips a device-side assert -- yields a NaN output row.           */
 TGB_API int tgb_embed_layernorm(const int64_t* ids, const float* table, int64_t vocab, const float* pos, int period,
                                 const float* addvec, const float* gamma, const float* beta, float eps, int64_t rows, int N,
                                 float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, tgb_stream_t stream);

@@ -233,6 +233,12 @@ def test_gather_bit_exact():
         assert got.dtype == torch.float32 and torch.equal(got, want)
     with pytest.raises(RuntimeError):
         ops.gather_frames(torch.zeros(1, 2, 3, dtype=torch.float32, device=DEV), torch.zeros(1, 1, dtype=torch.int64, device=DEV))
+    # more than 65535 output frames in one call (tiny frames): the frame index rides on gridDim.x
+    b, n, k = 70000, 3, 1
+    px = torch.randn(b, n, 4, generator=g)
+    idx = torch.randint(0, n, (b, k), generator=g)
+    got = ops.gather_frames(px.to(DEV), idx.to(DEV)).cpu()
+    assert torch.equal(got, select_ref.gather_frames(px, idx))
 
 
 # ------------------------------------------------------------------------------------------------ A10
@@ -568,6 +574,29 @@ def test_attention(b, h, sq, sk, d, masked):
     assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
 
 
+@pytest.mark.parametrize("sq,sk", [(32, 40), (32, 257), (40, 600)])
+def test_attention_fully_masked_row_is_uniform(sq, sk):
+    """A batch element whose keys are ALL masked with finfo.min (an empty instruction / encoder mask): the reference's
+    scores + finfo.min are all equal, so softmax is uniform over the keys and the output is the mean of V -- not zeros or
+    NaN.  Element 1 is partly masked, element 2 not at all (sk = 600: the key-streaming kernel)."""
+    b, h, d = 3, 12, 64
+    g = torch.Generator().manual_seed(sq + sk)
+    q = torch.randn(b * sq, h * d, generator=g).to(torch.bfloat16)
+    kv = torch.randn(b * sk, 2 * h * d, generator=g).to(torch.bfloat16)
+    k, v = kv[:, : h * d], kv[:, h * d:]
+    mask = torch.zeros(b, sk)
+    mask[0, :] = torch.finfo(torch.float32).min
+    mask[1, sk // 2:] = torch.finfo(torch.float32).min
+    want = _attn_ref(q, k, v, b, h, sq, sk, d, d ** -0.5, mask)
+    assert torch.isfinite(want).all()
+    kvd = kv.to(DEV)
+    got = ops.attention(q.to(DEV), kvd[:, : h * d], kvd[:, h * d:], b, h, sq, sk, d, d ** -0.5, mask.to(DEV)).cpu()
+    assert torch.isfinite(got.float()).all()
+    uniform = v.float().view(b, sk, h * d)[0].mean(0)
+    assert (got.float().view(b, sq, h * d)[0] - uniform).abs().max().item() < 2e-2
+    assert _relerr(got, want) < 1.5e-2 and _cos(got, want) > 0.9999
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("frames,scale_in,late_peak", [(1, 1.0, False), (3, 1.0, False), (19, 2.5, False), (2, 1.0, True),
                                                        (150, 1.0, False), (300, 1.0, True)])
@@ -597,6 +626,21 @@ def test_vit_attention_tcgen05(frames, scale_in, late_peak, variant):
     assert err < 1.5e-2 and _cos(got.cpu(), want) > 0.9999, (err, _cos(got.cpu(), want))
     other = ops.attention(qd[:, :1408], qd[:, 1408:2816], qd[:, 2816:], frames, 16, 257, 257, 88, 88 ** -0.5)
     assert _relerr(got.cpu(), other.cpu()) < 1.5e-2
+
+
+def test_embed_layernorm_out_of_range_id_is_loud():
+    """nn.Embedding raises on an id outside the table; the kernel cannot, so the row must come out as NaN (never a silently
+    clamped embedding) and its neighbours must be untouched."""
+    g = torch.Generator().manual_seed(3)
+    table = torch.randn(50, 768, generator=g)
+    gamma, beta = torch.rand(768, generator=g) + 0.5, torch.randn(768, generator=g)
+    ids = torch.tensor([3, 49, 50, 7, -1, 0])
+    f32, b16 = ops.embed_layernorm(ids.to(DEV), table.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-12)
+    f32, b16 = f32.cpu(), b16.cpu()
+    good = [0, 1, 3, 5]
+    want = torch.nn.functional.layer_norm(table[ids[good]], (768,), gamma, beta, 1e-12)
+    assert (f32[good] - want).abs().max().item() < 1e-4
+    assert torch.isnan(f32[[2, 4]]).all() and torch.isnan(b16[[2, 4]].float()).all()
 
 
 def test_cast_and_group_mean():

@@ -35,6 +35,11 @@ __device__ __forceinline__ T* attn_row(T* a, T* a2, long long ld, int b, int r, 
   return r < n1 ? a + ((long long)b * n1 + r) * ld : a2 + ((long long)b * (S - n1) + (r - n1)) * ld;
 }
 
+// additive mask value in log2 units, kept FINITE: the reference's (1 - mask) * finfo.min masks (xblip2.py:1106-1113) absorb
+// the score, so a row whose keys are ALL masked sees equal scores and softmax gives the uniform distribution over the
+// keys; finfo.min * log2(e) would overflow to -inf here and turn that row into exp2(-inf - (-inf)) = NaN / zeros instead.
+__device__ __forceinline__ float mask_log2(float m) { return fmaxf(m * 1.4426950408889634f, -3.4028234663852886e38f); }
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
   }
   if (p.mask)
     for (int i = tid; i < SkPad; i += blockDim.x)
-      smask[i] = i < p.Sk ? p.mask[(long long)b * p.Sk + i] * 1.4426950408889634f : 0.f;
+      smask[i] = i < p.Sk ? mask_log2(p.mask[(long long)b * p.Sk + i]) : 0.f;
   cp_async_wait_all();
   __syncthreads();
 
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(256) attention_chunked_kernel(const AttnParams
     }
     if (p.mask)
       for (int i = tid; i < len; i += blockDim.x)
-        smask[i] = (c0 + i) < p.Sk ? p.mask[(long long)b * p.Sk + c0 + i] * 1.4426950408889634f : 0.f;
+        smask[i] = (c0 + i) < p.Sk ? mask_log2(p.mask[(long long)b * p.Sk + c0 + i]) : 0.f;
     cp_async_wait_all();
     __syncthreads();
     int key0 = 0;

@@ -479,17 +479,18 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_fast_kernel(const uint
   }
 }
 
-// Gather: dst[(b*k + i)] = src[b, idx[b,i]] as 16-byte words; blockIdx.y = output frame, grid-stride over words.
+// Gather: dst[(b*k + i)] = src[b, idx[b,i]] as 16-byte words; blockIdx.x = output frame (no 65535 limit), the blockIdx.y
+// CTAs of a frame grid-stride over its words.
 __global__ void __launch_bounds__(256) gather_frames_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx,
                                                             uint4* __restrict__ dst, int N, int k, long long words) {
-  const int of = blockIdx.y;                    // output frame b*k + i
+  const int of = blockIdx.x;                    // output frame b*k + i
   const int b = of / k;
   long long j = idx[of];
   j = j < 0 ? 0 : (j >= N ? N - 1 : j);         // host validated; clamp keeps a bad index from faulting
   const uint4* s = src + ((long long)b * N + j) * words;
   uint4* d = dst + (long long)of * words;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.y * blockDim.x;
+  long long w = (long long)blockIdx.y * blockDim.x + threadIdx.x;
   for (; w + 3 * stride < words; w += 4 * stride) {       // 4 independent 16-B loads in flight per thread
     const uint4 a0 = __ldg(s + w), a1 = __ldg(s + w + stride), a2 = __ldg(s + w + 2 * stride), a3 = __ldg(s + w + 3 * stride);
     d[w] = a0; d[w + stride] = a1; d[w + 2 * stride] = a2; d[w + 3 * stride] = a3;
@@ -649,7 +650,7 @@ extern "C" int tgb_gather_frames(const void* src, const int64_t* indices, void* 
   TGB_CHECK_ARG(B >= 0 && N > 0 && k > 0, "gather: bad shape B=%d N=%d k=%d", B, N, k);
   TGB_CHECK_ARG(frame_bytes % 16 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0,
                 "gather: frame_bytes and pointers must be multiples of 16");
-  TGB_CHECK_ARG((long long)B * k <= 65535, "gather: B*k = %lld exceeds 65535 output frames per call", (long long)B * k);
+  TGB_CHECK_ARG((long long)B * k <= 2147483647LL, "gather: B*k = %lld output frames", (long long)B * k);
   if (B == 0) return TGB_OK;
   const long long words = (long long)(frame_bytes / 16);
   // enough CTAs per frame to keep >= 4 x SMs CTAs in flight, each thread moving >= 4 words
@@ -657,7 +658,7 @@ extern "C" int tgb_gather_frames(const void* src, const int64_t* indices, void* 
   const long long max_useful = (words + 256 * 4 - 1) / (256 * 4);
   if (per_frame > max_useful) per_frame = (int)max_useful;
   if (per_frame < 1) per_frame = 1;
-  dim3 grid(per_frame, B * k);
+  dim3 grid(B * k, per_frame);
   gather_frames_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (const long long*)indices, (uint4*)dst, N, k, words);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;

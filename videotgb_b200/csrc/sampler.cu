@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(256) embed_layernorm_kernel(const long long* _
   const int nvec = N >> 2;
   for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < R; r += (long long)gridDim.x * 8) {
     long long id = ids[r];
-    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    // nn.Embedding raises (CPU) / trips a device-side assert (CUDA) on an id outside the table.  No exceptions or host
+    // round trips here: the row comes out as NaN, which every consumer propagates -- loud, not silently clamped.
+    const bool bad_id = id < 0 || id >= vocab;
+    if (bad_id) id = 0;
     const float4* src = reinterpret_cast<const float4*>(table + id * N);
     float4 v[ROW_NV];
 #pragma unroll
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(256) embed_layernorm_kernel(const long long* _
           const float4 p = __ldg(reinterpret_cast<const float4*>(addvec) + c);
           a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
         }
+        if (bad_id) a.x = a.y = a.z = a.w = __int_as_float(0x7fc00000);
         v[i] = a;
       }
     }

@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(32) spans_to_indices_kernel(const long long* _
   __shared__ uint32_t bits[SEL_MAX_FRAMES / 32];
   __shared__ short cand[SEL_MAX_FRAMES];
   const int j = blockIdx.x, lane = threadIdx.x;
-  const int L = of_lengths[j];
+  // the reference divides by video_length - 1 (ZeroDivisionError below 2; the host mirror raises it for host-side lengths).
+  // Device-side lengths cannot raise: a value below 2 is treated as 2, so the arithmetic below stays defined.
+  const int L = of_lengths[j] < 2 ? 2 : of_lengths[j];
   const int nwords = (N + 31) / 32;
   for (int w = lane; w < nwords; w += 32) bits[w] = 0u;
   __syncwarp();

@@ -52,10 +52,13 @@ def select_indices(cand_start: torch.Tensor, cand_end: torch.Tensor, of_lengths,
                    variant: str = "eval", host_ints: bool = False) -> torch.Tensor:
     """-> int64 [B, nframe] sorted frame indices (device)."""
     mapping, inclusive = VARIANTS[variant]
-    if not torch.is_tensor(of_lengths):
-        if min(of_lengths) < 2:
+    if not torch.is_tensor(of_lengths) or not of_lengths.is_cuda:
+        # host-side lengths (the reference's batch["of_lengths"] is a Python list): same error as the reference's
+        # `... / (video_length - 1)`.  A CUDA tensor is not synchronised on: the kernel treats a length below 2 as 2.
+        host = [int(v) for v in (of_lengths.tolist() if torch.is_tensor(of_lengths) else of_lengths)]
+        if min(host) < 2:
             raise ZeroDivisionError("of_lengths must be >= 2 (the reference divides by video_length-1)")
-        of_lengths = torch.tensor(list(of_lengths), dtype=torch.int32, device=cand_start.device)
+        of_lengths = torch.tensor(host, dtype=torch.int32, device=cand_start.device)
     return ops.spans_to_indices(cand_start.contiguous(), cand_end.contiguous(), of_lengths.to(torch.int32).contiguous(),
                                 num_frames, nframe, mapping, inclusive, host_ints)
 
@@ -108,5 +111,7 @@ def pseudo_span_targets(scores: torch.Tensor, of_lengths) -> tuple:
 
 
 def mrc_loss(of_logits: torch.Tensor, start_targets: torch.Tensor, end_targets: torch.Tensor) -> torch.Tensor:
-    """Span cross-entropy on the sampler's mrc logits [B, Lof, 2] (LSTP_SF_blip2_module.py:238-253)."""
+    """Span cross-entropy on the sampler's mrc logits [B, Lof, 2] (LSTP_SF_blip2_module.py:238-253).
+    FORWARD VALUE ONLY: the result carries no autograd graph (the kernels implement inference; training the sampler
+    through this loss is out of scope) -- use it for evaluation / monitoring."""
     return ops.span_ce_loss(of_logits.to(torch.float32).contiguous(), start_targets.contiguous(), end_targets.contiguous())
