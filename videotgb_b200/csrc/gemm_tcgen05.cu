@@ -710,7 +710,44 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dim ld elements) -> tensor map with a [box_rows x 64] SWIZZLE_128B box.
-static int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+// A tensor map is a pure function of (base, extents, leading dimension, box / type / swizzle): the ~780 GEMM launches of a
+// step use a few dozen distinct ones (the activation buffers are reused by every layer), so each host thread keeps the
+// encoded descriptors in a small direct-mapped cache instead of calling cuTensorMapEncodeTiled up to five times per
+// launch.  `kind` distinguishes the builders and their box parameters.
+struct TmapSlot {
+  const void* base;
+  long long rows, cols, ld;
+  int kind;
+  bool used;
+  CUtensorMap map;
+};
+constexpr int TMAP_CACHE_SLOTS = 256;
+static TmapSlot* tmap_slot(const void* base, long long rows, long long cols, long long ld, int kind, bool* hit) {
+  static thread_local TmapSlot cache[TMAP_CACHE_SLOTS] = {};
+  unsigned long long h = reinterpret_cast<unsigned long long>(base) >> 4;
+  h ^= (unsigned long long)rows * 0x9E3779B97F4A7C15ull;
+  h ^= (unsigned long long)cols * 0xC2B2AE3D27D4EB4Full + (unsigned long long)ld * 0x165667B19E3779F9ull + (unsigned)kind * 0x27D4EB2Full;
+  h ^= h >> 29;
+  TmapSlot* s = &cache[h % TMAP_CACHE_SLOTS];
+  *hit = s->used && s->base == base && s->rows == rows && s->cols == cols && s->ld == ld && s->kind == kind;
+  return s;
+}
+template <typename Build>
+static int cached_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int kind, Build&& build) {
+  bool hit;
+  TmapSlot* s = tmap_slot(base, rows, cols, ld, kind, &hit);
+  if (hit) {
+    *map = s->map;
+    return TGB_OK;
+  }
+  const int st = build(map);
+  if (st != TGB_OK) return st;
+  s->base = base; s->rows = rows; s->cols = cols; s->ld = ld; s->kind = kind; s->used = true;
+  s->map = *map;
+  return TGB_OK;
+}
+
+static int make_tmap_uncached(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
@@ -731,8 +768,13 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
   return TGB_OK;
 }
 
+static int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  return cached_tmap(map, base, rows, cols, ld, 0x1000 + box_rows,
+                     [&](CUtensorMap* m) { return make_tmap_uncached(m, base, rows, cols, ld, box_rows); });
+}
+
 // bf16 output [M, N] (leading dim ldo) -> tensor map with the epilogue's [32 rows x 64 columns] SWIZZLE_128B store box
-static int make_tmap_out(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+static int make_tmap_out_uncached(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
@@ -752,8 +794,13 @@ static int make_tmap_out(CUtensorMap* map, const void* base, long long rows, lon
   return TGB_OK;
 }
 
-// the fp32 residual epilogue's boxes: [32 rows x 16 columns], fp32 (SWIZZLE_64B) or bf16 copy (32-byte rows, no swizzle)
-static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, bool f32, int pw = 16) {
+static int make_tmap_out(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+  return cached_tmap(map, base, rows, cols, ld, 0x2000,
+                     [&](CUtensorMap* m) { return make_tmap_out_uncached(m, base, rows, cols, ld); });
+}
+
+// the fp32 residual epilogue's boxes: [32 rows x pw columns], fp32 or bf16 copy (row bytes 32: no swizzle, 64 / 128: swizzled)
+static int make_tmap_box16_uncached(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, bool f32, int pw) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
@@ -774,6 +821,11 @@ static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, l
     return TGB_ECUDA;
   }
   return TGB_OK;
+}
+
+static int make_tmap_box16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, bool f32, int pw = 16) {
+  return cached_tmap(map, base, rows, cols, ld, 0x3000 + pw * 2 + (f32 ? 1 : 0),
+                     [&](CUtensorMap* m) { return make_tmap_box16_uncached(m, base, rows, cols, ld, f32, pw); });
 }
 
 // the bf16 epilogues read their bias unconditionally: a call without one gets this block of zeros
