@@ -986,7 +986,12 @@ static int dispatch_bn(int bn, const void* A, long long lda, const void* W, long
   return TGB_EINVAL;
 }
 
-// Tile choice: minimise the MMA time of the busiest SM; narrower tiles pay more operand traffic per flop.
+// Tile choice: minimise (waves of tiles) x (time of one wave).  Measured (tools/gemm_small_m.py,
+// profiles/r2_gemm_small_m.txt; qkv / fc1 shapes, M = 1028 .. 16448): a wave of 128-wide tiles takes 0.86 of a wave of
+// 256-wide ones -- half the MMA time, but the same A traffic from the L2, which is what a narrow tile is bound by -- so a
+// narrow tile only pays when it saves whole waves; single-CTA 128-row tiles cost 5-10 % more per wave than CTA pairs and win
+// exactly when they need fewer waves (M = 2056: 2 instead of 3).  The choice never changes a result: every output
+// element accumulates over K in the same order whatever the tile.
 static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
   // measured on B200: a tcgen05.mma with N=176 costs as much as N=256 (N is processed in 128-wide passes), so the
   // tiles are 256 / 128 / 64 wide; prefer 256, then 128.
@@ -1003,8 +1008,8 @@ static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
       const long long tiles = nblocks * mblocks;
       const long long slots = sm_count() / cg;
       const long long waves = (tiles + slots - 1) / slots;
-      double eff = bn >= 256 ? 1.0 : (bn == 128 ? 0.9 : 0.75);
-      if (cg == 1) eff *= 0.9;
+      double eff = bn >= 256 ? 1.0 : (bn == 128 ? 0.58 : 0.27);
+      if (cg == 1) eff *= 0.93;
       const double cost = (double)waves * bn / eff;
       if (best_cost < 0 || cost < best_cost * 0.999) { best_cost = cost; best_bn = bn; best_cg = cg; }
     }
