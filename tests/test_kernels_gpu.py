@@ -545,7 +545,12 @@ def _attn_ref(q, k, v, b, h, sq, sk, d, scale, mask=None):
 @pytest.mark.parametrize("b,h,sq,sk,d,masked", [(3, 16, 257, 257, 88, False), (2, 12, 32, 257, 64, False),
                                                 (2, 12, 32, 32, 64, False), (3, 12, 44, 44, 64, True),
                                                 (2, 12, 160, 160, 64, True), (1, 12, 1, 17, 64, False),
-                                                (1, 16, 100, 64, 88, False)])
+                                                (1, 16, 100, 64, 88, False),
+                                                # few query rows, several 64-key blocks: the key-sliced path (2 / 4 / 8 slices)
+                                                (3, 12, 32, 257, 64, True), (2, 12, 20, 130, 64, True), (2, 12, 56, 200, 64, True),
+                                                (2, 12, 8, 600, 64, True), (2, 16, 40, 257, 88, False),
+                                                # >= 2 items per SM: the persistent double-buffered form of that path
+                                                (30, 12, 32, 257, 64, True), (50, 12, 20, 130, 64, False), (26, 12, 56, 200, 64, True)])
 def test_attention(b, h, sq, sk, d, masked):
     g = torch.Generator().manual_seed(b + sq + sk)
     if sq == sk:

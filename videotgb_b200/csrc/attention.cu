@@ -26,6 +26,11 @@ struct AttnParams {
   const __nv_bfloat16* q2; const __nv_bfloat16* k2; const __nv_bfloat16* v2;
   __nv_bfloat16* out2;
   int n1;
+  // key slices per 16-row query tile (single-pass kernel): with few query rows (the Q-Former's 32 queries against 257
+  // image tokens) one warp per query tile leaves a 64-thread CTA that first waits for 66 KB of K/V and then walks all the
+  // keys alone; nslices > 1 gives every query tile `nslices` warps, each owning every nslices-th 64-key block, and merges
+  // their (max, sum, O) partials through shared memory.  blockDim = query tiles * nslices warps.
+  int nslices;
 };
 
 // address of sequence row r of batch b in a (possibly two-segment) operand with S rows per batch
@@ -159,8 +164,13 @@ __device__ __forceinline__ void attn_block(const uint32_t (&qf)[AttnCfg<D>::KS][
   }
 }
 
+// (d = 64 -- the Q-Former and sampler shapes -- is compiled for two resident CTAs per SM: one CTA's K / V staging then
+//  overlaps the other's math; ncu showed a single resident CTA alternating between waiting for 66 KB and computing.
+//  Q-Former cross attention, 1024 frames x 12 heads of 32 x 257: 611 -> 370 us per layer.  A persistent CTA per SM with
+//  two K / V buffers and the next item's cp.async copies in flight during the math measured 393 us: the shape is bound by
+//  the legacy mma.sync rate -- 27 GFLOP per layer at the ~155 TFLOP/s this path reaches is 178 us -- not by its loads.)
 template <int D>
-__global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(D == 64 ? 256 : 288, D == 64 ? 2 : 1) attention_kernel(const AttnParams p) {
   using C = AttnCfg<D>;
   extern __shared__ __align__(16) uint8_t smem[];
   const int SkPad = (p.Sk + 15) & ~15;
@@ -196,7 +206,9 @@ __global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
   const float* sm = p.mask ? smask : nullptr;
   const int mtiles = (p.Sq + 15) >> 4;
   const int g = lane >> 2, t2 = (lane & 3) * 2;
-  for (int mt = warp; mt < mtiles; mt += nwarps) {
+  const int nsl = p.nslices;
+  for (int mt = (nsl > 1 ? warp % mtiles : warp); mt < mtiles; mt += nwarps) {
+    const int sl = nsl > 1 ? warp / mtiles : 0;
     // ---- Q fragments straight from global (row-major A layout of m16n8k16)
     uint32_t qf[C::KS][4];
     const int r0 = mt * 16 + g, r1 = r0 + 8;
@@ -215,13 +227,49 @@ __global__ void __launch_bounds__(288) attention_kernel(const AttnParams p) {
 #pragma unroll
     for (int nd = 0; nd < C::ND; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f; }
     float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
-    int key0 = 0;
-    for (; key0 + 64 <= SkPad; key0 += 64)
+    const int nfull = SkPad >> 6;               // whole 64-key blocks; this warp owns blocks sl, sl + nsl, ...
+    int key0 = sl * 64;
+    for (; key0 + 64 <= SkPad; key0 += 64 * nsl)
       attn_block<D, 8>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
-    const int rem = SkPad - key0;               // 0, 16, 32 or 48 keys left
-    if (rem == 16) attn_block<D, 2>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
-    else if (rem == 32) attn_block<D, 4>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
-    else if (rem == 48) attn_block<D, 6>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
+    const int rem = SkPad - nfull * 64;         // 0, 16, 32 or 48 keys left: they belong to slice nfull % nsl
+    if (nfull % nsl == sl) {
+      key0 = nfull * 64;
+      if (rem == 16) attn_block<D, 2>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
+      else if (rem == 32) attn_block<D, 4>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
+      else if (rem == 48) attn_block<D, 6>(qf, o, mrow, lrow, sK, sV, key0, p.Sk, sm, p.scale_log2, lane);
+    }
+    if (nsl > 1) {
+      // ---- merge the slices of this query tile (all warps take this path together: blockDim = mtiles * nsl warps).
+      // Partials go through the K / V staging area, which every warp has finished reading after the first barrier.
+      constexpr int XS = C::ND * 4 + 4;           // floats per thread: O fragment, row maxima, row sums
+      __syncthreads();
+      float* xw = reinterpret_cast<float*>(smem) + ((size_t)warp * 32 + lane) * XS;
+      if (sl > 0) {
+#pragma unroll
+        for (int nd = 0; nd < C::ND; ++nd) {
+          xw[nd * 4 + 0] = o[nd][0]; xw[nd * 4 + 1] = o[nd][1]; xw[nd * 4 + 2] = o[nd][2]; xw[nd * 4 + 3] = o[nd][3];
+        }
+        xw[C::ND * 4 + 0] = mrow[0]; xw[C::ND * 4 + 1] = mrow[1]; xw[C::ND * 4 + 2] = lrow[0]; xw[C::ND * 4 + 3] = lrow[1];
+      }
+      __syncthreads();
+      if (sl > 0) continue;                       // (single pass: mt + nwarps >= mtiles, the loop ends here for every warp)
+      for (int s2 = 1; s2 < nsl; ++s2) {
+        const float* xo = reinterpret_cast<const float*>(smem) + ((size_t)(mt + s2 * mtiles) * 32 + lane) * XS;
+        const float m0 = xo[C::ND * 4 + 0], m1 = xo[C::ND * 4 + 1];
+        if (m0 == -INFINITY && m1 == -INFINITY) continue;       // that slice owned no key block
+        const float n0 = fmaxf(mrow[0], m0), n1 = fmaxf(mrow[1], m1);
+        const float a0 = ex2_approx(mrow[0] - n0), a1 = ex2_approx(mrow[1] - n1);
+        const float b0 = ex2_approx(m0 - n0), b1 = ex2_approx(m1 - n1);
+        mrow[0] = n0; mrow[1] = n1;
+        lrow[0] = lrow[0] * a0 + xo[C::ND * 4 + 2] * b0;
+        lrow[1] = lrow[1] * a1 + xo[C::ND * 4 + 3] * b1;
+#pragma unroll
+        for (int nd = 0; nd < C::ND; ++nd) {
+          o[nd][0] = o[nd][0] * a0 + xo[nd * 4 + 0] * b0; o[nd][1] = o[nd][1] * a0 + xo[nd * 4 + 1] * b0;
+          o[nd][2] = o[nd][2] * a1 + xo[nd * 4 + 2] * b1; o[nd][3] = o[nd][3] * a1 + xo[nd * 4 + 3] * b1;
+        }
+      }
+    }
     // ---- normalise and store
     float l0 = lrow[0], l1 = lrow[1];
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -336,10 +384,29 @@ static int launch_attention(const AttnParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)SkPad * (C::KP + C::VP) * 2 + (size_t)SkPad * 4;
   if (smem > 112 * 1024) return launch_attention_chunked<D>(p, stream);     // long key sequences: stream K/V
   auto kern = attention_kernel<D>;
-  TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+  TGB_ONCE_PER_DEVICE({
+    TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // ask for the largest shared-memory carve-out: the driver's default sized it for ONE CTA of this kernel per SM
+    TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  });
   const int mtiles = (p.Sq + 15) / 16;
-  int warps = mtiles < 9 ? mtiles : 9;            // 9 warps x 2 rounds cover the ViT's 17 row tiles
-  kern<<<p.B * p.H, warps * 32, smem, stream>>>(p);
+  const int max_warps = D == 64 ? 8 : 9;          // (9 warps x 2 rounds cover the ViT's 17 row tiles)
+  int warps = mtiles < max_warps ? mtiles : max_warps;
+  AttnParams q = p;
+  q.nslices = 1;
+  size_t smem_launch = smem;
+  const int nblocks = (SkPad + 63) / 64;
+  if (mtiles <= 4 && nblocks >= 2) {              // few query rows, several key blocks: split the keys between warps
+    int nsl = 8 / mtiles;
+    if (nsl > nblocks) nsl = nblocks;
+    if (nsl > 1) {
+      q.nslices = nsl;
+      warps = mtiles * nsl;
+      const size_t merge = (size_t)warps * 32 * (C::ND * 4 + 4) * 4;
+      if (merge > smem_launch) smem_launch = merge;
+    }
+  }
+  kern<<<p.B * p.H, warps * 32, smem_launch, stream>>>(q);
   TGB_CUDA(cudaGetLastError());
   return TGB_OK;
 }
