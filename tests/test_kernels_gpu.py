@@ -602,6 +602,51 @@ def test_attention_fully_masked_row_is_uniform(sq, sk):
     assert _relerr(got, want) < 1.5e-2 and _cos(got, want) > 0.9999
 
 
+@pytest.mark.parametrize("b,h,sk,masked,scale_in", [(1, 4, 257, False, 1.0), (3, 12, 257, False, 1.0), (3, 12, 257, True, 1.0),
+                                                    (2, 12, 256, False, 1.0), (2, 8, 255, False, 1.0), (2, 12, 200, True, 1.0),
+                                                    (5, 12, 130, False, 1.0), (4, 4, 65, True, 1.0), (3, 12, 257, False, 3.0),
+                                                    (40, 12, 257, False, 1.0), (100, 12, 257, True, 2.0), (210, 12, 257, False, 1.0)])
+def test_qformer_cross_attention_tcgen05(b, h, sk, masked, scale_in):
+    """The tcgen05 form of `ops.attention` for the Q-Former cross-attention shape (32 queries, d = 64, four heads stacked
+    in one 128-row MMA tile through a block-diagonal Q operand; key 256 on the CUDA cores) vs torch and vs the mma.sync
+    kernel it replaces.  Half of the queries get a dominant key planted at the LAST key (the CUDA-core tail when sk = 257)
+    and in the middle; 100 / 210 frames = 2-4 items per CTA, so every barrier and the stage ring wrap."""
+    d, sq = 64, 32
+    g = torch.Generator().manual_seed(b * 1000 + sk)
+    q = (torch.randn(b * sq, h * d, generator=g) * scale_in).to(torch.bfloat16)
+    kv = torch.randn(b * sk, 2 * h * d, generator=g).to(torch.bfloat16)
+    x = kv.float().view(b, sk, 2, h, d)
+    qv = q.float().view(b, sq, h, d)
+    x[:, sk - 1, 0] = qv[:, 3] * 0.7               # the last key aligned with query 3 of every head
+    x[:, sk // 2, 0] = qv[:, 17] * 0.7             # a middle key aligned with query 17
+    kv = x.view(b * sk, 2 * h * d).to(torch.bfloat16)
+    k, v = kv[:, : h * d], kv[:, h * d:]
+    mask = None
+    if masked:
+        mask = torch.zeros(b, sk)
+        for j in range(b):
+            mask[j, sk - 1 - (j % 7):] = -10000.0          # element 0 keeps every key but the last, 7 k + 0 masks only it
+            mask[j, (5 * j) % 40] = torch.finfo(torch.float32).min
+    scale = d ** -0.5
+    want = _attn_ref(q, k, v, b, h, sq, sk, d, scale, mask)
+    qd, kvd = q.to(DEV), kv.to(DEV)
+    md = None if mask is None else mask.to(DEV)
+    got = ops.attention(qd, kvd[:, : h * d], kvd[:, h * d:], b, h, sq, sk, d, scale, md)
+    ops.attention_set_tc(False)
+    try:
+        legacy = ops.attention(qd, kvd[:, : h * d], kvd[:, h * d:], b, h, sq, sk, d, scale, md)
+        torch.cuda.synchronize()
+    finally:
+        ops.attention_set_tc(True)
+    err, cos = _relerr(got.cpu(), want), _cos(got.cpu(), want)
+    assert err < 1.5e-2 and cos > 0.9999, (err, cos)
+    assert _relerr(got.cpu(), legacy.cpu()) < 1.5e-2
+    # strided output view (the kernel writes 128-byte row pieces at ldo) and a second call on the same buffers
+    wide = torch.zeros(b * sq, h * d + 64, dtype=torch.bfloat16, device=DEV)
+    ops.attention(qd, kvd[:, : h * d], kvd[:, h * d:], b, h, sq, sk, d, scale, md, out=wide[:, : h * d])
+    assert torch.equal(wide[:, : h * d], got) and not wide[:, h * d:].any()
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("frames,scale_in,late_peak", [(1, 1.0, False), (3, 1.0, False), (19, 2.5, False), (2, 1.0, True),
                                                        (150, 1.0, False), (300, 1.0, True)])

@@ -77,6 +77,7 @@ DEBUG_SIGNATURES = {
     "tgb_gemm_set_resid_piece": ([c_int], c_int),
     "tgb_vit_attention_set_variant": ([c_int], c_int),
     "tgb_vit_attention_set_prefetch": ([c_int], c_int),
+    "tgb_attention_set_tc": ([c_int], c_int),
 }
 
 _lib = None
@@ -105,6 +106,8 @@ def load() -> ctypes.CDLL:
         lib.tgb_gemm_set_resid_piece(int(os.environ["TGB_GEMM_RESID_PIECE"]))
     if os.environ.get("TGB_ATTN_VARIANT"):                                                                    # A/B knob
         lib.tgb_vit_attention_set_variant(int(os.environ["TGB_ATTN_VARIANT"]))
+    if os.environ.get("TGB_ATTN_TC"):                                                                         # A/B knob
+        lib.tgb_attention_set_tc(int(os.environ["TGB_ATTN_TC"]))
     if os.environ.get("TGB_ATTN_PREFETCH"):                                                                   # A/B knob
         lib.tgb_vit_attention_set_prefetch(int(os.environ["TGB_ATTN_PREFETCH"]))
     return lib

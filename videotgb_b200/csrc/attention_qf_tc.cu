@@ -1,0 +1,446 @@
+// Q-Former cross-attention on the 5th-gen tensor cores: 32 learned queries per frame against the <= 257 image tokens of
+// that frame, heads of 64 (xblip2.py:612-695 / xinstructblip.py:565-694: query @ key^T / sqrt(d) + mask -> softmax ->
+// @ value, per (frame, head)).  Specialised like the ViT kernel: Sq = 32, D = 64, H % 4 == 0, 64 < Sk <= 257.
+//
+// A tcgen05.mma tile has 128 rows and one (frame, head) has 32 queries, so an ITEM is one frame x FOUR heads stacked on
+// the M side, with a block-diagonal A operand that keeps the heads apart:
+//   Q' [128 x 256]   row (h,q), column (h',d) = Q_h[q,d] if h == h' else 0      (four 16 KB K-major slabs, one per head;
+//                    TMA drops each head's [32 x 64] box into rows 32h.. of slab h, the zeros are written once)
+//   S  [128 x 256] = sum_h Q'[:, slab h] K_h^T   16 x (M=128, N=256, K=16): row (h,q) only sees head h's keys
+//   O' [128 x 256] = P V'                        V' = [keys x (h',d)] MN-major;  row (h,q) keeps columns [64h, 64h+64)
+// Three quarters of the products hit zeros or are discarded -- the op is HBM-bound (K|V of a frame are read once:
+// 257 x 1536 x 2 B = 790 KB per frame against 0.1 GFLOP useful), the point is that the tensor pipe does it in 32 full-rate
+// instructions per item while `mma.sync` needed ~1100 per item.  Key 256 (the 257th image token) would cost a second
+// N = 16 MMA per k-step and 16 more TMEM columns than there are (S 256 + O 256 = 512): its score and its P V term are
+// 64-long dot products on the CUDA cores of the thread that owns the row.
+//   warps 0-3  softmax + epilogue: warp = head, lane = query (TMEM lane 32h + q).  Two streaming passes over the score
+//              row (max, then exp2 / sum / bf16 P written back over the scores it replaces), later O / l -> bf16 rows.
+//   warp 4     TMEM allocator + TMA producer: Q boxes, then a ring of 32 KB stages -- K_h [256 keys x 64] per head, then
+//              V [64 keys x 4 heads x 64] per key block -- filled strictly in the order the MMA issuer consumes them.
+//   warp 5     MMA issuer.  S(i+1) is issued right behind P V(i) (the pipe executes in order, so the P/S alias needs no
+//              barrier) and overlaps the epilogue of item i.
+#include "common.cuh"
+#include "tc_helpers.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace tgb {
+
+constexpr int QF_SQ = 32, QF_D = 64, QF_HG = 4, QF_KMAIN = 256, QF_SK_MAX = 257;
+constexpr int QF_THREADS = 192;
+constexpr int QF_STAGES = 4;
+constexpr int QF_STAGE_BYTES = 32768;                     // K_h: 256 x 128 B;  V block: 4 heads x 64 keys x 128 B
+constexpr int QF_QSLAB_BYTES = 128 * 128;                 // one head's slab of Q'
+constexpr int QF_QBOX_BYTES = QF_SQ * 128;                // the non-zero part of a slab
+constexpr int QF_SMEM_Q = 0;
+constexpr int QF_SMEM_RING = QF_HG * QF_QSLAB_BYTES;                          // 65536
+constexpr int QF_SMEM_BAR = QF_SMEM_RING + QF_STAGES * QF_STAGE_BYTES;       // 196608
+constexpr int QF_SMEM_BIAS = QF_SMEM_BAR + 256;           // float [2][272]: additive mask (log2 units), -inf beyond Sk
+constexpr int QF_BIAS_STRIDE = 272;
+constexpr int QF_SMEM_TOTAL = QF_SMEM_BIAS + 2 * QF_BIAS_STRIDE * 4 + 1024;  // + alignment slack
+static_assert(QF_SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+constexpr uint32_t QF_COL_S = 0, QF_COL_O = 256;          // TMEM: S fp32 [0,256) with P bf16 over [0,128), O fp32 [256,512)
+
+struct QfAttnParams {
+  const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v;
+  __nv_bfloat16* out;
+  const float* mask;            // additive f32 [B, Sk] or null
+  long long ldq, ldk, ldv, ldo;
+  int B, H, Sk;
+  int num_items;                // B * H / 4
+  float scale_log2;
+};
+
+__device__ __forceinline__ float qf_mask_log2(float m) { return fmaxf(m * 1.4426950408889634f, -3.4028234663852886e38f); }
+
+// dot product of two 64-long bf16 rows (fp32 accumulation; the bf16 x bf16 products are exact in fp32)
+__device__ __forceinline__ float qf_dot64(const __nv_bfloat16* a, const __nv_bfloat16* b) {
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(a) + c);
+    const uint4 y = __ldg(reinterpret_cast<const uint4*>(b) + c);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[e]));
+      const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[e]));
+      acc0 = fmaf(fx.x, fy.x, acc0);
+      acc1 = fmaf(fx.y, fy.y, acc1);
+    }
+  }
+  return acc0 + acc1;
+}
+
+// Pass 1: row max of  s_j * sl2 + bias_j  over the 256 tensor-core score columns (BIAS = false: max of the raw scores,
+// scaled by the caller; sl2 > 0).  32 columns per tcgen05.ld, rolled.
+template <bool BIAS>
+__device__ __forceinline__ float qf_row_max(uint32_t s_addr, const float* bias, float sl2) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < QF_KMAIN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32<0>(s_addr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (BIAS) {
+        const float4 bj = *reinterpret_cast<const float4*>(bias + c * 32 + j);
+        m0 = fmaxf(m0, fmaf(__uint_as_float(v[j]), sl2, bj.x));
+        m1 = fmaxf(m1, fmaf(__uint_as_float(v[j + 1]), sl2, bj.y));
+        m2 = fmaxf(m2, fmaf(__uint_as_float(v[j + 2]), sl2, bj.z));
+        m3 = fmaxf(m3, fmaf(__uint_as_float(v[j + 3]), sl2, bj.w));
+      } else {
+        m0 = fmaxf(m0, __uint_as_float(v[j]));
+        m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+        m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+        m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// Pass 2: p_j = 2^(s_j * sl2 + bias_j - m) for the 256 columns, 16 at a time; the bf16 pairs of chunk c go to TMEM
+// columns [8c, 8c+8) -- behind the read position -- and the next chunk's load is in flight while this one is
+// exponentiated.  Returns the row sum (four interleaved partial sums).
+template <bool BIAS>
+__device__ __forceinline__ float qf_exp_row(uint32_t s_addr, const float* bias, float sl2, float negm) {
+  float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+  const float2 s2 = make_float2(sl2, sl2), m2 = make_float2(negm, negm);
+  uint32_t cur[16], nxt[16];
+  tmem_ld16<0>(s_addr, cur);
+#pragma unroll 1
+  for (int c = 0; c < QF_KMAIN / 16; ++c) {
+    tmem_ld_wait();
+    if (c + 1 < QF_KMAIN / 16) tmem_ld16<0>(s_addr + (c + 1) * 16, nxt);
+    float2 x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 sj = make_float2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]));
+      if (BIAS) {
+        const float2 bj = *reinterpret_cast<const float2*>(bias + c * 16 + 2 * j);
+        x[j] = __fadd2_rn(__ffma2_rn(sj, s2, bj), m2);
+      } else {
+        x[j] = __ffma2_rn(sj, s2, m2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[j].x = ex2_approx(x[j].x);
+      x[j].y = ex2_approx(x[j].y);
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      la = __fadd2_rn(la, x[j]);
+      lb = __fadd2_rn(lb, x[j + 1]);
+      pk[j] = pack_bf16(x[j].x, x[j].y);
+      pk[j + 1] = pack_bf16(x[j + 1].x, x[j + 1].y);
+    }
+    tmem_st8<0>(s_addr + c * 8, pk);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+  }
+  return (la.x + la.y) + (lb.x + lb.y);
+}
+
+template <bool BIAS>
+__global__ void __launch_bounds__(QF_THREADS, 1)
+qformer_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                                  const __grid_constant__ CUtensorMap map_v, const QfAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + QF_SMEM_Q;
+  uint8_t* sRing = smem + QF_SMEM_RING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QF_SMEM_BAR);
+  uint64_t* ring_full = bars;                    // [QF_STAGES]
+  uint64_t* ring_empty = bars + QF_STAGES;       // [QF_STAGES]
+  uint64_t* q_full = bars + 2 * QF_STAGES;
+  uint64_t* q_free = q_full + 1;
+  uint64_t* s_full = q_full + 2;
+  uint64_t* p_full = q_full + 3;
+  uint64_t* o_full = q_full + 4;
+  uint64_t* o_free = q_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 6);
+  float* bias_s = reinterpret_cast<float*>(smem + QF_SMEM_BIAS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int groups = p.H / QF_HG;                            // items per frame
+  const int nmain = p.Sk < QF_KMAIN ? p.Sk : QF_KMAIN;       // keys on the tensor cores
+  const bool has_tail = p.Sk > QF_KMAIN;                     // key 256 on the CUDA cores
+  const int nvb = (nmain + 63) >> 6;                         // 64-key V blocks
+  const int nks = (nmain + 15) >> 4;                         // 16-key k-steps of P V
+
+  // the zero blocks of Q' are written once; TMA only ever touches the diagonal boxes
+  for (int i = threadIdx.x; i < QF_HG * QF_QSLAB_BYTES / 16; i += QF_THREADS)
+    reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+  }
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < QF_STAGES; ++s) {
+      mbar_init(&ring_full[s], 1);
+      mbar_init(&ring_empty[s], 1);
+    }
+    mbar_init(q_full, 1); mbar_init(q_free, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 128);
+    mbar_init(o_full, 1); mbar_init(o_free, 128);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int i = 0, st = 0;
+      uint32_t ring_ph = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+        const int b = w / groups, g = w - b * groups;
+        const int col0 = g * QF_HG * QF_D;
+        mbar_wait(q_free, (i & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, QF_HG * QF_QBOX_BYTES);
+#pragma unroll
+        for (int h = 0; h < QF_HG; ++h)
+          tma_load_3d(sQ + h * (QF_QSLAB_BYTES + QF_QBOX_BYTES), &map_q, q_full, col0 + h * QF_D, 0, b);
+#pragma unroll 1
+        for (int h = 0; h < QF_HG; ++h) {                      // K_h: keys [0,256) as two 128-row boxes
+          mbar_wait(&ring_empty[st], ring_ph ^ 1);
+          mbar_arrive_expect_tx(&ring_full[st], QF_STAGE_BYTES);
+          uint8_t* dst = sRing + st * QF_STAGE_BYTES;
+          tma_load_3d(dst, &map_k, &ring_full[st], col0 + h * QF_D, 0, b);
+          tma_load_3d(dst + QF_STAGE_BYTES / 2, &map_k, &ring_full[st], col0 + h * QF_D, 128, b);
+          if (++st == QF_STAGES) { st = 0; ring_ph ^= 1; }
+        }
+#pragma unroll 1
+        for (int vb = 0; vb < nvb; ++vb) {                     // V block: 64 keys x 4 heads
+          mbar_wait(&ring_empty[st], ring_ph ^ 1);
+          mbar_arrive_expect_tx(&ring_full[st], QF_STAGE_BYTES);
+          uint8_t* dst = sRing + st * QF_STAGE_BYTES;
+#pragma unroll
+          for (int h = 0; h < QF_HG; ++h)
+            tma_load_3d(dst + h * (QF_STAGE_BYTES / QF_HG), &map_v, &ring_full[st], col0 + h * QF_D, vb * 64, b);
+          if (++st == QF_STAGES) { st = 0; ring_ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 256) | (1u << 16);       // B (= V') is MN-major
+      const uint32_t q_addr = smem_u32(sQ), ring_addr = smem_u32(sRing);
+      int i = 0, st = 0;
+      uint32_t ring_ph = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+        mbar_wait(q_full, i & 1);
+#pragma unroll 1
+        for (int h = 0; h < QF_HG; ++h) {
+          mbar_wait(&ring_full[st], ring_ph);
+          tc_fence_after();
+          const uint32_t k_addr = ring_addr + st * QF_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = umma_desc_sw128(q_addr + h * QF_QSLAB_BYTES + ks * 32);
+            const uint64_t db = umma_desc_sw128(k_addr + ks * 32);
+            umma_bf16_ss(tmem_base + QF_COL_S, da, db, idesc_s, (h | ks) ? 1u : 0u);
+          }
+          umma_commit(&ring_empty[st]);
+          if (++st == QF_STAGES) { st = 0; ring_ph ^= 1; }
+        }
+        umma_commit(s_full);
+        umma_commit(q_free);
+        mbar_wait(p_full, i & 1);
+        mbar_wait(o_free, (i & 1) ^ 1);                        // the epilogue of item i-1 has read its O
+        tc_fence_after();
+        int kk = 0;
+#pragma unroll 1
+        for (int vb = 0; vb < nvb; ++vb) {
+          mbar_wait(&ring_full[st], ring_ph);
+          tc_fence_after();
+          const uint32_t v_addr = ring_addr + st * QF_STAGE_BYTES;
+#pragma unroll 1
+          for (int ks = 0; ks < 4 && kk < nks; ++ks, ++kk) {
+            const uint64_t db = umma_desc_mn_sw128(v_addr + ks * 2048, QF_STAGE_BYTES / QF_HG, 1024);
+            umma_bf16_ts(tmem_base + QF_COL_O, tmem_base + QF_COL_S + kk * 8, db, idesc_pv, kk ? 1u : 0u);
+          }
+          umma_commit(&ring_empty[st]);
+          if (++st == QF_STAGES) { st = 0; ring_ph ^= 1; }
+        }
+        umma_commit(o_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ softmax + epilogue (warp = head, lane = query)
+    const int h = warp;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(h * 32) << 16);
+    const uint32_t s_addr = lane_base + QF_COL_S;
+    const float sl2 = p.scale_log2;
+    int i = 0;
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+      const int b = w / groups, g = w - b * groups;
+      const int col = (g * QF_HG + h) * QF_D;
+      float* bias = bias_s + (i & 1) * QF_BIAS_STRIDE;
+      if (BIAS) {                                              // additive mask in log2 units; -inf beyond the last key
+        for (int j = threadIdx.x; j < QF_BIAS_STRIDE; j += 128) {
+          float bj = -INFINITY;
+          if (j < p.Sk) bj = p.mask ? qf_mask_log2(__ldg(p.mask + (long long)b * p.Sk + j)) : 0.f;
+          bias[j] = bj;
+        }
+      }
+      // key 256: its score is a 64-long dot product of this thread's query row
+      float s_tail = 0.f;
+      if (has_tail)
+        s_tail = qf_dot64(p.q + ((long long)b * QF_SQ + lane) * p.ldq + col,
+                          p.k + ((long long)b * p.Sk + QF_KMAIN) * p.ldk + col);
+      if (BIAS) named_bar_sync(1, 128);
+      mbar_wait_parked(s_full, i & 1);
+      tc_fence_after();
+      float m = qf_row_max<BIAS>(s_addr, bias, sl2);
+      if (!BIAS) m *= sl2;
+      float t_tail = -INFINITY;
+      if (has_tail) {
+        t_tail = BIAS ? fmaf(s_tail, sl2, bias[QF_KMAIN]) : s_tail * sl2;
+        m = fmaxf(m, t_tail);
+      }
+      float l = qf_exp_row<BIAS>(s_addr, bias, sl2, -m);
+      const float p_tail = has_tail ? ex2_approx(t_tail - m) : 0.f;
+      l += p_tail;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // ---- epilogue: O[q, 64h .. 64h+63] (+ the tail key's term) / l
+      uint4 vt[8];
+      if (has_tail) {
+        const uint4* vrow = reinterpret_cast<const uint4*>(p.v + ((long long)b * p.Sk + QF_KMAIN) * p.ldv + col);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) vt[c] = __ldg(vrow + c);
+      }
+      const float inv = 1.f / l;
+      mbar_wait_parked(o_full, i & 1);
+      tc_fence_after();
+      uint32_t o[64];
+      tmem_ld32<0>(lane_base + QF_COL_O + h * 64, o);
+      tmem_ld32<32>(lane_base + QF_COL_O + h * 64 + 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_relaxed(o_free);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * QF_SQ + lane) * p.ldo + col);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[c * 8 + e]);
+        if (has_tail) {
+          const uint32_t ws[4] = {vt[c].x, vt[c].y, vt[c].z, vt[c].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ws[e]));
+            f[2 * e] = fmaf(p_tail, fv.x, f[2 * e]);
+            f[2 * e + 1] = fmaf(p_tail, fv.y, f[2 * e + 1]);
+          }
+        }
+        dst[c] = make_uint4(pack_bf16(f[0] * inv, f[1] * inv), pack_bf16(f[2] * inv, f[3] * inv),
+                            pack_bf16(f[4] * inv, f[5] * inv), pack_bf16(f[6] * inv, f[7] * inv));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 qf_encode_fn() {
+  static std::atomic<PFN_cuTensorMapEncodeTiled_v12000> fn{nullptr};
+  PFN_cuTensorMapEncodeTiled_v12000 f = fn.load(std::memory_order_acquire);
+  if (f) return f;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  f = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  fn.store(f, std::memory_order_release);
+  return f;
+}
+
+static std::atomic<int> g_qf_attention_tc{1};
+
+bool qf_cross_attention_tc_eligible(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                    const void* out, int64_t ldo, int B, int H, int Sq, int Sk, int D, float scale) {
+  if (!g_qf_attention_tc.load()) return false;
+  if (Sq != QF_SQ || D != QF_D || H % QF_HG != 0 || Sk <= 64 || Sk > QF_SK_MAX || !(scale > 0.f) || B <= 0) return false;
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return false;
+  if (ldq < (int64_t)H * D || ldk < (int64_t)H * D || ldv < (int64_t)H * D || ldo < (int64_t)H * D) return false;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16) return false;
+  return true;
+}
+
+int qf_cross_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                          int64_t ldo, const float* mask, int B, int H, int Sk, float scale, cudaStream_t stream) {
+  auto fn = qf_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return TGB_ECUDA;
+  }
+  // [frame][row][column] views: rows beyond a frame's last one are out of bounds (zero-filled), never the next frame's
+  CUtensorMap map_q, map_k, map_v;
+  const cuuint32_t estr[3] = {1, 1, 1};
+  struct Spec { CUtensorMap* map; const void* base; int64_t ld; int rows; cuuint32_t box_rows; const char* what; };
+  const Spec specs[3] = {{&map_q, q, ldq, QF_SQ, QF_SQ, "q"}, {&map_k, k, ldk, Sk, 128, "k"}, {&map_v, v, ldv, Sk, 64, "v"}};
+  for (const Spec& s : specs) {
+    cuuint64_t dims[3] = {(cuuint64_t)H * QF_D, (cuuint64_t)s.rows, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)s.ld * 2, (cuuint64_t)s.rows * (cuuint64_t)s.ld * 2};
+    cuuint32_t box[3] = {64, s.box_rows, 1};
+    CUresult r = fn(s.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(s.base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("attention (tcgen05 cross): cuTensorMapEncodeTiled failed for %s (CUresult %d)", s.what, (int)r);
+      return TGB_ECUDA;
+    }
+  }
+  TGB_ONCE_PER_DEVICE({
+    TGB_CUDA(cudaFuncSetAttribute(qformer_cross_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM_TOTAL));
+    TGB_CUDA(cudaFuncSetAttribute(qformer_cross_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QF_SMEM_TOTAL));
+  });
+  QfAttnParams p;
+  p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
+  p.out = (__nv_bfloat16*)out; p.mask = mask;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+  p.B = B; p.H = H; p.Sk = Sk;
+  p.num_items = B * (H / QF_HG);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
+  if (mask || Sk < QF_KMAIN)
+    qformer_cross_attention_tc_kernel<true><<<grid, QF_THREADS, QF_SMEM_TOTAL, stream>>>(map_q, map_k, map_v, p);
+  else
+    qformer_cross_attention_tc_kernel<false><<<grid, QF_THREADS, QF_SMEM_TOTAL, stream>>>(map_q, map_k, map_v, p);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
+}
+
+}  // namespace tgb
+
+/* 1 = the 32-query / <= 257-key / d = 64 shapes of tgb_attention_bf16 run the tcgen05 kernel (default), 0 = they run the
+ * generic mma.sync kernel like every other shape (cross-check). */
+extern "C" int tgb_attention_set_tc(int on) {
+  tgb::g_qf_attention_tc = on ? 1 : 0;
+  return TGB_OK;
+}

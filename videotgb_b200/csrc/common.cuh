@@ -48,6 +48,13 @@ int cuda_status(cudaError_t e, const char* what);
 int check_device();      // TGB_OK if the current device is sm_100, else TGB_EARCH
 int sm_count();
 
+// attention_qf_tc.cu: tcgen05 form of tgb_attention_bf16 for the Q-Former cross-attention shape (32 queries, d = 64,
+// H % 4 == 0, 64 < Sk <= 257); tgb_attention_bf16 dispatches to it when `eligible` says so.
+bool qf_cross_attention_tc_eligible(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                    const void* out, int64_t ldo, int B, int H, int Sq, int Sk, int D, float scale);
+int qf_cross_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                          int64_t ldo, const float* mask, int B, int H, int Sk, float scale, cudaStream_t stream);
+
 // ------------------------------------------------------------------ small device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

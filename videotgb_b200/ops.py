@@ -543,6 +543,12 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor])
     return out
 
 
+def attention_set_tc(on: bool) -> None:
+    """Test knob: True (default) = the Q-Former cross-attention shape of `attention` (32 queries, d = 64, heads % 4 == 0,
+    64 < Sk <= 257) runs the tcgen05 kernel; False = the generic mma.sync kernel (cross-check)."""
+    check(_lib.load().tgb_attention_set_tc(1 if on else 0))
+
+
 def vit_attention_set_variant(variant: int) -> None:
     """Test knob: 0 = ping-pong kernel (default), 1 = one-shot kernel."""
     check(_lib.load().tgb_vit_attention_set_variant(int(variant)))
