@@ -645,6 +645,9 @@ def test_qformer_cross_attention_tcgen05(b, h, sk, masked, scale_in):
     wide = torch.zeros(b * sq, h * d + 64, dtype=torch.bfloat16, device=DEV)
     ops.attention(qd, kvd[:, : h * d], kvd[:, h * d:], b, h, sq, sk, d, scale, md, out=wide[:, : h * d])
     assert torch.equal(wide[:, : h * d], got) and not wide[:, h * d:].any()
+    if not masked:        # an all-zero additive mask (encoder_attention_mask of ones) is bit-identical to no mask
+        zero = ops.attention(qd, kvd[:, : h * d], kvd[:, h * d:], b, h, sq, sk, d, scale, torch.zeros(b, sk, device=DEV))
+        assert torch.equal(zero, got)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])

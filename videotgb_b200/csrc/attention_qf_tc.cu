@@ -87,10 +87,10 @@ __device__ __forceinline__ float qf_row_max(uint32_t s_addr, const float* bias, 
     for (int j = 0; j < 32; j += 4) {
       if (BIAS) {
         const float4 bj = *reinterpret_cast<const float4*>(bias + c * 32 + j);
-        m0 = fmaxf(m0, fmaf(__uint_as_float(v[j]), sl2, bj.x));
-        m1 = fmaxf(m1, fmaf(__uint_as_float(v[j + 1]), sl2, bj.y));
-        m2 = fmaxf(m2, fmaf(__uint_as_float(v[j + 2]), sl2, bj.z));
-        m3 = fmaxf(m3, fmaf(__uint_as_float(v[j + 3]), sl2, bj.w));
+        m0 = fmaxf(m0, __fmaf_rn(__uint_as_float(v[j]), sl2, bj.x));
+        m1 = fmaxf(m1, __fmaf_rn(__uint_as_float(v[j + 1]), sl2, bj.y));
+        m2 = fmaxf(m2, __fmaf_rn(__uint_as_float(v[j + 2]), sl2, bj.z));
+        m3 = fmaxf(m3, __fmaf_rn(__uint_as_float(v[j + 3]), sl2, bj.w));
       } else {
         m0 = fmaxf(m0, __uint_as_float(v[j]));
         m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
@@ -108,7 +108,6 @@ __device__ __forceinline__ float qf_row_max(uint32_t s_addr, const float* bias, 
 template <bool BIAS>
 __device__ __forceinline__ float qf_exp_row(uint32_t s_addr, const float* bias, float sl2, float negm) {
   float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-  const float2 s2 = make_float2(sl2, sl2), m2 = make_float2(negm, negm);
   uint32_t cur[16], nxt[16];
   tmem_ld16<0>(s_addr, cur);
 #pragma unroll 1
@@ -121,9 +120,14 @@ __device__ __forceinline__ float qf_exp_row(uint32_t s_addr, const float* bias, 
       const float2 sj = make_float2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]));
       if (BIAS) {
         const float2 bj = *reinterpret_cast<const float2*>(bias + c * 16 + 2 * j);
-        x[j] = __fadd2_rn(__ffma2_rn(sj, s2, bj), m2);
+        x[j].x = __fadd_rn(__fmaf_rn(sj.x, sl2, bj.x), negm);
+        x[j].y = __fadd_rn(__fmaf_rn(sj.y, sl2, bj.y), negm);
       } else {
-        x[j] = __ffma2_rn(sj, s2, m2);
+        // two roundings, exactly the BIAS form with a zero bias, so that an all-ones mask and no mask give bit-identical
+        // results.  Scalar _rn intrinsics on purpose: ptxas contracts the packed mul.rn.f32x2 + add.rn.f32x2 pair into
+        // one FFMA2 (observed in SASS), the scalar forms are never fused; the phase is MUFU-bound either way.
+        x[j].x = __fadd_rn(__fmul_rn(sj.x, sl2), negm);
+        x[j].y = __fadd_rn(__fmul_rn(sj.y, sl2), negm);
       }
     }
 #pragma unroll
@@ -309,14 +313,14 @@ qformer_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, con
       mbar_wait_parked(s_full, i & 1);
       tc_fence_after();
       float m = qf_row_max<BIAS>(s_addr, bias, sl2);
-      if (!BIAS) m *= sl2;
+      if (!BIAS) m = __fmul_rn(m, sl2);
       float t_tail = -INFINITY;
       if (has_tail) {
-        t_tail = BIAS ? fmaf(s_tail, sl2, bias[QF_KMAIN]) : s_tail * sl2;
+        t_tail = BIAS ? __fmaf_rn(s_tail, sl2, bias[QF_KMAIN]) : __fmul_rn(s_tail, sl2);
         m = fmaxf(m, t_tail);
       }
       float l = qf_exp_row<BIAS>(s_addr, bias, sl2, -m);
-      const float p_tail = has_tail ? ex2_approx(t_tail - m) : 0.f;
+      const float p_tail = has_tail ? ex2_approx(__fsub_rn(t_tail, m)) : 0.f;
       l += p_tail;
       tmem_st_wait();
       tc_fence_before();
