@@ -48,6 +48,14 @@ def main():
         print(f"cross 32x257, {f} frames, {'tcgen05 ' if tc else 'mma.sync'}: {ms * 1e3:7.1f} us  {nbytes / ms / 1e6:7.0f} GB/s "
               f"({nbytes / ms / 1e6 / 6550.1:.2f} of the copy peak)")
     ops.attention_set_tc(True)
+    if os.environ.get("TGB_QF_DBG"):       # timing experiments (wrong results): which resource bounds the tcgen05 kernel
+        from videotgb_b200 import _lib
+        lib = _lib.load()
+        for bits, what in ((1, "no operand loads after the first ring fill"), (2, "no softmax arithmetic"),
+                           (3, "neither loads nor softmax"), (4, "no output stores"), (0, "normal")):
+            lib.tgb_debug_qf_attention_dbg(bits)
+            ms = graph_time(cross)
+            print(f"   dbg {bits} ({what}): {ms * 1e3:7.1f} us")
     qkv = torch.randn(f * 32, 3 * h * d, device="cuda").to(torch.bfloat16)
     ms = graph_time(lambda: ops.attention(qkv[:, : h * d], qkv[:, h * d: 2 * h * d], qkv[:, 2 * h * d:], f, h, 32, 32, d, d ** -0.5, out=out))
     nbytes = f * 32 * 4 * h * d * 2
