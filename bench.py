@@ -380,6 +380,22 @@ def hbm_roofline(ctx):
     row("of_patch_reduce_kernel (A1 flow embedding: conv+fc reassociated)", 401408, 1024, "candidate flow frame",
         timeit(lambda: ops.of_patch_reduce(flow, fcw)))
     del flow
+    # Q-Former cross attention (tcgen05, HBM-bound: K|V of a frame are read once).  Three K|V buffers in rotation: 2.4 GB,
+    # nothing of a launch's input is left in the L2 from the previous one.
+    fq, hq, dq = 1024, 12, 64
+    qc = torch.randn(fq * 32, hq * dq, device=dev).to(torch.bfloat16)
+    kvs = [torch.randn(fq * 257, 2 * hq * dq, device=dev).to(torch.bfloat16) for _ in range(3)]
+    ctx_out = torch.empty(fq * 32, hq * dq, dtype=torch.bfloat16, device=dev)
+    turn = [0]
+
+    def cross():
+        kv = kvs[turn[0] % 3]
+        turn[0] += 1
+        ops.attention(qc, kv[:, : hq * dq], kv[:, hq * dq:], fq, hq, 32, 257, dq, dq ** -0.5, out=ctx_out)
+
+    row("qformer_cross_attention_tc_kernel (A14 cross attention, 32 queries x 257 image tokens, 12 heads of 64)",
+        257 * 2 * hq * dq * 2 + 2 * 32 * hq * dq * 2, fq, "frame", timeit(cross, iters=9))
+    del qc, kvs, ctx_out
     torch.cuda.empty_cache()
     return {"peak_source": "MEASURED_PEAKS.json hbm_gbs" if ctx.peaks else "fallback 6550", "unit": "GB/s",
             "l2": "buffers_larger_than_l2",
