@@ -53,7 +53,7 @@ def main():
     for rnd in range(7):
         for name, m, n, k, epi in SHAPES:
             fn = runner(name, epi)
-            for vname, bal in (("rowblocks", 2), ("balanced", 1), ("roundrobin", 0)):
+            for vname, bal in (("groups", 3), ("rowblocks", 2), ("balanced", 1), ("roundrobin", 0)):
                 ops.gemm_set_schedule(bal)
                 fn()
                 res.setdefault((name, vname), []).append(timeit(fn))
@@ -63,7 +63,7 @@ def main():
     for name, m, n, k, epi in SHAPES:
         fl = 2.0 * m * n * k
         line = f"{name:10s}"
-        for vname in ("rowblocks", "balanced", "roundrobin", "cublas"):
+        for vname in ("groups", "rowblocks", "balanced", "roundrobin", "cublas"):
             if (name, vname) in res:
                 ms = statistics.median(res[(name, vname)])
                 line += f"  {vname}: {ms:.3f} ms {fl / ms / 1e9:6.0f} TF"

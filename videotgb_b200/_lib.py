@@ -99,7 +99,7 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
         fn.restype = res
     _lib = lib
-    sched = {"roundrobin": 0, "balanced": 1, "rowblocks": 2}.get(os.environ.get("TGB_GEMM_SCHEDULE", ""))   # A/B knob
+    sched = {"roundrobin": 0, "balanced": 1, "rowblocks": 2, "groups": 3}.get(os.environ.get("TGB_GEMM_SCHEDULE", ""))   # A/B knob
     if sched is not None:
         lib.tgb_gemm_set_schedule(sched)
     if os.environ.get("TGB_GEMM_RESID_PIECE"):                                                                # A/B knob

@@ -228,6 +228,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const int n_blocks = p.num_n_blocks;
   const int n_start = cluster_id % n_blocks;
   auto tile_at = [&](int round) {
+    if (sched_shift == -2) {
+      // Group mode (A/B knob): the grid is a whole number of groups of NB clusters; a group owns one A row block per round
+      // and its members rotate through the N tiles, so the clusters that share a row block never change and stay within
+      // one half-width tile of each other.
+      const int grp = cluster_id / n_blocks, pos = cluster_id - grp * n_blocks;
+      return round * num_clusters + grp * n_blocks + (pos + round) % n_blocks;
+    }
     if (sched_shift < 0) {
       const int pass = round / n_blocks;
       int n = round - pass * n_blocks + n_start;
@@ -916,11 +923,15 @@ static int launch_gemm_ew(const void* A, long long lda, const void* W, long long
   TGB_ONCE_PER_DEVICE(TGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_clusters = sm_count() / CG;
-  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  int clusters = tiles < max_clusters ? tiles : max_clusters;
   const int sched = g_sched_balanced.load();
   p.sched_shift = sched ? balanced_shift(clusters, p.num_m_blocks, p.num_n_blocks,
                                          BN == 256 && p.N - (p.num_n_blocks - 1) * BN <= BN / 2) : 0;
   if (sched == 2 && row_block_schedule_ok(clusters, p.num_m_blocks)) p.sched_shift = -1;
+  if (sched == 3 && p.num_n_blocks >= 2 && clusters >= p.num_n_blocks && tiles >= 4 * clusters) {
+    clusters = clusters / p.num_n_blocks * p.num_n_blocks;
+    p.sched_shift = -2;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(Cfg::THREADS);
@@ -1041,8 +1052,8 @@ extern "C" int tgb_gemm_set_epilogue_warps(int warps) {
 }
 
 extern "C" int tgb_gemm_set_schedule(int mode) {
-  if (mode < 0 || mode > 2) {
-    set_last_error("schedule must be 0 (round-robin), 1 (balanced tiles, default) or 2 (row blocks when M allows)");
+  if (mode < 0 || mode > 3) {
+    set_last_error("schedule must be 0 (round-robin), 1 (balanced tiles, default), 2 (row blocks when M allows) or 3 (fixed groups)");
     return TGB_EINVAL;
   }
   g_sched_balanced = mode;

@@ -370,7 +370,7 @@ def gemm_set_cta_group(cta_group: int) -> None:
 
 def gemm_set_schedule(mode) -> None:
     """1 / True = balanced persistent tile schedule (default); 0 / False = plain round-robin; 2 = whole A row blocks per
-    cluster when M allows (measured slower).  A/B knob."""
+    cluster when M allows (measured slower); 3 = fixed groups of N-block-count clusters sharing an A row block.  A/B knob."""
     check(_lib.load().tgb_gemm_set_schedule(1 if mode is True else int(mode)))
 
 
