@@ -169,7 +169,10 @@ TGB_API int tgb_layernorm_f32(const float* x, int64_t ldx, const float* gamma, c
 /* ---------------------------------------------------------------- attention ---------------------------
  * softmax(Q K^T * scale + mask) V for one (batch, head) per CTA; fp32 softmax, bf16 tensor-core operands.
  * (xblip2.py:174-189 ViT, :647-686 Q-Former).  q/k/v: bf16, row (b*S + i), head h at columns [h*D, (h+1)*D).
- * mask: f32 additive [B, Sk] or NULL.  out: bf16 [B*Sq, ldo].  D in {64, 88}; long key sequences stream K/V through shared memory.               */
+ * mask: f32 additive [B, Sk] or NULL.  out: bf16 [B*Sq, ldo].  D in {64, 88}; long key sequences stream K/V through shared memory.
+ * The Q-Former cross-attention shape (Sq = 32, D = 64, H % 4 == 0, 64 < Sk <= 257: xblip2.py:647-686 with the 257 image
+ * tokens as keys) and its self-attention shape (Sq = Sk = 32, D = 64, H % 4 == 0) run on tcgen05 (four heads per 128-row
+ * MMA tile, csrc/attention_qf_tc.cu); same contract.                                                                          */
 TGB_API int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                        void* out, int64_t ldo, const float* mask, int B, int H, int Sq, int Sk, int D, float scale,
                        tgb_stream_t stream);

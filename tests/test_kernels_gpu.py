@@ -650,6 +650,51 @@ def test_qformer_cross_attention_tcgen05(b, h, sk, masked, scale_in):
         assert torch.equal(zero, got)
 
 
+@pytest.mark.parametrize("b,h,masked,scale_in", [(1, 4, False, 1.0), (3, 12, False, 1.0), (3, 12, True, 1.0), (2, 8, True, 3.0),
+                                                 (60, 12, False, 1.0), (200, 12, True, 1.0), (500, 12, False, 2.0)])
+def test_qformer_self_attention_tcgen05(b, h, masked, scale_in):
+    """The tcgen05 form of `ops.attention` for the Q-Former self-attention shape (32 x 32, d = 64: four heads stacked on the
+    query AND the key side of one 128 x 128 score tile, block-diagonal P as the tensor-memory operand of P V) vs torch and vs
+    the mma.sync kernel, reading q / k / v as column slices of the fused projection.  200 / 500 frames = 4-10 items per CTA:
+    both tensor-memory slots, the three-stage ring and every barrier wrap."""
+    d, s_ = 64, 32
+    g = torch.Generator().manual_seed(b * 77 + h)
+    qkv = (torch.randn(b * s_, 3 * h * d, generator=g) * scale_in).to(torch.bfloat16)
+    x = qkv.float().view(b, s_, 3, h, d)
+    x[:, 31, 1] = x[:, 5, 0] * 0.8                 # the last key aligned with query 5 of every head
+    qkv = x.view(b * s_, 3 * h * d).to(torch.bfloat16)
+    q, k, v = qkv[:, : h * d], qkv[:, h * d: 2 * h * d], qkv[:, 2 * h * d:]
+    mask = None
+    if masked:
+        mask = torch.zeros(b, s_)
+        for j in range(b):
+            mask[j, s_ - 1 - (j % 9):] = -10000.0
+            mask[j, (3 * j) % 20] = torch.finfo(torch.float32).min
+        mask[b - 1, :] = torch.finfo(torch.float32).min          # a fully masked element: uniform softmax, not NaN
+    scale = d ** -0.5
+    want = _attn_ref(q, k, v, b, h, s_, s_, d, scale, mask)
+    assert torch.isfinite(want).all()
+    qd = qkv.to(DEV)
+    md = None if mask is None else mask.to(DEV)
+    args = (qd[:, : h * d], qd[:, h * d: 2 * h * d], qd[:, 2 * h * d:], b, h, s_, s_, d, scale)
+    got = ops.attention(*args, md)
+    ops.attention_set_tc(False)
+    try:
+        legacy = ops.attention(*args, md)
+        torch.cuda.synchronize()
+    finally:
+        ops.attention_set_tc(True)
+    assert torch.isfinite(got.float()).all()
+    err, cos = _relerr(got.cpu(), want), _cos(got.cpu(), want)
+    assert err < 1.5e-2 and cos > 0.9999, (err, cos)
+    assert _relerr(got.cpu(), legacy.cpu()) < 1.5e-2
+    wide = torch.zeros(b * s_, h * d + 64, dtype=torch.bfloat16, device=DEV)
+    ops.attention(*args, md, out=wide[:, : h * d])
+    assert torch.equal(wide[:, : h * d], got) and not wide[:, h * d:].any()
+    if not masked:
+        assert torch.equal(ops.attention(*args, torch.zeros(b, s_, device=DEV)), got)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("frames,scale_in,late_peak", [(1, 1.0, False), (3, 1.0, False), (19, 2.5, False), (2, 1.0, True),
                                                        (150, 1.0, False), (300, 1.0, True)])

@@ -1,4 +1,4 @@
-"""Q-Former attention shapes: cross on the tcgen05 kernel and on the generic mma.sync kernel, self on the generic kernel: cross (32 queries x 257 image tokens) and self (32 x 32), 1024 frames.
+"""Q-Former attention shapes: cross and self on the tcgen05 kernels and on the generic mma.sync kernel: cross (32 queries x 257 image tokens) and self (32 x 32), 1024 frames.
 
     python tools/attn_small_bench.py       (B200 box; CUDA-graph replays, algorithmic bytes / time vs MEASURED_PEAKS hbm_gbs)
 """
@@ -57,9 +57,13 @@ def main():
             ms = graph_time(cross)
             print(f"   dbg {bits} ({what}): {ms * 1e3:7.1f} us")
     qkv = torch.randn(f * 32, 3 * h * d, device="cuda").to(torch.bfloat16)
-    ms = graph_time(lambda: ops.attention(qkv[:, : h * d], qkv[:, h * d: 2 * h * d], qkv[:, 2 * h * d:], f, h, 32, 32, d, d ** -0.5, out=out))
     nbytes = f * 32 * 4 * h * d * 2
-    print(f"self  32x32,  {f} frames: {ms * 1e3:7.1f} us  {nbytes / ms / 1e6:7.0f} GB/s ({nbytes / ms / 1e6 / 6550.1:.2f} of the copy peak; 201 MB, L2 resident)")
+    for tc in (True, False):
+        ops.attention_set_tc(tc)
+        ms = graph_time(lambda: ops.attention(qkv[:, : h * d], qkv[:, h * d: 2 * h * d], qkv[:, 2 * h * d:], f, h, 32, 32, d, d ** -0.5, out=out))
+        print(f"self  32x32,  {f} frames, {'tcgen05 ' if tc else 'mma.sync'}: {ms * 1e3:7.1f} us  {nbytes / ms / 1e6:7.0f} GB/s "
+              f"({nbytes / ms / 1e6 / 6550.1:.2f} of the copy peak; 201 MB, partly L2 resident)")
+    ops.attention_set_tc(True)
 
 
 if __name__ == "__main__":

@@ -430,6 +430,8 @@ extern "C" int tgb_attention_bf16(const void* q, int64_t ldq, const void* k, int
   // the Q-Former cross-attention shape (32 queries x <= 257 image tokens) runs on tcgen05 (attention_qf_tc.cu)
   if (qf_cross_attention_tc_eligible(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Sq, Sk, D, scale))
     return qf_cross_attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, mask, B, H, Sk, scale, (cudaStream_t)stream);
+  if (qf_self_attention_tc_eligible(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Sq, Sk, D, scale))
+    return qf_self_attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, mask, B, H, scale, (cudaStream_t)stream);
   AttnParams p;
   p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
   p.out = (__nv_bfloat16*)out; p.mask = mask;

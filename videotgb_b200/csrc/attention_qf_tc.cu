@@ -391,6 +391,213 @@ qformer_cross_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, con
   }
 }
 
+// =====================================================================================================================
+// Q-Former SELF attention on tcgen05 (xblip2.py:612-695 with the 32 query rows as keys): Sq = Sk = 32, D = 64, H % 4 == 0.
+// Same item (one frame x four heads = 128 MMA rows), but with 32 keys per head the heads are stacked on the KEY side too
+// and the block structure moves from Q to P:
+//   S  [128 x 128] = Q4 K4^T          Q4 / K4 = [(h,q) or (h',j)][d], plain K-major tiles: 4 MMAs (M=128, N=128, K=16);
+//                                     only the diagonal blocks S[(h,q),(h,j)] are read
+//   O  [128 x  64] = P' V4            P' = [(h,q)][(h',j)] bf16 in tensor memory, block diagonal: a thread writes its 32
+//                                     probabilities into columns of its own head, the off-diagonal zeros are written once
+//                                     per CTA; V4 = [(h',j)][d] as an MN-major operand: 8 MMAs (N = 64)
+// TMEM: two slots of S 128 | P' 64 | O 64 columns, so the softmax of item i overlaps S(i+1) and P V(i-1).  Stages of
+// 48 KB (Q4, K4, V4: twelve [32 x 64] TMA boxes) in a ring of three.
+// =====================================================================================================================
+constexpr int QS_K = 32;
+constexpr int QS_STAGES = 3;
+constexpr int QS_TILE_BYTES = 128 * 128;                   // Q4, K4 or V4
+constexpr int QS_STAGE_BYTES = 3 * QS_TILE_BYTES;          // 49152
+constexpr int QS_SMEM_BAR = QS_STAGES * QS_STAGE_BYTES;    // 147456
+constexpr int QS_SMEM_TOTAL = QS_SMEM_BAR + 256 + 1024;
+constexpr uint32_t QS_SLOT_COLS = 256, QS_COL_S = 0, QS_COL_P = 128, QS_COL_O = 192;
+
+template <bool BIAS>
+__global__ void __launch_bounds__(QF_THREADS, 1)
+qformer_self_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                                 const __grid_constant__ CUtensorMap map_v, const QfAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QS_SMEM_BAR);
+  uint64_t* st_full = bars;                      // [QS_STAGES]
+  uint64_t* st_empty = bars + QS_STAGES;         // [QS_STAGES]
+  uint64_t* s_full = bars + 2 * QS_STAGES;       // [2]
+  uint64_t* p_full = s_full + 2;                 // [2]
+  uint64_t* o_full = s_full + 4;                 // [2]
+  uint64_t* o_free = s_full + 6;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int groups = p.H / QF_HG;
+  int n_local = 0;                               // items of this CTA
+  if ((int)blockIdx.x < p.num_items) n_local = (p.num_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+  }
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < QS_STAGES; ++s) {
+      mbar_init(&st_full[s], 1);
+      mbar_init(&st_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128);
+      mbar_init(&o_full[s], 1); mbar_init(&o_free[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int i = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+        const int b = w / groups, g = w - b * groups;
+        const int col0 = g * QF_HG * QF_D;
+        const int st = i % QS_STAGES;
+        const uint32_t ph = (i / QS_STAGES) & 1;
+        mbar_wait(&st_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&st_full[st], QS_STAGE_BYTES);
+        uint8_t* dst = smem + st * QS_STAGE_BYTES;
+#pragma unroll
+        for (int h = 0; h < QF_HG; ++h) {
+          tma_load_3d(dst + h * QF_QBOX_BYTES, &map_q, &st_full[st], col0 + h * QF_D, 0, b);
+          tma_load_3d(dst + QS_TILE_BYTES + h * QF_QBOX_BYTES, &map_k, &st_full[st], col0 + h * QF_D, 0, b);
+          tma_load_3d(dst + 2 * QS_TILE_BYTES + h * QF_QBOX_BYTES, &map_v, &st_full[st], col0 + h * QF_D, 0, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ================================================================ MMA issuer:  S(0), then per item  S(i+1), P V(i)
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);        // B (= V4) is MN-major
+      const uint32_t base_addr = smem_u32(smem);
+      auto issue_s = [&](int i) {
+        const int st = i % QS_STAGES, slot = i & 1;
+        mbar_wait(&st_full[st], (i / QS_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = base_addr + st * QS_STAGE_BYTES, k_addr = q_addr + QS_TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16_ss(tmem_base + slot * QS_SLOT_COLS + QS_COL_S, umma_desc_sw128(q_addr + ks * 32),
+                       umma_desc_sw128(k_addr + ks * 32), idesc_s, ks ? 1u : 0u);
+        umma_commit(&s_full[slot]);
+      };
+      auto issue_pv = [&](int i) {
+        const int st = i % QS_STAGES, slot = i & 1;
+        const uint32_t use_ph = (i >> 1) & 1;
+        mbar_wait(&p_full[slot], use_ph);
+        mbar_wait(&o_free[slot], use_ph ^ 1);                  // the epilogue of item i-2 has read this slot's O
+        tc_fence_after();
+        const uint32_t v_addr = base_addr + st * QS_STAGE_BYTES + 2 * QS_TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16_ts(tmem_base + slot * QS_SLOT_COLS + QS_COL_O, tmem_base + slot * QS_SLOT_COLS + QS_COL_P + ks * 8,
+                       umma_desc_mn_sw128(v_addr + ks * 2048, 8192, 1024), idesc_pv, ks ? 1u : 0u);
+        umma_commit(&o_full[slot]);
+        umma_commit(&st_empty[st]);
+      };
+      if (n_local > 0) issue_s(0);
+      for (int i = 0; i < n_local; ++i) {
+        if (i + 1 < n_local) issue_s(i + 1);
+        issue_pv(i);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ softmax + epilogue (warp = head, lane = query)
+    const int h = warp;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(h * 32) << 16);
+    const float sl2 = p.scale_log2;
+    {   // the off-diagonal blocks of P' stay zero for the whole kernel
+      uint32_t z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0u;
+#pragma unroll
+      for (int slot = 0; slot < 2; ++slot) {
+        tmem_st32<0>(lane_base + slot * QS_SLOT_COLS + QS_COL_P, z);
+        tmem_st32<0>(lane_base + slot * QS_SLOT_COLS + QS_COL_P + 32, z);
+      }
+      tmem_st_wait();
+    }
+    float inv_prev = 0.f;
+    int b_prev = 0, col_prev = 0;
+    auto epilogue = [&](int i, float inv, int b, int col) {
+      const int slot = i & 1;
+      mbar_wait_parked(&o_full[slot], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t o[64];
+      tmem_ld32<0>(lane_base + slot * QS_SLOT_COLS + QS_COL_O, o);
+      tmem_ld32<32>(lane_base + slot * QS_SLOT_COLS + QS_COL_O + 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_relaxed(&o_free[slot]);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * QF_SQ + lane) * p.ldo + col);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        dst[c] = make_uint4(pack_bf16(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv),
+                            pack_bf16(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv),
+                            pack_bf16(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv),
+                            pack_bf16(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
+    };
+    int i = 0;
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x, ++i) {
+      const int b = w / groups, g = w - b * groups;
+      const int col = (g * QF_HG + h) * QF_D;
+      const int slot = i & 1;
+      float mk = 0.f;                                          // lane j holds the additive mask of key j (log2 units)
+      if (BIAS) mk = qf_mask_log2(__ldg(p.mask + (long long)b * QS_K + lane));
+      mbar_wait_parked(&s_full[slot], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[32];
+      tmem_ld32<0>(lane_base + slot * QS_SLOT_COLS + QS_COL_S + h * QS_K, sv);
+      tmem_ld_wait();
+      float t[32];
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // the same two roundings with and without a mask (see qf_exp_row)
+        t[j] = BIAS ? __fmaf_rn(__uint_as_float(sv[j]), sl2, __shfl_sync(0xffffffffu, mk, j)) : __fmul_rn(__uint_as_float(sv[j]), sl2);
+        m = fmaxf(m, t[j]);
+      }
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float p0 = ex2_approx(__fsub_rn(t[j], m)), p1 = ex2_approx(__fsub_rn(t[j + 1], m));
+        l0 += p0;
+        l1 += p1;
+        pk[j >> 1] = pack_bf16(p0, p1);
+      }
+      tmem_st16<0>(lane_base + slot * QS_SLOT_COLS + QS_COL_P + h * (QS_K / 2), pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[slot]);
+      if (i > 0) epilogue(i - 1, inv_prev, b_prev, col_prev);   // deferred by one item: P V(i-1) has had a softmax's time
+      inv_prev = 1.f / (l0 + l1);
+      b_prev = b;
+      col_prev = col;
+    }
+    if (i > 0) epilogue(i - 1, inv_prev, b_prev, col_prev);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 qf_encode_fn() {
   static std::atomic<PFN_cuTensorMapEncodeTiled_v12000> fn{nullptr};
   PFN_cuTensorMapEncodeTiled_v12000 f = fn.load(std::memory_order_acquire);
@@ -416,6 +623,59 @@ bool qf_cross_attention_tc_eligible(const void* q, int64_t ldq, const void* k, i
   if (ldq < (int64_t)H * D || ldk < (int64_t)H * D || ldv < (int64_t)H * D || ldo < (int64_t)H * D) return false;
   if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16) return false;
   return true;
+}
+
+bool qf_self_attention_tc_eligible(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                   const void* out, int64_t ldo, int B, int H, int Sq, int Sk, int D, float scale) {
+  if (!g_qf_attention_tc.load()) return false;
+  if (Sq != QF_SQ || Sk != QS_K || D != QF_D || H % QF_HG != 0 || !(scale > 0.f) || B <= 0) return false;
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return false;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16) return false;
+  return true;
+}
+
+int qf_self_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                         int64_t ldo, const float* mask, int B, int H, float scale, cudaStream_t stream) {
+  auto fn = qf_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return TGB_ECUDA;
+  }
+  CUtensorMap maps[3];
+  const void* bases[3] = {q, k, v};
+  const int64_t lds[3] = {ldq, ldk, ldv};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  for (int i = 0; i < 3; ++i) {
+    cuuint64_t dims[3] = {(cuuint64_t)H * QF_D, (cuuint64_t)QF_SQ, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)lds[i] * 2, (cuuint64_t)QF_SQ * (cuuint64_t)lds[i] * 2};
+    cuuint32_t box[3] = {64, QF_SQ, 1};
+    CUresult r = fn(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(bases[i]), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("attention (tcgen05 self): cuTensorMapEncodeTiled failed for operand %d (CUresult %d)", i, (int)r);
+      return TGB_ECUDA;
+    }
+  }
+  TGB_ONCE_PER_DEVICE({
+    TGB_CUDA(cudaFuncSetAttribute(qformer_self_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_SMEM_TOTAL));
+    TGB_CUDA(cudaFuncSetAttribute(qformer_self_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_SMEM_TOTAL));
+  });
+  QfAttnParams p;
+  p.q = (const __nv_bfloat16*)q; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
+  p.out = (__nv_bfloat16*)out; p.mask = mask;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+  p.B = B; p.H = H; p.Sk = QS_K;
+  p.num_items = B * (H / QF_HG);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.dbg = 0;
+  const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
+  if (mask)
+    qformer_self_attention_tc_kernel<true><<<grid, QF_THREADS, QS_SMEM_TOTAL, stream>>>(maps[0], maps[1], maps[2], p);
+  else
+    qformer_self_attention_tc_kernel<false><<<grid, QF_THREADS, QS_SMEM_TOTAL, stream>>>(maps[0], maps[1], maps[2], p);
+  TGB_CUDA(cudaGetLastError());
+  return TGB_OK;
 }
 
 int qf_cross_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,

@@ -54,6 +54,11 @@ bool qf_cross_attention_tc_eligible(const void* q, int64_t ldq, const void* k, i
                                     const void* out, int64_t ldo, int B, int H, int Sq, int Sk, int D, float scale);
 int qf_cross_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                           int64_t ldo, const float* mask, int B, int H, int Sk, float scale, cudaStream_t stream);
+// ... and for the Q-Former self-attention shape (Sq = Sk = 32, d = 64, H % 4 == 0)
+bool qf_self_attention_tc_eligible(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                   const void* out, int64_t ldo, int B, int H, int Sq, int Sk, int D, float scale);
+int qf_self_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                         int64_t ldo, const float* mask, int B, int H, float scale, cudaStream_t stream);
 
 // ------------------------------------------------------------------ small device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -30,8 +30,8 @@ TGB_API int tgb_gemm_set_resid_piece(int width);
  * 3 = CTA-pair kernel (cta_group::2), 4 = split-row ping-pong kernel (two threads per query row), 5 = ping-pong kernel
  * with the software-pipelined exp pass.  Measurements: profiles/r2_attention_experiments.txt. */
 TGB_API int tgb_vit_attention_set_variant(int variant);
-/* tgb_attention_bf16: 1 = the Q-Former cross-attention shape (32 queries, d = 64, H % 4 == 0, 64 < Sk <= 257) runs the
- * tcgen05 kernel (default), 0 = it runs the generic mma.sync kernel like every other shape (cross-check). */
+/* tgb_attention_bf16: 1 = the Q-Former shapes (32 queries, d = 64, H % 4 == 0; 64 < Sk <= 257 or Sk == 32) run the
+ * tcgen05 kernels (default), 0 = they run the generic mma.sync kernel like every other shape (cross-check). */
 TGB_API int tgb_attention_set_tc(int on);
 /* split-row kernel: 1 = prefetch the next item's operands into the L2 (measured 30 % slower), 0 = off (default). */
 TGB_API int tgb_vit_attention_set_prefetch(int on);
