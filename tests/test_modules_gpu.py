@@ -229,6 +229,45 @@ def test_instruct_qformer(vit2, gold):
         m(input_ids=None, query_embeds=None)
 
 
+def test_sampler_graph_replay_matches_eager():
+    """The sampler's layer stack is captured as a CUDA graph the second time a shape is seen: calls 2 and 3 (capture,
+    replay) on NEW inputs are bit-identical to the eager path, a different question length falls back to eager / a second
+    graph, and a weight load drops the graphs."""
+    sd = syn.sampler_state_dict()
+    m = RopeBertModel(NS(fusion_layer=6, encoder_width=768)).to(DEV)
+    m.load_state_dict(sd)
+    of, of_mask, of_len, qids, qmask = cases.sampler_inputs()
+
+    def call(model, k, tq=None):
+        ofk = (of + 0.05 * k * torch.randn(of.shape, generator=torch.Generator().manual_seed(k))).to(DEV)
+        ids = torch.roll(qids, k, dims=1)
+        msk = qmask
+        if tq is not None:
+            ids, msk = ids[:, :tq], qmask[:, :tq]
+        return model(encoder_embeds=ofk, attention_mask=of_mask.to(DEV), encoder_hidden_states=ids.to(DEV),
+                     encoder_attention_mask=msk.to(DEV), mode="fusion")
+
+    eager = RopeBertModel(NS(fusion_layer=6, encoder_width=768)).to(DEV)
+    eager.load_state_dict(sd)
+    eager.graph_max_tokens = 0
+    for k in range(4):
+        seq, logits = call(m, k)
+        seq_e, logits_e = call(eager, k)
+        assert torch.equal(seq, seq_e) and torch.equal(logits, logits_e), k
+    assert len(m._graphs.entries) == 1 and len(eager._graphs.entries) == 0
+    tq = qids.shape[1] - 3
+    for k in range(3):
+        seq, logits = call(m, 10 + k, tq)
+        seq_e, logits_e = call(eager, 10 + k, tq)
+        assert torch.equal(seq, seq_e) and torch.equal(logits, logits_e)
+    assert len(m._graphs.entries) == 2
+    m.load_state_dict(sd)
+    assert len(m._graphs.entries) == 0
+    seq, logits = call(m, 1)
+    seq_e, logits_e = call(eager, 1)
+    assert torch.equal(seq, seq_e) and torch.equal(logits, logits_e)
+
+
 @pytest.mark.parametrize("mode", ["fusion", "multi_modal"])
 def test_sampler(gold, mode):
     meta, arr = gold

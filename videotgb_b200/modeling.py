@@ -129,15 +129,26 @@ class _GraphCache:
 
     def __init__(self):
         self.entries = {}
+        self.seen = {}
 
     def clear(self):
         self.entries.clear()
+        self.seen.clear()
 
-    def run(self, key, inputs, body):
+    def run(self, key, inputs, body, min_seen: int = 1):
+        """`min_seen` > 1: a key is captured only at its `min_seen`-th occurrence and runs eagerly before that (callers
+        whose shapes may change from call to call -- e.g. the padded question length -- do not pay a capture per call)."""
         ent = self.entries.pop(key, None)
         if ent is not None:
             self.entries[key] = ent                            # most recently used goes last
         else:
+            if min_seen > 1:
+                n = self.seen.get(key, 0) + 1
+                if len(self.seen) > 64:
+                    self.seen.clear()
+                self.seen[key] = n
+                if n < min_seen:
+                    return tuple(body(*inputs))
             while len(self.entries) >= self.MAX_ENTRIES:
                 self.entries.pop(next(iter(self.entries)))
             static_in = [t.clone() for t in inputs]

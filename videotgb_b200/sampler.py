@@ -45,6 +45,7 @@ class RopeBertModel(_KernelModule):
         max_pos = _cfg(config, "max_position_embeddings", 512)
         types = _cfg(config, "type_vocab_size", 2)
         self.head_dim = d // self.heads
+        self.graph_max_tokens = 8192       # layer stacks over at most this many rows replay a CUDA graph (0 disables)
         self.flow_patch, self.flow_size = 16, 224
         if d % self.heads != 0:
             raise ValueError(f"The hidden size ({d}) is not a multiple of the number of attention heads ({self.heads})")
@@ -235,6 +236,29 @@ class RopeBertModel(_KernelModule):
         # no text mask = all ones = a zero additive mask = none at all (the kernels treat NULL as zeros)
         cross_mask = None if encoder_attention_mask is None else \
             ops.additive_mask(encoder_attention_mask, torch.finfo(torch.float32).min)[0]
+        # The layer stack is ~17 launches per layer of a few microseconds each (M = B*(Lof+2) rows): launch-bound from
+        # Python, so a shape seen for the second time is captured and replayed as one CUDA graph.
+        have_cross_mask = cross_mask is not None
+        inputs = [x_f32, x_bf16, txt, self_mask] + ([cross_mask] if have_cross_mask else [])
+
+        def body(x_f32, x_bf16, txt, self_mask, cross_mask=None):
+            return self._run_layers(pk, lo, hi, x_f32, x_bf16, txt, self_mask, cross_mask, b, s, tq)
+
+        if b * s <= self.graph_max_tokens and self._use_graph(1):
+            x_f32, logits_all = self._graphs.run(("sampler", lo, hi, b, s, tq, have_cross_mask), inputs, body, min_seen=2)
+        else:
+            x_f32, logits_all = body(*inputs)
+        seq_out = x_f32.view(b, s, d)
+        logits = logits_all.view(b, s, 2)[:, 1:-1]
+        if not return_dict:
+            return seq_out, logits
+        return _model_output("BaseModelOutputWithPoolingAndCrossAttentions", last_hidden_state=seq_out,
+                             pooler_output=logits, past_key_values=None, hidden_states=None, attentions=None,
+                             cross_attentions=None)
+
+    def _run_layers(self, pk, lo, hi, x_f32, x_bf16, txt, self_mask, cross_mask, b, s, tq):
+        """Layers [lo, hi) + the mrc head on [B*s, 768] rows -> (sequence output f32 [B*s, 768], logits f32 [B*s, 2])."""
+        d, h, hd = self.hidden, self.heads, self.head_dim
         scale = 1.0 / math.sqrt(hd)
         for i in range(lo, hi):
             lp = pk.layers[i]
@@ -256,10 +280,4 @@ class RopeBertModel(_KernelModule):
             inter = ops.gemm(x_bf16, lp.i_w, lp.i_b, ops.EPI_BF16_GELU)
             acc = ops.gemm(inter, lp.o_w, lp.o_b, ops.EPI_F32_RESID, resid=x_f32)
             x_bf16, x_f32 = ops.layernorm(acc, lp.o_ln[0], lp.o_ln[1], self.eps, want_bf16=True, want_f32=True)
-        seq_out = x_f32.view(b, s, d)
-        logits = ops.linear_small(x_f32, pk.mrc_w, pk.mrc_b).view(b, s, 2)[:, 1:-1]
-        if not return_dict:
-            return seq_out, logits
-        return _model_output("BaseModelOutputWithPoolingAndCrossAttentions", last_hidden_state=seq_out,
-                             pooler_output=logits, past_key_values=None, hidden_states=None, attentions=None,
-                             cross_attentions=None)
+        return x_f32, ops.linear_small(x_f32, pk.mrc_w, pk.mrc_b)
