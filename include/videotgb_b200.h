@@ -143,9 +143,10 @@ TGB_API int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw
  *   TGB_EPI_BF16_LN / TGB_EPI_BF16_GELU_LN   consumer: A = bf16 copy of the un-normalised residual rows, W = W',
  *                       bias = bias', rowstats f32 [M,2] = (mean, rstd) per row, colsum f32 [N]
  *   TGB_EPI_F32_RESID_STATS                  producer: out f32 = acc + bias + resid (as TGB_EPI_F32_RESID), plus
- *                       out_bf16 [M, ldo2] = bf16(out) and partial_stats f32 [M, slots, 2] = (sum, sum of squares) of
- *                       each row over the columns of one slot; slots = tgb_gemm_ln_stats_slots(M, N) (two per 256-column tile); every slot is
- *                       written exactly once per launch (no atomics: results are run-to-run deterministic)
+ *                       out_bf16 [M, ldo2] = bf16(out) and partial_stats f32 [slots, M, 2] (slot-major) = (sum, sum of
+ *                       squares) of each row over the columns of one slot; slots = tgb_gemm_ln_stats_slots(M, N) (two per
+ *                       128-column block of N, whatever the tile width: a row's statistics do not depend on M); every slot
+ *                       is written exactly once per launch (no atomics: results are run-to-run deterministic)
  * The consumer multiplies the UN-normalised rows on the tensor cores, so its error grows with |row mean| / row std
  * (measured: 1x the separate-LayerNorm error at 0.25, 2x at 4, 4.6e-2 at 32); tgb_ln_stats_finalize can track the largest
  * ratio it sees in max_ratio (f32 scalar, zero it first; NULL = off) so that the host can fall back to tgb_layernorm_f32.

@@ -386,13 +386,13 @@ def test_gemm_ln_statistics_producer(m, n, k, cta_group, resid_piece):
     assert slots > 0 and slots % 2 == 0
     x = resid.to(DEV)
     xb = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
-    part = torch.full((m, slots, 2), float("nan"), device=DEV)
+    part = torch.full((slots, m, 2), float("nan"), device=DEV)          # slot-major
     ops.gemm_ln(a.to(DEV), w.to(DEV), bias.to(DEV), ops.EPI_F32_RESID_STATS, x, resid=x, out_bf16=xb, partial_stats=part)
     got = x.cpu()
     assert (got.double() - want).abs().max().item() < 2e-4 * want.abs().max().item()
     assert torch.equal(xb.cpu(), got.to(torch.bfloat16))      # the copy is the rounded fp32 result
     assert torch.isfinite(part).all()                          # every slot of every row written
-    ps = part.cpu().double().sum(dim=1)
+    ps = part.cpu().double().sum(dim=0)
     assert (ps[:, 0] - got.double().sum(dim=1)).abs().max().item() < 1e-3
     assert ((ps[:, 1] - (got.double() ** 2).sum(dim=1)).abs() / (got.double() ** 2).sum(dim=1)).max().item() < 1e-5
     for eps in (1e-6, 1e-12):
@@ -407,6 +407,31 @@ def test_gemm_ln_statistics_producer(m, n, k, cta_group, resid_piece):
     x2 = resid.to(DEV)
     ops.gemm_ln(a.to(DEV), w.to(DEV), bias.to(DEV), ops.EPI_F32_RESID_STATS, x2, resid=x2, out_bf16=xb, partial_stats=part2)
     assert torch.equal(part, part2)
+
+
+@pytest.mark.parametrize("n,k", [(1408, 1408), (1408, 6144), (768, 512), (136, 256)])
+def test_gemm_ln_statistics_do_not_depend_on_the_batch(n, k):
+    """The statistics slots are (128-column block, epilogue warp) pairs whatever the tile width, so a small pass (128-wide
+    tiles, chosen to spread 4 frames over more SMs) and a large pass (256-wide tiles) give the same rows bit-identical
+    outputs, bf16 copies AND partial statistics -- what keeps a frame's tokens independent of the batch it is encoded in."""
+    g = torch.Generator().manual_seed(n + k)
+    m_small, m_big = 257 * 4, 257 * 150
+    a = torch.randn(m_big, k, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) * 0.03).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    resid = (torch.randn(m_big, n, generator=g) * 2 + 0.7).to(DEV)
+    outs = []
+    for m in (m_big, m_small):
+        x = resid[:m].clone()
+        xb = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+        part = torch.full((ops.ln_stats_slots(m, n), m, 2), float("nan"), device=DEV)
+        ops.gemm_ln(a[:m], w, bias, ops.EPI_F32_RESID_STATS, x, resid=x, out_bf16=xb, partial_stats=part)
+        assert torch.isfinite(part).all()
+        stats = torch.empty(m, 2, device=DEV)
+        ops.ln_stats_finalize(part, n, 1e-6, stats)
+        outs.append((x[:m_small], xb[:m_small], part[:, :m_small], stats[:m_small]))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
 
 
 def test_rowstats_cast():
@@ -511,7 +536,7 @@ def test_gemm_schedules_agree(m):
             o_res = ops.gemm(a, w, bias, ops.EPI_F32_RESID, resid=resid)
             o_f32 = ops.gemm(a, w, bias, ops.EPI_F32)
             xb = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
-            part = torch.empty(m, ops.ln_stats_slots(m, n), 2, device=DEV)
+            part = torch.empty(ops.ln_stats_slots(m, n), m, 2, device=DEV)
             x = resid.clone()
             ops.gemm_ln(a, w, bias, ops.EPI_F32_RESID_STATS, x, resid=x, out_bf16=xb, partial_stats=part)
         finally:

@@ -34,7 +34,7 @@ def main():
         bias = torch.randn(n, device="cuda")
         out = torch.randn(m, n, device="cuda")
         xb = torch.empty(m, n, dtype=torch.bfloat16, device="cuda") if epi == ops.EPI_F32_RESID_STATS else None
-        part = torch.empty(m, ops.ln_stats_slots(m, n), 2, device="cuda") if xb is not None else None
+        part = torch.empty(ops.ln_stats_slots(m, n), m, 2, device="cuda") if xb is not None else None
         bufs[name] = (a, w, bias, out, xb, part)
 
     def runner(name, epi):

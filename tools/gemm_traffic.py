@@ -27,7 +27,7 @@ for name, m, n, k, epi in SHAPES:
     torch.cuda.synchronize()
     if epi == ops.EPI_F32_RESID_STATS:
         xb = torch.empty(m, n, dtype=torch.bfloat16, device="cuda")
-        part = torch.empty(m, ops.ln_stats_slots(m, n), 2, device="cuda")
+        part = torch.empty(ops.ln_stats_slots(m, n), m, 2, device="cuda")
         wr += m * n * 2 + part.numel() * 4
         ops.gemm_ln(a, w, bias, epi, out, resid=out, out_bf16=xb, partial_stats=part)
     elif f32:

@@ -109,12 +109,18 @@ __global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   float ratio = 0.f;                       // rows past M take part in the warp reduction with a neutral value (no early exit)
   if (row < M) {
-    const float2* pr = part + (long long)row * slots;
+    // slot-major layout [slots][M]: a warp reads 32 consecutive rows of one slot = 256 contiguous bytes per load
+    // (eleven loads in flight per thread: the kernel moves 8 * slots bytes per row and is latency-bound otherwise)
     double s = 0.0, q = 0.0;
-    for (int j = 0; j < slots; ++j) {
-      const float2 v = pr[j];
-      s += static_cast<double>(v.x);
-      q += static_cast<double>(v.y);
+    for (int j0 = 0; j0 < slots; j0 += 11) {
+      float2 v[11];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) v[k] = j0 + k < slots ? __ldg(part + (long long)(j0 + k) * M + row) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {          // slots past the end add +0.0: the sums are unchanged
+        s += static_cast<double>(v[k].x);
+        q += static_cast<double>(v[k].y);
+      }
     }
     const double mean = s / N;
     double var = q / N - mean * mean;
@@ -124,9 +130,18 @@ __global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __
     ratio = fabsf(static_cast<float>(mean)) * rstd;
   }
   if (max_ratio != nullptr) {
+    // one atomic per CTA: thousands of same-address atomics serialise in the L2 and were the kernel's floor
+    __shared__ float wmax[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
-    if ((threadIdx.x & 31) == 0 && ratio > 0.f) atomicMax(reinterpret_cast<int*>(max_ratio), __float_as_int(ratio));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = ratio;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float r = wmax[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) r = fmaxf(r, wmax[w]);
+      if (r > 0.f) atomicMax(reinterpret_cast<int*>(max_ratio), __float_as_int(r));
+    }
   }
 }
 

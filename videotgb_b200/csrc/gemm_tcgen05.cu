@@ -488,6 +488,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const int row_base = piece_rows(tile);
         const int col = piece_col(tile, j);
         if (j == sub) {                              // first piece of a tile: the accumulator must be complete
+          if (T::STATS && sub > 0 && (p.N & 127)) {
+            // the partial last 128-column block of N may hold fewer pieces than there are warps per lane quarter: the slot
+            // this warp never reaches is defined as empty (a later real flush by the same thread would overwrite it)
+            const int tail0 = p.N & ~127;
+            const int tile_col0 = col - j * PW;
+            if (tail0 >= tile_col0 && tail0 < tile_col0 + BN && p.N - tail0 <= sub * PW && row_base + lane < p.M)
+              p.pstats[(long long)((tail0 >> 7) * NSUB + sub) * p.M + row_base + lane] = make_float2(0.f, 0.f);
+          }
           mbar_wait_parked(&tmem_full[acc], acc_phase);
           tc_fence_after();
         }
@@ -547,14 +555,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           if (T::STATS) tma_store_2d(&tma_c2, wbase + RES_NBOX * RES_BOX_BYTES + (n & 1) * RES_COPY_BYTES, col, row_base);
         }
         if (lane == 0) bulk_commit();
-        if (tile_done) {
-          if (T::STATS) {
-            if (row_base + lane < p.M)
-              p.pstats[(long long)(row_base + lane) * p.nslots + (tile % p.num_n_blocks) * NSUB + sub] =
+        if (T::STATS) {
+          // One (sum, sum of squares) slot per (128-column block of N, warp of the lane quarter), written when this warp's
+          // walk leaves the block.  The partition does not depend on the tile width, so 256- and 128-wide tiles -- large
+          // and small passes -- produce bit-identical statistics.
+          if (tile_done || (piece_col(ntile, nj) >> 7) != (col >> 7)) {
+            if (row_base + lane < p.M && col < p.N)
+              p.pstats[(long long)((col >> 7) * NSUB + sub) * p.M + row_base + lane] =      // slot-major: 32 rows = 256 B
                   make_float2(ssum.x + ssum.y, ssq.x + ssq.y);
             ssum = make_float2(0.f, 0.f);
             ssq = make_float2(0.f, 0.f);
           }
+        }
+        if (tile_done) {
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         round = nround;
@@ -682,7 +695,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 2);
           ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 2);
           if ((lane & 3) == 0 && rok[i])
-            p.pstats[(long long)(row_base + i * 8 + trow) * p.nslots + n_blk * NSUB + sub] = make_float2(ssum[i], ssq[i]);
+            p.pstats[(long long)(n_blk * NSUB + sub) * p.M + row_base + i * 8 + trow] = make_float2(ssum[i], ssq[i]);
         }
       }
       tc_fence_before();
@@ -958,7 +971,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
     // wide residual pieces (whole 128-byte lines) for short main loops, where the epilogue traffic sets the time
     const int force_pw = g_force_resid_piece.load();
     const int pw = force_pw ? force_pw : (p.K <= 2048 ? 32 : 16);
-    if constexpr (BN == 256) {
+    if constexpr (BN >= 128) {       // the piece width must not depend on the tile width: it decides which columns a slot sums
       if (pw == 32) return launch_gemm_ew<BN, EPI, CG, 8, 32>(A, lda, W, ldw, p, stream);
     }
     return launch_gemm_ew<BN, EPI, CG, 8, 16>(A, lda, W, ldw, p, stream);
@@ -1003,7 +1016,7 @@ static int dispatch_bn(int bn, const void* A, long long lda, const void* W, long
 // narrow tile only pays when it saves whole waves; single-CTA 128-row tiles cost 5-10 % more per wave than CTA pairs and win
 // exactly when they need fewer waves (M = 2056: 2 instead of 3).  The choice never changes a result: every output
 // element accumulates over K in the same order whatever the tile.
-static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
+static void choose_tile(int M, int N, int* bn_out, int* cg_out, int min_bn = 64) {
   // measured on B200: a tcgen05.mma with N=176 costs as much as N=256 (N is processed in 128-wide passes), so the
   // tiles are 256 / 128 / 64 wide; prefer 256, then 128.
   const int cands[4] = {256, 128, 64, 64};
@@ -1015,6 +1028,7 @@ static void choose_tile(int M, int N, int* bn_out, int* cg_out) {
     const long long mblocks = (M + BM * cg - 1) / (BM * cg);
     for (int i = 0; i < 4; ++i) {
       const int bn = cands[i];
+      if (bn < min_bn) continue;
       const long long nblocks = (N + bn - 1) / bn;
       const long long tiles = nblocks * mblocks;
       const long long slots = sm_count() / cg;
@@ -1095,11 +1109,12 @@ static int gemm_entry(const void* A, int64_t lda, const void* W, int64_t ldw, in
                       ((uintptr_t)partial_stats % 8) == 0,
                   "gemm: the statistics epilogue needs out_bf16 (ld %% 8 == 0) and partial_stats");
   int auto_bn, cg;
-  choose_tile(M, N, &auto_bn, &cg);
+  // the statistics slots are (128-column block of N, epilogue warp) pairs whatever the tile: that partition -- and with it
+  // a row's statistics and the whole encoder -- is bit-identical whatever batch the row is encoded in, and a small pass may
+  // still take 128-wide tiles to spread over more SMs (64-wide ones would split a slot's pieces between tiles)
+  choose_tile(M, N, &auto_bn, &cg, epilogue == TGB_EPI_F32_RESID_STATS ? 128 : 64);
   if (bn == 0) bn = auto_bn;
-  // the statistics slots are (256-column tile, epilogue warp) pairs: keeping that partition independent of M keeps a
-  // row's statistics -- and with them the whole encoder -- bit-identical whatever batch the row is encoded in
-  if (epilogue == TGB_EPI_F32_RESID_STATS) bn = 256;
+  if (epilogue == TGB_EPI_F32_RESID_STATS && bn < 128) bn = 128;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.epi = epilogue;
   p.num_m_blocks = p.num_n_blocks = p.num_k_blocks = 0;
@@ -1107,7 +1122,7 @@ static int gemm_entry(const void* A, int64_t lda, const void* W, int64_t ldw, in
   p.bias = bias; p.resid = resid; p.rowbias = rowbias; p.out = out; p.ldo = ldo; p.ldr = ldr;
   p.rowstats = rowstats; p.colsum = colsum; p.out2 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo2 = ldo2;
   p.pstats = reinterpret_cast<float2*>(partial_stats);
-  p.nslots = ((N + bn - 1) / bn) * 2;
+  p.nslots = ((N + 127) / 128) * 2;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (cg == 2) return dispatch_bn<2>(bn, A, lda, W, ldw, p, s);
   return dispatch_bn<1>(bn, A, lda, W, ldw, p, s);
@@ -1126,7 +1141,7 @@ extern "C" int tgb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
 
 extern "C" int tgb_gemm_ln_stats_slots(int M, int N) {
   if (M <= 0 || N <= 0) return 0;
-  return ((N + 255) / 256) * 2;
+  return ((N + 127) / 128) * 2;
 }
 
 extern "C" int tgb_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epilogue,

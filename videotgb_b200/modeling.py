@@ -312,7 +312,7 @@ class Blip2VisionModel(_KernelModule):
             # the residual GEMMs emit that copy plus per-row partial (sum, sum of squares), a tiny kernel turns them into
             # (mean, rstd), and the qkv / fc1 GEMMs apply rstd * (acc - mean * colsum) + bias'
             stats = torch.empty((m, 2), dtype=torch.float32, device=dev)
-            part = torch.empty((m, ops.ln_stats_slots(m, d), 2), dtype=torch.float32, device=dev)
+            part = torch.empty((ops.ln_stats_slots(m, d), m, 2), dtype=torch.float32, device=dev)      # slot-major
             ops.rowstats_cast(x, self.eps, ln, stats)
             for lw in pk.layers:
                 ops.gemm_ln(ln, lw.qkv_w, lw.qkv_b, ops.EPI_BF16_LN, qkv, rowstats=stats, colsum=lw.qkv_c1)

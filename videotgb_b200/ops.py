@@ -280,7 +280,7 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epilogue: int,
             partial_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The LayerNorm-fold GEMMs (include/videotgb_b200.h, tgb_gemm_bf16_ln).
     EPI_BF16_LN / EPI_BF16_GELU_LN: out bf16 = act(rstd_m * (a @ w.T - mean_m * colsum) + bias), rowstats f32 [M,2].
-    EPI_F32_RESID_STATS: out f32 = a @ w.T + bias + resid, out_bf16 = bf16(out), partial_stats f32 [M, slots, 2]."""
+    EPI_F32_RESID_STATS: out f32 = a @ w.T + bias + resid, out_bf16 = bf16(out), partial_stats f32 [slots, M, 2] (slot-major)."""
     _need(a, torch.bfloat16, "a", contiguous=False)
     _need(w, torch.bfloat16, "w", contiguous=False)
     m, k, lda = _rows(a, "a")
@@ -325,13 +325,13 @@ def ln_stats_slots(m: int, n: int) -> int:
 
 def ln_stats_finalize(partial_stats: torch.Tensor, n: int, eps: float, rowstats: torch.Tensor,
                       max_ratio: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """partial_stats f32 [M, slots, 2] (sum, sum of squares) -> rowstats f32 [M, 2] (mean, rstd).
+    """partial_stats f32 [slots, M, 2] (sum, sum of squares; slot-major) -> rowstats f32 [M, 2] (mean, rstd).
     max_ratio: optional f32 scalar tensor that accumulates max |mean| * rstd over the rows (zero it first)."""
     _need(partial_stats, torch.float32, "partial_stats")
     _need(rowstats, torch.float32, "rowstats")
-    m, slots, two = partial_stats.shape
+    slots, m, two = partial_stats.shape
     if two != 2 or rowstats.shape != (m, 2):
-        raise _lib.TgbError("ln_stats_finalize: partial_stats must be [M, slots, 2] and rowstats [M, 2]")
+        raise _lib.TgbError("ln_stats_finalize: partial_stats must be [slots, M, 2] and rowstats [M, 2]")
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
