@@ -158,13 +158,17 @@ class _GraphCache:
                 body(*static_in)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
             with torch.cuda.graph(graph):
                 static_out = body(*static_in)
-            ent = self.entries[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = ent
+            kernels = ops.LAUNCHES - n0                        # recorded, not launched: counted at every replay instead
+            ops.LAUNCHES = n0
+            ent = self.entries[key] = (graph, static_in, static_out, kernels)
+        graph, static_in, static_out, kernels = ent
         for dst, src in zip(static_in, inputs):
             dst.copy_(src)
         graph.replay()
+        ops.LAUNCHES += kernels
         return tuple(t.clone() for t in static_out)
 
 
