@@ -90,3 +90,55 @@ def test_row_block_schedule_covers_every_tile_once_and_keeps_row_blocks_private(
     _, bal = _walk(clusters, nb, mb, best)
     rows = [(7 if c < mb - 6 * clusters else 6) * (nb - 1 + 0.65) for c in range(clusters)]
     assert abs(max(rows) - max(bal)) < 1e-6 * max(bal) + 0.7      # within one half tile of the searched schedule
+
+
+def test_group_schedule_covers_every_tile_once_and_keeps_the_sharers_together():
+    """Group mode of tile_at (csrc/gemm_tcgen05.cu, sched_shift == -2; A/B knob tgb_gemm_set_schedule(3)): the grid is
+    C = (clusters // NB) * NB clusters, round r of cluster c is the tile r*C + NB*(c // NB) + (c % NB + r) % NB.  Every tile
+    is computed exactly once, the NB clusters of a group always share one A row block, and every cluster meets the cheap
+    last N tile once every NB rounds."""
+    for clusters, nb, mb in [(74, 6, 514), (74, 17, 514), (74, 11, 514), (9, 3, 10)]:
+        used = clusters // nb * nb
+        tiles = nb * mb
+        seen = [0] * tiles
+        last = [0] * used
+        rounds = [0] * used
+        for c in range(used):
+            r = 0
+            while True:
+                t = r * used + nb * (c // nb) + (c % nb + r) % nb
+                if t >= tiles:
+                    break
+                seen[t] += 1
+                assert t // nb == r * (used // nb) + c // nb           # the group's row block of this round
+                last[c] += t % nb == nb - 1
+                rounds[c] += 1
+                r += 1
+        assert all(v == 1 for v in seen), (clusters, nb, mb)
+        assert all(abs(l - r / nb) <= 1 for l, r in zip(last, rounds))
+
+
+def _slot_columns(n, bn, pw):
+    """Columns summed into every statistics slot by the fp32-residual epilogue with tile width `bn` and piece width `pw`
+    (csrc/gemm_tcgen05.cu): warp `sub` of a lane quarter walks the pieces sub, sub + 2, ... of a tile, a slot is
+    (128-column block of N, sub), flushed when the walk leaves the block.  Returns {slot: [columns in summation order]}."""
+    slots = {}
+    for col0 in range(0, n, bn):
+        for sub in range(2):
+            j = sub
+            while j < bn // pw and col0 + j * pw < n:
+                col = col0 + j * pw
+                slots.setdefault(((col >> 7), sub), []).extend(c for c in range(col, col + pw) if c < n)
+                j += 2
+    return slots
+
+
+def test_statistics_slots_do_not_depend_on_the_tile_width():
+    """The LayerNorm-fold statistics are batch-invariant because the columns a slot sums, and their order, depend on N and
+    the piece width only -- not on whether a pass took 256- or 128-wide tiles."""
+    for n in (1408, 768, 1024, 136, 272):
+        for pw in (16, 32):
+            wide, narrow = _slot_columns(n, 256, pw), _slot_columns(n, 128, pw)
+            assert wide == narrow, (n, pw)
+            assert sorted(c for cols in wide.values() for c in cols) == list(range(n))      # every column exactly once
+            assert len(wide) <= ((n + 127) // 128) * 2                                      # tgb_gemm_ln_stats_slots
