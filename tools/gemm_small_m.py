@@ -33,19 +33,26 @@ def graph_time(fn, iters=20, replays=5):
 def main():
     for frames in (4, 8, 16, 32, 64):
         m = 257 * frames
-        for name, n, k, epi in (("qkv", 4224, 1408, ops.EPI_BF16), ("fc1", 6144, 1408, ops.EPI_BF16_GELU)):
+        shapes = (("qkv", 4224, 1408, ops.EPI_BF16), ("fc1", 6144, 1408, ops.EPI_BF16_GELU))
+        if os.environ.get("TGB_SMALL_M_RESID"):      # the residual GEMMs (the statistics variants share their tiles and schedule)
+            shapes = (("proj", 1408, 1408, ops.EPI_F32_RESID), ("fc2", 1408, 6144, ops.EPI_F32_RESID))
+        for name, n, k, epi in shapes:
             a = torch.randn(m, k, device="cuda").to(torch.bfloat16)
             # several weight copies, cycled, so that every launch streams its weights from DRAM like a real layer stack does
             ws = [(torch.randn(n, k, device="cuda") * 0.05).to(torch.bfloat16) for _ in range(10)]
             bias = torch.randn(n, device="cuda")
-            out = torch.empty(m, n, dtype=torch.bfloat16, device="cuda")
+            resid = epi == ops.EPI_F32_RESID
+            out = torch.randn(m, n, device="cuda") if resid else torch.empty(m, n, dtype=torch.bfloat16, device="cuda")
             line = f"M={m:6d} {name}:"
             state = {"i": 0}
 
             def run(bn):
                 w = ws[state["i"] % len(ws)]
                 state["i"] += 1
-                ops.gemm(a, w, bias, epi, out=out, bn=bn)
+                if resid:
+                    ops.gemm(a, w, bias, epi, out=out, resid=out, bn=bn)
+                else:
+                    ops.gemm(a, w, bias, epi, out=out, bn=bn)
 
             for cg in (2, 1):
                 ops.gemm_set_cta_group(cg)
