@@ -967,7 +967,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
   // warps and the extra pipeline stage than with 16)
   const int force_ew = g_force_ew.load();
   int ew = force_ew ? force_ew : 8;
-  if constexpr (EpiTraits<EPI>::RESID) {       // 8 epilogue warps: the statistics slot layout (2 per 256-column tile) is fixed
+  if constexpr (EpiTraits<EPI>::RESID) {       // 8 epilogue warps: the statistics slot layout (2 per 128-column block of N) is fixed
     // wide residual pieces (whole 128-byte lines) for short main loops, where the epilogue traffic sets the time
     const int force_pw = g_force_resid_piece.load();
     const int pw = force_pw ? force_pw : (p.K <= 2048 ? 32 : 16);
